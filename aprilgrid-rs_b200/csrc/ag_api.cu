@@ -1,0 +1,814 @@
+// C ABI of the aprilgrid B200 library: handle, workspaces, chunked multi-stream pipeline.
+// See include/aprilgrid_b200.h for the contract of every entry point.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "ag_codebook.h"
+#include "ag_common.cuh"
+#include "ag_kernels.h"
+
+using namespace ag;
+
+namespace {
+
+struct FamilyInfo {
+  int edge, border, hamming, n_codes;
+  const uint64_t* codes;
+};
+
+bool family_info(int family, FamilyInfo* f) {  // src/detector.rs:369-405
+  switch (family) {
+    case AG_T16H5: *f = {4, 2, 1, ag_t16h5_count, ag_t16h5_codes}; return true;
+    case AG_T25H7: *f = {5, 2, 2, ag_t25h7_count, ag_t25h7_codes}; return true;
+    case AG_T25H9: *f = {5, 2, 2, ag_t25h9_count, ag_t25h9_codes}; return true;
+    case AG_T36H11: *f = {6, 2, 3, ag_t36h11_count, ag_t36h11_codes}; return true;
+    case AG_T36H11B1: *f = {6, 1, 3, ag_t36h11_count, ag_t36h11_codes}; return true;
+  }
+  return false;
+}
+
+std::string g_create_error;
+
+// Device buffers of one pipeline slot (one chunk in flight).
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  int cap_frames = 0;
+  size_t cap_px = 0, cap_words = 0, cap_in_bytes = 0;
+  int cap_clusters = 0, cap_saddles = 0, cap_tags = 0;
+  uint8_t* d_in = nullptr;
+  float *d_blur = nullptr, *d_resp = nullptr;
+  uint32_t *d_min = nullptr, *d_mask = nullptr, *d_status = nullptr;
+  int *d_parent = nullptr, *d_acc = nullptr, *d_ncl = nullptr, *d_nref = nullptr, *d_ntags = nullptr;
+  float2* d_centers = nullptr;
+  ag_saddle *d_raw = nullptr, *d_refined = nullptr;
+  uint8_t *d_raw_valid = nullptr, *d_board_ws = nullptr;
+  ag_tag* d_tags = nullptr;
+  // pinned result staging
+  ag_tag* h_tags = nullptr;
+  int* h_ntags = nullptr;
+  uint32_t* h_status = nullptr;
+  // taps
+  int32_t* d_tap_quads = nullptr;
+  int* d_tap_nquads = nullptr;
+  BoardWsLayout layout{};
+};
+
+}  // namespace
+
+struct ag_detector {
+  int device = 0;
+  int family = AG_T36H11;
+  FamilyInfo fam{};
+  ag_params params{};
+  std::mutex mu;
+  std::string err;
+  Slot slot[2];
+  uint64_t launches = 0;
+  long chunk_frames = 32;
+  long max_clusters = 16384;
+  long max_saddles = 2048;
+  uint64_t* d_codes = nullptr;  // family table in global memory (renderer)
+  // stage-tap state
+  FrameGeom tap_geom{};
+  bool tap_valid = false;
+  // scratch for the standalone operators
+  float *d_f32_a = nullptr, *d_f32_b = nullptr, *d_f32_c = nullptr, *d_taps = nullptr;
+  size_t f32_cap = 0;
+};
+
+namespace {
+
+#define AG_CUDA(det, call)                                                                   \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      char b__[512];                                                                         \
+      snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),     \
+               __FILE__, __LINE__);                                                          \
+      (det)->err = b__;                                                                      \
+      return AG_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+int fail(ag_detector* det, int code, const char* msg) {
+  if (det) det->err = msg;
+  return code;
+}
+
+int bytes_per_px(int format) { return format == AG_L8 ? 1 : (format == AG_L16 ? 2 : 3); }
+
+int make_geom(ag_detector* det, int w, int h, size_t row_stride, size_t frame_stride, int format,
+              FrameGeom* g) {
+  if (w <= 0 || h <= 0) return fail(det, AG_ERR_INVALID, "width/height must be positive");
+  if (format != AG_L8 && format != AG_L16 && format != AG_RGB8)
+    return fail(det, AG_ERR_INVALID, "unknown pixel format");
+  if ((long long)w * h > (1ll << 30)) return fail(det, AG_ERR_INVALID, "image too large");
+  size_t min_row = (size_t)w * bytes_per_px(format);
+  if (row_stride == 0) row_stride = min_row;
+  if (row_stride < min_row) return fail(det, AG_ERR_INVALID, "row_stride smaller than a row");
+  if (format == AG_L16 && (row_stride & 1)) return fail(det, AG_ERR_INVALID, "L16 row_stride must be even");
+  if (frame_stride == 0) frame_stride = row_stride * h;
+  if (frame_stride < row_stride * (size_t)(h - 1) + min_row)
+    return fail(det, AG_ERR_INVALID, "frame_stride smaller than a frame");
+  g->w = w;
+  g->h = h;
+  g->wpr = (w + 31) / 32;
+  g->n_words = g->wpr * h;
+  g->n_px = w * h;
+  g->row_stride = row_stride;
+  g->frame_stride = frame_stride;
+  g->format = format;
+  return AG_OK;
+}
+
+template <typename T>
+int regrow(ag_detector* det, T** p, size_t count) {
+  if (*p) AG_CUDA(det, cudaFree(*p));
+  *p = nullptr;
+  if (count == 0) count = 1;
+  AG_CUDA(det, cudaMalloc((void**)p, count * sizeof(T)));
+  return AG_OK;
+}
+
+// Make sure a slot can hold `frames` frames of geometry g with `cap_tags` tags per frame.
+int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int cap_tags,
+                bool need_input) {
+  int rc;
+  if (!S.stream) {
+    AG_CUDA(det, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    AG_CUDA(det, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+  }
+  const bool grow_frames = frames > S.cap_frames;
+  const int F = std::max(frames, S.cap_frames);
+  const size_t px = std::max((size_t)g.n_px, S.cap_px);
+  const size_t words = std::max((size_t)g.n_words, S.cap_words);
+  if (grow_frames || px > S.cap_px || words > S.cap_words) {
+    // make sure nothing is in flight on the buffers we are about to free
+    AG_CUDA(det, cudaStreamSynchronize(S.stream));
+    if ((rc = regrow(det, &S.d_blur, (size_t)F * px))) return rc;
+    if ((rc = regrow(det, &S.d_resp, (size_t)F * px))) return rc;
+    if ((rc = regrow(det, &S.d_parent, (size_t)F * px))) return rc;
+    if ((rc = regrow(det, &S.d_mask, (size_t)F * words))) return rc;
+    S.cap_px = px;
+    S.cap_words = words;
+  }
+  const int ncl = (int)det->max_clusters, nsd = (int)det->max_saddles;
+  if (grow_frames || ncl != S.cap_clusters || nsd != S.cap_saddles) {
+    AG_CUDA(det, cudaStreamSynchronize(S.stream));
+    if ((rc = regrow(det, &S.d_min, (size_t)F))) return rc;
+    if ((rc = regrow(det, &S.d_status, (size_t)F))) return rc;
+    if ((rc = regrow(det, &S.d_ncl, (size_t)F))) return rc;
+    if ((rc = regrow(det, &S.d_nref, (size_t)F))) return rc;
+    if ((rc = regrow(det, &S.d_ntags, (size_t)F))) return rc;
+    if ((rc = regrow(det, &S.d_acc, (size_t)F * ncl * 3))) return rc;
+    if ((rc = regrow(det, &S.d_centers, (size_t)F * ncl))) return rc;
+    if ((rc = regrow(det, &S.d_raw, (size_t)F * ncl))) return rc;
+    if ((rc = regrow(det, &S.d_raw_valid, (size_t)F * ncl))) return rc;
+    if ((rc = regrow(det, &S.d_refined, (size_t)F * nsd))) return rc;
+    S.layout = make_board_layout(nsd);
+    if ((rc = regrow(det, &S.d_board_ws, (size_t)F * S.layout.bytes_per_frame))) return rc;
+    if ((rc = regrow(det, &S.d_tap_quads, (size_t)F * S.layout.max_quads * 4))) return rc;
+    if ((rc = regrow(det, &S.d_tap_nquads, (size_t)F))) return rc;
+    if (S.h_ntags) cudaFreeHost(S.h_ntags);
+    if (S.h_status) cudaFreeHost(S.h_status);
+    AG_CUDA(det, cudaMallocHost((void**)&S.h_ntags, sizeof(int) * F));
+    AG_CUDA(det, cudaMallocHost((void**)&S.h_status, sizeof(uint32_t) * F));
+    S.cap_clusters = ncl;
+    S.cap_saddles = nsd;
+  }
+  if (grow_frames || cap_tags > S.cap_tags) {
+    AG_CUDA(det, cudaStreamSynchronize(S.stream));
+    const int ct = std::max(cap_tags, S.cap_tags);
+    if ((rc = regrow(det, &S.d_tags, (size_t)F * ct))) return rc;
+    if (S.h_tags) cudaFreeHost(S.h_tags);
+    AG_CUDA(det, cudaMallocHost((void**)&S.h_tags, sizeof(ag_tag) * (size_t)F * ct));
+    S.cap_tags = ct;
+  }
+  if (need_input) {
+    const size_t in_bytes = (size_t)F * g.frame_stride;
+    if (in_bytes > S.cap_in_bytes) {
+      AG_CUDA(det, cudaStreamSynchronize(S.stream));
+      if ((rc = regrow(det, &S.d_in, in_bytes))) return rc;
+      S.cap_in_bytes = in_bytes;
+    }
+  }
+  S.cap_frames = F;
+  return AG_OK;
+}
+
+void free_slot(Slot& S) {
+  cudaFree(S.d_in); cudaFree(S.d_blur); cudaFree(S.d_resp); cudaFree(S.d_min); cudaFree(S.d_mask);
+  cudaFree(S.d_status); cudaFree(S.d_parent); cudaFree(S.d_acc); cudaFree(S.d_ncl);
+  cudaFree(S.d_nref); cudaFree(S.d_ntags); cudaFree(S.d_centers); cudaFree(S.d_raw);
+  cudaFree(S.d_refined); cudaFree(S.d_raw_valid); cudaFree(S.d_board_ws); cudaFree(S.d_tags);
+  cudaFree(S.d_tap_quads); cudaFree(S.d_tap_nquads);
+  if (S.h_tags) cudaFreeHost(S.h_tags);
+  if (S.h_ntags) cudaFreeHost(S.h_ntags);
+  if (S.h_status) cudaFreeHost(S.h_status);
+  if (S.done) cudaEventDestroy(S.done);
+  if (S.stream) cudaStreamDestroy(S.stream);
+  S = Slot();
+}
+
+// Dense front end of one chunk on stream s: K1 + K2.
+int run_dense(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
+              bool write_blur, cudaStream_t s) {
+  det->launches += launch_blur_hessian(d_frames, g, n, S.d_blur, S.d_resp, S.d_min, write_blur, 0, s);
+  det->launches += launch_threshold(S.d_resp, g, n, S.d_min, S.d_mask, s);
+  AG_CUDA(det, cudaGetLastError());
+  return AG_OK;
+}
+
+// Sparse stages up to the refined saddle list.
+int run_sparse(ag_detector* det, Slot& S, const FrameGeom& g, int n, uint32_t* d_status,
+               cudaStream_t s) {
+  AG_CUDA(det, cudaMemsetAsync(d_status, 0, sizeof(uint32_t) * n, s));
+  det->launches += launch_label_clusters(S.d_mask, g, n, S.d_parent, S.cap_clusters, S.d_acc,
+                                         S.d_centers, S.d_ncl, d_status, s);
+  det->launches += launch_refine_filter(S.d_blur, g, n, S.d_centers, S.d_ncl, S.cap_clusters, S.d_raw,
+                                        S.d_raw_valid, det->params.min_saddle_angle,
+                                        det->params.max_saddle_angle, S.cap_saddles, S.d_refined,
+                                        S.d_nref, d_status, s);
+  AG_CUDA(det, cudaGetLastError());
+  return AG_OK;
+}
+
+int run_boards(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
+               ag_tag* d_tags, int cap, int* d_ntags, uint32_t* d_status, bool taps,
+               cudaStream_t s) {
+  det->launches += launch_boards_decode(
+      d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, S.layout, det->fam.n_codes, det->fam.edge,
+      det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
+      d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout.max_quads,
+      s);
+  AG_CUDA(det, cudaGetLastError());
+  return AG_OK;
+}
+
+int run_chunk(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
+              ag_tag* d_tags, int cap, int* d_ntags, uint32_t* d_status, bool taps,
+              cudaStream_t s) {
+  int rc;
+  if ((rc = run_dense(det, S, d_frames, g, n, true, s))) return rc;
+  if ((rc = run_sparse(det, S, g, n, d_status, s))) return rc;
+  return run_boards(det, S, d_frames, g, n, d_tags, cap, d_ntags, d_status, taps, s);
+}
+
+void rochade_tables_host(float cone[25], float pinv[150]) {
+  // cone kernel, src/detector.rs:240-254 (half_size_patch = 2)
+  const float gamma = 2.0f;
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 5; ++j) {
+      volatile float a = (gamma - (float)i) * (gamma - (float)i);
+      volatile float b = (gamma - (float)j) * (gamma - (float)j);
+      volatile float s = a + b;
+      float v = gamma + 1.0f - sqrtf(s);
+      cone[i * 5 + j] = v > 0.0f ? v : 0.0f;
+    }
+  volatile float sum = 0.0f;
+  for (int i = 0; i < 25; ++i) sum = sum + cone[i];
+  for (int i = 0; i < 25; ++i) cone[i] = cone[i] / sum;
+  // Pseudo-inverse of the 25x6 design matrix [x^2, xy, y^2, x, y, 1], x, y in -2..2
+  // (src/detector.rs:208-237 obtains it with an f32 QR).  On the symmetric grid the normal
+  // equations decouple: with S2 = sum x^2 = 10, S4 = sum x^4 = 34 per axis and N = 5,
+  //   a_xx = (x^2 - S2/N) / (N S4 - S2^2)            = (x^2 - 2) / 70
+  //   a_xy = x y / S2^2                              = x y / 100
+  //   a_x  = x / (N S2)                              = x / 50
+  //   a_1  = (1 - N S2 (a_xx + a_yy)) / N^2          = (27 - 5 (x^2 + y^2)) / 175
+  int idx = 0;
+  for (int r = 0; r < 5; ++r)
+    for (int c = 0; c < 5; ++c, ++idx) {
+      const double x = c - 2, y = r - 2;
+      const double p1 = (x * x - 2.0) / 70.0, p3 = (y * y - 2.0) / 70.0;
+      pinv[0 * 25 + idx] = (float)p1;
+      pinv[1 * 25 + idx] = (float)(x * y / 100.0);
+      pinv[2 * 25 + idx] = (float)p3;
+      pinv[3 * 25 + idx] = (float)(x / 50.0);
+      pinv[4 * 25 + idx] = (float)(y / 50.0);
+      pinv[5 * 25 + idx] = (float)((1.0 - 50.0 * (p1 + p3)) / 25.0);
+    }
+}
+
+// Sort-free host copy-out of one chunk's results.
+void copy_out(const Slot& S, int n, int cap, int slot_cap, ag_tag* out, int* n_per_frame,
+              uint32_t* frame_status, int frame0, bool* truncated) {
+  for (int i = 0; i < n; ++i) {
+    int cnt = S.h_ntags[i];
+    n_per_frame[frame0 + i] = cnt;
+    if (cnt > cap) *truncated = true;
+    int m = std::min(cnt, cap);
+    memcpy(out + (size_t)(frame0 + i) * cap, S.h_tags + (size_t)i * slot_cap, sizeof(ag_tag) * m);
+    if (frame_status) frame_status[frame0 + i] = S.h_status[i];
+  }
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char* ag_version(void) { return "aprilgrid-b200 0.1.0 (sm_100a)"; }
+
+void ag_default_params(ag_params* out) {
+  if (!out) return;
+  out->tag_spacing_ratio = 0.3f;
+  out->min_saddle_angle = 30.0f;
+  out->max_saddle_angle = 60.0f;
+  out->max_num_of_boards = 2;
+}
+
+int ag_family_from_str(const char* name, int* family_out) {
+  if (!name || !family_out) return AG_ERR_INVALID;
+  static const struct { const char* n; int f; } tab[] = {
+      {"t16h5", AG_T16H5},   {"T16H5", AG_T16H5},   {"t25h7", AG_T25H7},      {"T25H7", AG_T25H7},
+      {"t25h9", AG_T25H9},   {"T25H9", AG_T25H9},   {"t36h11", AG_T36H11},    {"T36H11", AG_T36H11},
+      {"t36h11b1", AG_T36H11B1}, {"T36H11B1", AG_T36H11B1}};
+  for (auto& e : tab)
+    if (strcmp(name, e.n) == 0) {
+      *family_out = e.f;
+      return AG_OK;
+    }
+  return AG_ERR_INVALID;
+}
+
+int ag_family_info(int family, int* edge, int* border, int* hamming, int* n_codes,
+                   const uint64_t** codes) {
+  FamilyInfo f;
+  if (!family_info(family, &f)) return AG_ERR_INVALID;
+  if (edge) *edge = f.edge;
+  if (border) *border = f.border;
+  if (hamming) *hamming = f.hamming;
+  if (n_codes) *n_codes = f.n_codes;
+  if (codes) *codes = f.codes;
+  return AG_OK;
+}
+
+const char* ag_last_error(const ag_detector* det) {
+  return det ? det->err.c_str() : g_create_error.c_str();
+}
+
+int ag_create(int family, const ag_params* params, int device, ag_detector** out) {
+  if (!out) return AG_ERR_INVALID;
+  *out = nullptr;
+  FamilyInfo fam;
+  if (!family_info(family, &fam)) {
+    g_create_error = "unknown tag family";
+    return AG_ERR_INVALID;
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                     " (this library has no CPU path)";
+    return AG_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n_dev) {
+    g_create_error = "device ordinal out of range";
+    return AG_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    g_create_error = "device is not an sm_100 (Blackwell B200) part; kernels are built for sm_100a only";
+    return AG_ERR_NO_DEVICE;
+  }
+  ag_detector* det = new ag_detector();
+  det->device = device;
+  det->family = family;
+  det->fam = fam;
+  if (params) det->params = *params;
+  else ag_default_params(&det->params);
+  if (cudaSetDevice(device) != cudaSuccess) {
+    g_create_error = "cudaSetDevice failed";
+    delete det;
+    return AG_ERR_CUDA;
+  }
+  float cone[25], pinv[150];
+  rochade_tables_host(cone, pinv);
+  if (upload_rochade_tables(cone, pinv) != 0 || upload_codes(fam.codes, fam.n_codes) != 0 ||
+      cudaMalloc((void**)&det->d_codes, sizeof(uint64_t) * fam.n_codes) != cudaSuccess ||
+      cudaMemcpy(det->d_codes, fam.codes, sizeof(uint64_t) * fam.n_codes, cudaMemcpyHostToDevice) !=
+          cudaSuccess) {
+    g_create_error = std::string("table upload failed: ") + cudaGetErrorString(cudaGetLastError());
+    delete det;
+    return AG_ERR_CUDA;
+  }
+  *out = det;
+  return AG_OK;
+}
+
+void ag_destroy(ag_detector* det) {
+  if (!det) return;
+  cudaSetDevice(det->device);
+  cudaDeviceSynchronize();
+  free_slot(det->slot[0]);
+  free_slot(det->slot[1]);
+  cudaFree(det->d_codes);
+  cudaFree(det->d_f32_a); cudaFree(det->d_f32_b); cudaFree(det->d_f32_c); cudaFree(det->d_taps);
+  delete det;
+}
+
+int ag_set_option(ag_detector* det, const char* key, long value) {
+  if (!det || !key) return AG_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(det->mu);
+  if (!strcmp(key, "chunk_frames")) {
+    if (value < 1 || value > 65535) return fail(det, AG_ERR_INVALID, "chunk_frames out of range");
+    det->chunk_frames = value;
+  } else if (!strcmp(key, "max_clusters")) {
+    if (value < 16 || value > (1 << 22)) return fail(det, AG_ERR_INVALID, "max_clusters out of range");
+    det->max_clusters = value;
+  } else if (!strcmp(key, "max_saddles")) {
+    if (value < 16 || value > 16384) return fail(det, AG_ERR_INVALID, "max_saddles out of range");
+    det->max_saddles = value;
+  } else {
+    return fail(det, AG_ERR_INVALID, "unknown option");
+  }
+  return AG_OK;
+}
+
+uint64_t ag_launch_count(const ag_detector* det) { return det ? det->launches : 0; }
+
+int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_stride, int n_frames,
+                           int width, int height, size_t row_stride, int format, ag_tag* d_out,
+                           int cap_per_frame, int* d_n_per_frame, uint32_t* d_frame_status,
+                           void* stream) {
+  if (!det) return AG_ERR_INVALID;
+  if (!d_frames || !d_out || !d_n_per_frame || n_frames < 0 || cap_per_frame < 1)
+    return fail(det, AG_ERR_INVALID, "null pointer or bad count");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  FrameGeom g;
+  int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
+  if (rc) return rc;
+  Slot& S = det->slot[0];
+  const int chunk = (int)std::min<long>(det->chunk_frames, std::max(n_frames, 1));
+  if ((rc = ensure_slot(det, S, g, chunk, 1, false))) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : S.stream;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    const int n = std::min(chunk, n_frames - f0);
+    const uint8_t* in = (const uint8_t*)d_frames + (size_t)f0 * g.frame_stride;
+    uint32_t* st = d_frame_status ? d_frame_status + f0 : S.d_status;
+    if ((rc = run_chunk(det, S, in, g, n, d_out + (size_t)f0 * cap_per_frame, cap_per_frame,
+                        d_n_per_frame + f0, st, false, s)))
+      return rc;
+  }
+  return AG_OK;
+}
+
+int ag_dense_batch_device(ag_detector* det, const void* d_frames, size_t frame_stride, int n_frames,
+                          int width, int height, size_t row_stride, int format, void* stream) {
+  if (!det) return AG_ERR_INVALID;
+  if (!d_frames || n_frames < 0) return fail(det, AG_ERR_INVALID, "null pointer or bad count");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  FrameGeom g;
+  int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
+  if (rc) return rc;
+  Slot& S = det->slot[0];
+  const int chunk = (int)std::min<long>(det->chunk_frames, std::max(n_frames, 1));
+  if ((rc = ensure_slot(det, S, g, chunk, 1, false))) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : S.stream;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    const int n = std::min(chunk, n_frames - f0);
+    const uint8_t* in = (const uint8_t*)d_frames + (size_t)f0 * g.frame_stride;
+    if ((rc = run_dense(det, S, in, g, n, true, s))) return rc;
+  }
+  return AG_OK;
+}
+
+int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, int n_frames, int width,
+                    int height, size_t row_stride, int format, ag_tag* out, int cap_per_frame,
+                    int* n_per_frame, uint32_t* frame_status) {
+  if (!det) return AG_ERR_INVALID;
+  if (!frames || !out || !n_per_frame || n_frames < 0 || cap_per_frame < 1)
+    return fail(det, AG_ERR_INVALID, "null pointer or bad count");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  FrameGeom g;
+  int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
+  if (rc) return rc;
+  if (n_frames == 0) return AG_OK;
+  const int chunk = (int)std::min<long>(det->chunk_frames, n_frames);
+  const int n_slots = n_frames > chunk ? 2 : 1;
+  for (int i = 0; i < n_slots; ++i)
+    if ((rc = ensure_slot(det, det->slot[i], g, chunk, cap_per_frame, true))) return rc;
+  bool truncated = false;
+  // Software pipeline over two slots: while slot A computes chunk i, slot B uploads chunk i+1.
+  struct Pending { int f0, n; bool live; } pend[2] = {{0, 0, false}, {0, 0, false}};
+  int which = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk, which ^= 1) {
+    Slot& S = det->slot[which];
+    if (pend[which].live) {
+      AG_CUDA(det, cudaEventSynchronize(S.done));
+      copy_out(S, pend[which].n, cap_per_frame, S.cap_tags, out, n_per_frame, frame_status,
+               pend[which].f0, &truncated);
+      pend[which].live = false;
+    }
+    const int n = std::min(chunk, n_frames - f0);
+    const uint8_t* src = (const uint8_t*)frames + (size_t)f0 * g.frame_stride;
+    const size_t bytes = (size_t)(n - 1) * g.frame_stride + g.row_stride * (size_t)(g.h - 1) +
+                         (size_t)g.w * bytes_per_px(g.format);
+    AG_CUDA(det, cudaMemcpyAsync(S.d_in, src, bytes, cudaMemcpyHostToDevice, S.stream));
+    if ((rc = run_chunk(det, S, S.d_in, g, n, S.d_tags, S.cap_tags, S.d_ntags, S.d_status, false,
+                        S.stream)))
+      return rc;
+    AG_CUDA(det, cudaMemcpyAsync(S.h_ntags, S.d_ntags, sizeof(int) * n, cudaMemcpyDeviceToHost, S.stream));
+    AG_CUDA(det, cudaMemcpyAsync(S.h_status, S.d_status, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost,
+                                 S.stream));
+    AG_CUDA(det, cudaMemcpyAsync(S.h_tags, S.d_tags, sizeof(ag_tag) * (size_t)n * S.cap_tags,
+                                 cudaMemcpyDeviceToHost, S.stream));
+    AG_CUDA(det, cudaEventRecord(S.done, S.stream));
+    pend[which] = {f0, n, true};
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (!pend[i].live) continue;
+    Slot& S = det->slot[i];
+    AG_CUDA(det, cudaEventSynchronize(S.done));
+    copy_out(S, pend[i].n, cap_per_frame, S.cap_tags, out, n_per_frame, frame_status, pend[i].f0,
+             &truncated);
+  }
+  if (truncated) return fail(det, AG_ERR_CAPACITY, "cap_per_frame too small for at least one frame");
+  return AG_OK;
+}
+
+int ag_detect(ag_detector* det, const void* pixels, int width, int height, size_t row_stride,
+              int format, ag_tag* out, int cap, int* n) {
+  if (!n) return det ? fail(det, AG_ERR_INVALID, "n is null") : AG_ERR_INVALID;
+  int cnt = 0;
+  int rc = ag_detect_batch(det, pixels, 0, 1, width, height, row_stride, format, out, cap, &cnt, nullptr);
+  *n = cnt;
+  return rc;
+}
+
+// ---- stage taps -----------------------------------------------------------------------------
+int ag_stage_run(ag_detector* det, const void* pixels, int width, int height, size_t row_stride,
+                 int format) {
+  if (!det) return AG_ERR_INVALID;
+  if (!pixels) return fail(det, AG_ERR_INVALID, "pixels is null");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  det->tap_valid = false;
+  FrameGeom g;
+  int rc = make_geom(det, width, height, row_stride, 0, format, &g);
+  if (rc) return rc;
+  Slot& S = det->slot[0];
+  if ((rc = ensure_slot(det, S, g, 1, det->fam.n_codes, true))) return rc;
+  const size_t bytes = g.row_stride * (size_t)(g.h - 1) + (size_t)g.w * bytes_per_px(g.format);
+  AG_CUDA(det, cudaMemcpyAsync(S.d_in, pixels, bytes, cudaMemcpyHostToDevice, S.stream));
+  if ((rc = run_chunk(det, S, S.d_in, g, 1, S.d_tags, S.cap_tags, S.d_ntags, S.d_status, true, S.stream)))
+    return rc;
+  AG_CUDA(det, cudaStreamSynchronize(S.stream));
+  det->tap_geom = g;
+  det->tap_valid = true;
+  return AG_OK;
+}
+
+#define AG_TAP_PROLOGUE()                                                         \
+  if (!det) return AG_ERR_INVALID;                                                \
+  std::lock_guard<std::mutex> lk(det->mu);                                        \
+  if (!det->tap_valid) return fail(det, AG_ERR_INVALID, "call ag_stage_run first"); \
+  AG_CUDA(det, cudaSetDevice(det->device));                                       \
+  Slot& S = det->slot[0];                                                         \
+  const FrameGeom& g = det->tap_geom;                                             \
+  (void)g;
+
+int ag_stage_blur(ag_detector* det, float* out) {
+  AG_TAP_PROLOGUE();
+  AG_CUDA(det, cudaMemcpy(out, S.d_blur, sizeof(float) * g.n_px, cudaMemcpyDeviceToHost));
+  return AG_OK;
+}
+int ag_stage_response(ag_detector* det, float* out) {
+  AG_TAP_PROLOGUE();
+  AG_CUDA(det, cudaMemcpy(out, S.d_resp, sizeof(float) * g.n_px, cudaMemcpyDeviceToHost));
+  return AG_OK;
+}
+int ag_stage_threshold(ag_detector* det, float* min_and_thr) {
+  AG_TAP_PROLOGUE();
+  uint32_t k;
+  AG_CUDA(det, cudaMemcpy(&k, S.d_min, sizeof(k), cudaMemcpyDeviceToHost));
+  float m = ordered_to_float(k);
+  volatile float t = m * 0.05f;
+  min_and_thr[0] = m;
+  min_and_thr[1] = t;
+  return AG_OK;
+}
+static int tap_labels(ag_detector* det, Slot& S, const FrameGeom& g, int32_t* labels, uint8_t* mask) {
+  int32_t* d_lab = nullptr;
+  uint8_t* d_m = nullptr;
+  if (labels) AG_CUDA(det, cudaMalloc((void**)&d_lab, sizeof(int32_t) * g.n_px));
+  if (mask) AG_CUDA(det, cudaMalloc((void**)&d_m, g.n_px));
+  det->launches += launch_labels_tap(S.d_mask, g, S.d_parent, d_lab, d_m, S.stream);
+  AG_CUDA(det, cudaStreamSynchronize(S.stream));
+  if (labels) AG_CUDA(det, cudaMemcpy(labels, d_lab, sizeof(int32_t) * g.n_px, cudaMemcpyDeviceToHost));
+  if (mask) AG_CUDA(det, cudaMemcpy(mask, d_m, g.n_px, cudaMemcpyDeviceToHost));
+  cudaFree(d_lab);
+  cudaFree(d_m);
+  return AG_OK;
+}
+int ag_stage_mask(ag_detector* det, uint8_t* out) {
+  AG_TAP_PROLOGUE();
+  return tap_labels(det, S, g, nullptr, out);
+}
+int ag_stage_labels(ag_detector* det, int32_t* out) {
+  AG_TAP_PROLOGUE();
+  return tap_labels(det, S, g, out, nullptr);
+}
+int ag_stage_centers(ag_detector* det, float* xy_out, int cap, int* n) {
+  AG_TAP_PROLOGUE();
+  int cnt = 0;
+  AG_CUDA(det, cudaMemcpy(&cnt, S.d_ncl, sizeof(int), cudaMemcpyDeviceToHost));
+  *n = cnt;
+  int m = std::min(cnt, cap);
+  if (m > 0) AG_CUDA(det, cudaMemcpy(xy_out, S.d_centers, sizeof(float2) * m, cudaMemcpyDeviceToHost));
+  return AG_OK;
+}
+int ag_stage_saddles(ag_detector* det, int which, ag_saddle* out, int cap, int* n) {
+  AG_TAP_PROLOGUE();
+  if (which == 1) {
+    int cnt = 0;
+    AG_CUDA(det, cudaMemcpy(&cnt, S.d_nref, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    int m = std::min(cnt, cap);
+    if (m > 0) AG_CUDA(det, cudaMemcpy(out, S.d_refined, sizeof(ag_saddle) * m, cudaMemcpyDeviceToHost));
+    return AG_OK;
+  }
+  int ncl = 0;
+  AG_CUDA(det, cudaMemcpy(&ncl, S.d_ncl, sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<ag_saddle> raw(std::max(ncl, 1));
+  std::vector<uint8_t> valid(std::max(ncl, 1));
+  if (ncl > 0) {
+    AG_CUDA(det, cudaMemcpy(raw.data(), S.d_raw, sizeof(ag_saddle) * ncl, cudaMemcpyDeviceToHost));
+    AG_CUDA(det, cudaMemcpy(valid.data(), S.d_raw_valid, ncl, cudaMemcpyDeviceToHost));
+  }
+  int cnt = 0;
+  for (int i = 0; i < ncl; ++i)
+    if (valid[i]) {
+      if (cnt < cap) out[cnt] = raw[i];
+      ++cnt;
+    }
+  *n = cnt;
+  return AG_OK;
+}
+int ag_stage_board_quads(ag_detector* det, int32_t* quads_out, int cap, int* n) {
+  AG_TAP_PROLOGUE();
+  int cnt = 0;
+  AG_CUDA(det, cudaMemcpy(&cnt, S.d_tap_nquads, sizeof(int), cudaMemcpyDeviceToHost));
+  *n = cnt;
+  int m = std::min(std::min(cnt, cap), S.layout.max_quads);
+  if (m > 0) AG_CUDA(det, cudaMemcpy(quads_out, S.d_tap_quads, sizeof(int32_t) * 4 * m, cudaMemcpyDeviceToHost));
+  return AG_OK;
+}
+int ag_stage_tags(ag_detector* det, ag_tag* out, int cap, int* n) {
+  AG_TAP_PROLOGUE();
+  int cnt = 0;
+  AG_CUDA(det, cudaMemcpy(&cnt, S.d_ntags, sizeof(int), cudaMemcpyDeviceToHost));
+  *n = cnt;
+  int m = std::min(std::min(cnt, cap), S.cap_tags);
+  if (m > 0) AG_CUDA(det, cudaMemcpy(out, S.d_tags, sizeof(ag_tag) * m, cudaMemcpyDeviceToHost));
+  return AG_OK;
+}
+
+int ag_refined_saddle_points(ag_detector* det, const void* pixels, int width, int height,
+                             size_t row_stride, int format, ag_saddle* out, int cap, int* n) {
+  if (!det) return AG_ERR_INVALID;
+  if (!pixels || !out || !n) return fail(det, AG_ERR_INVALID, "null pointer");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  det->tap_valid = false;
+  FrameGeom g;
+  int rc = make_geom(det, width, height, row_stride, 0, format, &g);
+  if (rc) return rc;
+  Slot& S = det->slot[0];
+  if ((rc = ensure_slot(det, S, g, 1, 1, true))) return rc;
+  const size_t bytes = g.row_stride * (size_t)(g.h - 1) + (size_t)g.w * bytes_per_px(g.format);
+  AG_CUDA(det, cudaMemcpyAsync(S.d_in, pixels, bytes, cudaMemcpyHostToDevice, S.stream));
+  if ((rc = run_dense(det, S, S.d_in, g, 1, true, S.stream))) return rc;
+  if ((rc = run_sparse(det, S, g, 1, S.d_status, S.stream))) return rc;
+  int cnt = 0;
+  AG_CUDA(det, cudaMemcpyAsync(&cnt, S.d_nref, sizeof(int), cudaMemcpyDeviceToHost, S.stream));
+  AG_CUDA(det, cudaStreamSynchronize(S.stream));
+  *n = cnt;
+  int m = std::min(cnt, cap);
+  if (m > 0) AG_CUDA(det, cudaMemcpy(out, S.d_refined, sizeof(ag_saddle) * m, cudaMemcpyDeviceToHost));
+  return cnt > cap ? fail(det, AG_ERR_CAPACITY, "saddle capacity too small") : AG_OK;
+}
+
+// ---- standalone operators ---------------------------------------------------------------------
+static int ensure_f32(ag_detector* det, size_t n) {
+  if (n <= det->f32_cap) return AG_OK;
+  int rc;
+  if ((rc = regrow(det, &det->d_f32_a, n))) return rc;
+  if ((rc = regrow(det, &det->d_f32_b, n))) return rc;
+  if ((rc = regrow(det, &det->d_f32_c, n))) return rc;
+  if (!det->d_taps && (rc = regrow(det, &det->d_taps, 256))) return rc;
+  det->f32_cap = n;
+  return AG_OK;
+}
+
+int ag_gaussian_blur_f32(ag_detector* det, const float* img, int width, int height, float sigma,
+                         float* out) {
+  if (!det) return AG_ERR_INVALID;
+  if (!img || !out || width <= 0 || height <= 0) return fail(det, AG_ERR_INVALID, "bad argument");
+  // taps exactly as src/image_util.rs:111-124 computes them at run time (platform expf)
+  int radius = (int)ceilf(sigma * 2.0f);
+  if (radius < 0 || radius > 100) return fail(det, AG_ERR_INVALID, "sigma out of range");
+  std::vector<float> taps(2 * radius + 1);
+  {
+    volatile float two_sigma_sq = 2.0f * sigma * sigma;
+    volatile float sum = 0.0f;
+    for (int i = 0; i <= 2 * radius; ++i) {
+      float x = (float)(i - radius);
+      volatile float xx = x * x;
+      float v = expf(-xx / two_sigma_sq);
+      taps[i] = v;
+      sum = sum + v;
+    }
+    for (auto& v : taps) v = v / sum;
+  }
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  const size_t n = (size_t)width * height;
+  int rc = ensure_f32(det, n);
+  if (rc) return rc;
+  Slot& S = det->slot[0];
+  if (!S.stream) {
+    AG_CUDA(det, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    AG_CUDA(det, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+  }
+  AG_CUDA(det, cudaMemcpyAsync(det->d_taps, taps.data(), sizeof(float) * taps.size(),
+                               cudaMemcpyHostToDevice, S.stream));
+  AG_CUDA(det, cudaMemcpyAsync(det->d_f32_a, img, sizeof(float) * n, cudaMemcpyHostToDevice, S.stream));
+  det->launches += launch_blur_f32(det->d_f32_a, det->d_f32_b, det->d_f32_c, width, height, det->d_taps,
+                                   radius, S.stream);
+  AG_CUDA(det, cudaGetLastError());
+  AG_CUDA(det, cudaMemcpyAsync(out, det->d_f32_c, sizeof(float) * n, cudaMemcpyDeviceToHost, S.stream));
+  AG_CUDA(det, cudaStreamSynchronize(S.stream));
+  return AG_OK;
+}
+
+int ag_hessian_response(ag_detector* det, const float* img, int width, int height, float* out) {
+  if (!det) return AG_ERR_INVALID;
+  if (!img || !out || width <= 0 || height <= 0) return fail(det, AG_ERR_INVALID, "bad argument");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  const size_t n = (size_t)width * height;
+  int rc = ensure_f32(det, n);
+  if (rc) return rc;
+  Slot& S = det->slot[0];
+  if (!S.stream) {
+    AG_CUDA(det, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    AG_CUDA(det, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+  }
+  AG_CUDA(det, cudaMemcpyAsync(det->d_f32_a, img, sizeof(float) * n, cudaMemcpyHostToDevice, S.stream));
+  det->launches += launch_hessian_f32(det->d_f32_a, det->d_f32_c, width, height, S.stream);
+  AG_CUDA(det, cudaGetLastError());
+  AG_CUDA(det, cudaMemcpyAsync(out, det->d_f32_c, sizeof(float) * n, cudaMemcpyDeviceToHost, S.stream));
+  AG_CUDA(det, cudaStreamSynchronize(S.stream));
+  return AG_OK;
+}
+
+int ag_render_boards_device(ag_detector* det, void* d_frames, int n_frames, int width, int height,
+                            int cols, int rows, uint64_t seed, void* stream) {
+  if (!det) return AG_ERR_INVALID;
+  if (!d_frames || n_frames < 0 || width <= 0 || height <= 0 || cols < 1 || rows < 1)
+    return fail(det, AG_ERR_INVALID, "bad argument");
+  if (cols * rows > det->fam.n_codes) return fail(det, AG_ERR_INVALID, "board has more tags than the family has codes");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  if (n_frames == 0) return AG_OK;
+  for (int f0 = 0; f0 < n_frames; f0 += 32768) {
+    int n = std::min(32768, n_frames - f0);
+    det->launches += launch_render_boards((uint8_t*)d_frames + (size_t)f0 * width * height, n, width,
+                                          height, cols, rows, det->d_codes, det->fam.edge,
+                                          det->fam.border, seed + (uint64_t)f0 * 0x51ed27ull,
+                                          (cudaStream_t)stream);
+  }
+  AG_CUDA(det, cudaGetLastError());
+  return AG_OK;
+}
+
+// Test hook (not in the public header): exhaustive unorm conversion tables.
+AG_API int ag_test_unorm_tables(ag_detector* det, float* out8, float* out16, float* ref8, float* ref16) {
+  if (!det) return AG_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  float* d = nullptr;
+  AG_CUDA(det, cudaMalloc((void**)&d, sizeof(float) * (256 + 65536) * 2));
+  float *d8 = d, *d16 = d + 256, *r8 = d16 + 65536, *r16 = r8 + 256;
+  det->launches += launch_unorm_table(d8, d16, r8, r16, 0);
+  AG_CUDA(det, cudaDeviceSynchronize());
+  AG_CUDA(det, cudaMemcpy(out8, d8, 256 * 4, cudaMemcpyDeviceToHost));
+  AG_CUDA(det, cudaMemcpy(out16, d16, 65536 * 4, cudaMemcpyDeviceToHost));
+  AG_CUDA(det, cudaMemcpy(ref8, r8, 256 * 4, cudaMemcpyDeviceToHost));
+  AG_CUDA(det, cudaMemcpy(ref16, r16, 65536 * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return AG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,771 @@
+// Board assembly and tag decoding for ONE frame, written once for two compilation modes:
+//
+//   * device (nvcc, __CUDA_ARCH__): executed by one warp per frame.  All 32 lanes run the
+//     same control flow on the same data ("warp-uniform"); the lanes split the data-parallel
+//     inner loops (nearest-neighbour scans, candidate-quad tests, bit sampling, Hamming
+//     search) and lane 0 performs the stores.
+//   * host (tests/host_board_test.cpp): the same source with a warp of one lane, so the
+//     control logic can be unit-tested against the oracle in a container without a GPU.
+//     That build is test-only; the shipped library has no CPU path.
+//
+// Reference: src/detector.rs:42-169 (decode), :448-476, :505-639; src/board.rs:26-235;
+// src/saddle.rs:17-67; src/math_util.rs:15-33.
+//
+// Where the reference iterates a std HashMap (random order per process) this code uses a
+// fixed order, the same one as the oracle:
+//   * most populated round(theta) bin: ties -> the largest angle      (detector.rs:610-616)
+//   * quads of a board are visited in ascending (x, y) lattice order  (board.rs:49-51)
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__)
+#define AGB_DEVICE 1
+#else
+#define AGB_DEVICE 0
+#endif
+
+#if defined(__CUDACC__)
+#define AGB_FN __host__ __device__ inline
+#else
+#define AGB_FN inline
+#endif
+
+namespace agb {
+
+constexpr int kGrid = 64;  // lattice of tag positions, coordinates -32..31 on both axes
+constexpr int kGridOff = kGrid / 2;
+constexpr int kCells = kGrid * kGrid;
+constexpr int kHistBins = 192;  // round(theta) + 90 in [0, 180]
+constexpr int kMaxCodes = 640;  // >= 587
+constexpr float kPi = 3.14159274101257324f;
+constexpr int kNone = 0x7fffffff;
+
+struct TagRec {  // == ag_tag
+  uint32_t id;
+  float xy[8];
+};
+
+// One board under construction (board.rs:18-25).  Arrays live in the per-frame workspace;
+// the counters are warp-uniform registers.
+struct BoardState {
+  int16_t* cell;     // [kCells] 0 = never visited, -1 = None, q+1 = Some(quad q)
+  int16_t* quads;    // [max_quads][4] saddle indices
+  int16_t* touched;  // [kCells] indices of non-zero cells (cheap reset)
+  uint8_t* active;   // [max_saddles] active_idxs
+  int n_quads, n_touched, score;
+};
+
+struct Frame {
+  int n;                 // saddles in the current round
+  float *sx, *sy, *st;   // current round (SoA): position, theta
+  float *sx2, *sy2, *st2;  // the other half of the ping-pong
+  BoardState bs[2];
+  int16_t* stack;   // [2 * (max_quads + 1)] DFS stack: cell index, next direction
+  int16_t* seeds;   // [max_saddles]
+  int16_t* nn_idx;  // [64] 50-NN result
+  int16_t* same;    // [64]
+  int16_t* diff;    // [64]
+  int16_t* samp;    // [64] sampled brightness (-1 = outside the image)
+  int* hist;        // [kHistBins]
+  uint8_t* remove;  // [max_saddles]
+  int max_quads;
+  // image for bit sampling (original pixels; converted to luma8 on the fly)
+  const uint8_t* img;
+  int w, h, format;
+  size_t row_stride;
+  // family
+  const uint64_t* codes;
+  int n_codes, edge, border, hamming;
+  // results
+  uint8_t* tag_valid;  // [kMaxCodes]
+  TagRec* tag_by_id;   // [kMaxCodes]
+  // optional tap: quads of the first board found, in visiting order
+  int32_t* tap_quads;
+  int* tap_n_quads;
+  int tap_cap;
+  uint32_t status;
+  int lane;  // 0 on host
+};
+
+// ---- warp plumbing ---------------------------------------------------------------------
+#if AGB_DEVICE
+#define AGB_SYNC() __syncwarp()
+#define AGB_LANES 32
+AGB_FN unsigned agb_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+#else
+#define AGB_SYNC() ((void)0)
+#define AGB_LANES 1
+AGB_FN unsigned agb_ballot(bool p) { return p ? 1u : 0u; }
+#endif
+AGB_FN int agb_ffs(unsigned m) {  // index of lowest set bit, m != 0
+#if AGB_DEVICE
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
+AGB_FN int agb_popcll(uint64_t v) {
+#if AGB_DEVICE
+  return __popcll(v);
+#else
+  return __builtin_popcountll(v);
+#endif
+}
+
+// ---- exact f32 arithmetic (no contraction in either build) --------------------------------
+#if AGB_DEVICE
+AGB_FN float fmul(float a, float b) { return __fmul_rn(a, b); }
+AGB_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
+AGB_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
+AGB_FN float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+#else
+AGB_FN float fmul(float a, float b) { volatile float r = a * b; return r; }
+AGB_FN float fadd(float a, float b) { volatile float r = a + b; return r; }
+AGB_FN float fsub(float a, float b) { volatile float r = a - b; return r; }
+AGB_FN float fdiv(float a, float b) { volatile float r = a / b; return r; }
+#endif
+// libm results for f32 arguments: evaluated in f64 and rounded once.
+AGB_FN float atan2_cr(float y, float x) { return (float)atan2((double)y, (double)x); }
+AGB_FN float cos_cr(float x) { return (float)cos((double)x); }
+AGB_FN float sin_cr(float x) { return (float)sin((double)x); }
+
+AGB_FN uint32_t sat_u32(float v) {  // Rust `as u32`
+  if (!(v > 0.0f)) return 0u;
+  if (v >= 4294967296.0f) return 0xffffffffu;
+  return (uint32_t)v;
+}
+AGB_FN int sat_i32(float v) {  // Rust `as i32`
+  if (v != v) return 0;
+  if (v >= 2147483648.0f) return 2147483647;
+  if (v <= -2147483648.0f) return (int)0x80000000;
+  return (int)v;
+}
+
+// ---- math_util.rs:15-33 ------------------------------------------------------------------
+AGB_FN float theta_distance_degree(float t0, float t1) {
+  float d = fadd(fsub(t0, t1), 90.0f);
+  if (d < 0.0f) d = fadd(d, 180.0f);
+  else if (d > 180.0f) d = fsub(d, 180.0f);
+  return d > 90.0f ? fsub(d, 90.0f) : fsub(90.0f, d);
+}
+AGB_FN float cross2(float ax, float ay, float bx, float by) { return fsub(fmul(ax, by), fmul(ay, bx)); }
+AGB_FN float dot2(float ax, float ay, float bx, float by) { return fadd(fmul(ax, bx), fmul(ay, by)); }
+AGB_FN float angle_degree(float ax, float ay, float bx, float by) {
+  float y = fsub(fmul(by, ax), fmul(bx, ay));
+  float x = fadd(fmul(ax, bx), fmul(ay, by));
+  return fdiv(fmul(atan2_cr(y, x), 180.0f), kPi);
+}
+
+// ---- saddle.rs:17-67, split in two so the (s0, s1)-only test can be hoisted ---------------
+AGB_FN bool quad_diag_ok(const Frame& F, int s0, int s1) {  // "filter white block", :26-38
+  float v02x = fsub(F.sx[s1], F.sx[s0]), v02y = fsub(F.sy[s1], F.sy[s0]);
+  float th = fmul(fdiv(F.st[s0], 180.0f), kPi);
+  float vx = cos_cr(th), vy = sin_cr(th);
+  float a = fabsf(angle_degree(v02x, v02y, vx, vy));
+  return a >= 60.0f && a <= 120.0f;
+}
+AGB_FN bool quad_rest_ok(const Frame& F, int s0, int d0, int s1, int d1) {
+  if (theta_distance_degree(F.st[d0], F.st[d1]) > 5.0f) return false;
+  float v01x = fsub(F.sx[d0], F.sx[s0]), v01y = fsub(F.sy[d0], F.sy[s0]);
+  float v03x = fsub(F.sx[d1], F.sx[s0]), v03y = fsub(F.sy[d1], F.sy[s0]);
+  float v02x = fsub(F.sx[s1], F.sx[s0]), v02y = fsub(F.sy[s1], F.sy[s0]);
+  float c0 = cross2(v01x, v01y, v02x, v02y);
+  float c1 = cross2(v02x, v02y, v03x, v03y);
+  if (fmul(c0, c1) < 0.0f) return false;
+  float v12x = fsub(F.sx[s1], F.sx[d0]), v12y = fsub(F.sy[s1], F.sy[d0]);
+  float v23x = fsub(F.sx[d1], F.sx[s1]), v23y = fsub(F.sy[d1], F.sy[s1]);
+  float c01 = cross2(v01x, v01y, v12x, v12y);
+  float c12 = cross2(v12x, v12y, v23x, v23y);
+  if (fmul(c01, c12) < 0.0f) return false;
+  float v30x = fsub(F.sx[s0], F.sx[d1]), v30y = fsub(F.sy[s0], F.sy[d1]);
+  float a0 = angle_degree(v01x, v01y, v12x, v12y);
+  float a1 = angle_degree(v12x, v12y, v23x, v23y);
+  float a2 = angle_degree(v23x, v23y, v30x, v30y);
+  float a3 = angle_degree(v30x, v30y, v01x, v01y);
+  if (fabsf(fsub(a0, a2)) > 10.0f || fabsf(fsub(a1, a3)) > 10.0f) return false;
+  if (dot2(v01x, v01y, v02x, v02y) < 0.0f || dot2(v03x, v03y, v02x, v02y) < 0.0f) return false;
+  return true;
+}
+AGB_FN bool is_valid_quad(const Frame& F, int s0, int d0, int s1, int d1) {
+  // Both halves only ever return false early, so evaluating the diagonal test first gives
+  // the same verdict as the reference's order (saddle.rs:18-38).
+  return quad_diag_ok(F, s0, s1) && quad_rest_ok(F, s0, d0, s1, d1);
+}
+
+// ---- nearest neighbours (kdtree 0.8 `nearest`, restated as exact search) -------------------
+// squared_euclidean: (0 + dx*dx) + dy*dy
+AGB_FN float dist2(const Frame& F, float qx, float qy, int i) {
+  float dx = fsub(qx, F.sx[i]), dy = fsub(qy, F.sy[i]);
+  return fadd(fmul(dx, dx), fmul(dy, dy));
+}
+// strict (d2, idx) lexicographic order; ties in distance resolve to the lower index
+AGB_FN bool nn_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+#if AGB_DEVICE
+AGB_FN void warp_argmin(float& d, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float od = __shfl_xor_sync(0xffffffffu, d, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (nn_less(od, oi, d, i)) { d = od; i = oi; }
+  }
+}
+#else
+AGB_FN void warp_argmin(float&, int&) {}
+#endif
+
+// The (up to) 3 nearest saddles with d2 <= r2, ascending.  Equals "3 nearest overall, then
+// drop those outside the radius" (board.rs:192-200): points inside the radius always precede
+// points outside it in the distance order.
+AGB_FN int nearest3_within(const Frame& F, float qx, float qy, float r2, int out[3]) {
+  float bd[3] = {3.0e38f, 3.0e38f, 3.0e38f};
+  int bi[3] = {kNone, kNone, kNone};
+  for (int i = F.lane; i < F.n; i += AGB_LANES) {
+    float d = dist2(F, qx, qy, i);
+    if (d <= r2 && nn_less(d, i, bd[2], bi[2])) {
+      bd[2] = d; bi[2] = i;
+      if (nn_less(bd[2], bi[2], bd[1], bi[1])) {
+        float t = bd[1]; bd[1] = bd[2]; bd[2] = t;
+        int u = bi[1]; bi[1] = bi[2]; bi[2] = u;
+      }
+      if (nn_less(bd[1], bi[1], bd[0], bi[0])) {
+        float t = bd[0]; bd[0] = bd[1]; bd[1] = t;
+        int u = bi[0]; bi[0] = bi[1]; bi[1] = u;
+      }
+    }
+  }
+  int cnt = 0;
+  // merge the per-lane sorted triples: three rounds of warp arg-min over the lanes' heads
+  for (int r = 0; r < 3; ++r) {
+    float d = bd[0];
+    int i = bi[0];
+    warp_argmin(d, i);
+    if (i == kNone) break;  // warp-uniform
+    out[cnt++] = i;
+    if (bi[0] == i) {
+      bd[0] = bd[1]; bi[0] = bi[1];
+      bd[1] = bd[2]; bi[1] = bi[2];
+      bd[2] = 3.0e38f; bi[2] = kNone;
+    }
+  }
+  return cnt;
+}
+
+// Nearest single saddle (board.rs:88).
+AGB_FN int nearest1(const Frame& F, float qx, float qy) {
+  float bd = 3.0e38f;
+  int bi = kNone;
+  for (int i = F.lane; i < F.n; i += AGB_LANES) {
+    float d = dist2(F, qx, qy, i);
+    if (nn_less(d, i, bd, bi)) { bd = d; bi = i; }
+  }
+  warp_argmin(bd, bi);
+  return bi;
+}
+
+// The k (<= 64) nearest saddles of a point, ascending, written to F.nn_idx; returns the count.
+// Selection by repeated extraction: each round takes the smallest (d2, idx) strictly greater
+// than the previous pick.
+AGB_FN int nearest_k(Frame& F, float qx, float qy, int k) {
+  int cnt = 0;
+  float last_d = -1.0f;
+  int last_i = -1;
+  const int kk = k < F.n ? k : F.n;
+  for (int r = 0; r < kk; ++r) {
+    float bd = 3.0e38f;
+    int bi = kNone;
+    for (int i = F.lane; i < F.n; i += AGB_LANES) {
+      float d = dist2(F, qx, qy, i);
+      if (nn_less(last_d, last_i, d, i) && nn_less(d, i, bd, bi)) { bd = d; bi = i; }
+    }
+    warp_argmin(bd, bi);
+    if (bi == kNone) break;
+    if (F.lane == 0) F.nn_idx[cnt] = (int16_t)bi;
+    ++cnt;
+    last_d = bd;
+    last_i = bi;
+  }
+  AGB_SYNC();
+  return cnt;
+}
+
+// ---- Board (board.rs) -----------------------------------------------------------------------
+// x is the major axis so that ascending cell index == ascending (x, y).
+AGB_FN int cell_index(int x, int y) { return (x + kGridOff) * kGrid + (y + kGridOff); }
+AGB_FN int cell_x(int ci) { return ci / kGrid - kGridOff; }
+AGB_FN int cell_y(int ci) { return ci % kGrid - kGridOff; }
+AGB_FN bool cell_in_range(int x, int y) {
+  return x >= -kGridOff && x < kGridOff && y >= -kGridOff && y < kGridOff;
+}
+
+// Undo everything the previous build on this state did (cells back to 0, saddles active).
+AGB_FN void board_reset(Frame& F, BoardState& B) {
+  for (int t = F.lane; t < B.n_touched; t += AGB_LANES) B.cell[B.touched[t]] = 0;
+  for (int t = F.lane; t < B.n_quads * 4; t += AGB_LANES) B.active[B.quads[t]] = 1;
+  AGB_SYNC();
+  B.n_touched = 0;
+  B.n_quads = 0;
+  B.score = 0;
+}
+
+// find_closest_potential_saddle_idxs (board.rs:177-234) for the edge s0 -> s1.
+AGB_FN void find_closest(const Frame& F, const BoardState& B, int s0, int s1, int out0[3], int* n0,
+                         int out1[3], int* n1) {
+  const float ratio0 = fadd(1.0f, 0.3f);  // 1.0 + spacing_ratio; detector.rs:621 passes 0.3
+  float dx = fsub(F.sx[s0], F.sx[s1]), dy = fsub(F.sy[s0], F.sy[s1]);
+  float radius_sq = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
+  float v10x = fsub(F.sx[s1], F.sx[s0]), v10y = fsub(F.sy[s1], F.sy[s0]);
+  float nv0x = fadd(F.sx[s0], fmul(v10x, ratio0)), nv0y = fadd(F.sy[s0], fmul(v10y, ratio0));
+  float nv1x = fadd(F.sx[s1], fmul(v10x, ratio0)), nv1y = fadd(F.sy[s1], fmul(v10y, ratio0));
+  int nn[3];
+  int c = nearest3_within(F, nv0x, nv0y, radius_sq, nn);
+  int k0 = 0;
+  for (int j = 0; j < c; ++j)
+    if (B.active[nn[j]] && theta_distance_degree(F.st[s0], F.st[nn[j]]) < 5.0f) out0[k0++] = nn[j];
+  c = nearest3_within(F, nv1x, nv1y, radius_sq, nn);
+  int k1 = 0;
+  for (int j = 0; j < c; ++j)
+    if (B.active[nn[j]] && theta_distance_degree(F.st[s1], F.st[nn[j]]) < 5.0f) out1[k1++] = nn[j];
+  *n0 = k0;
+  *n1 = k1;
+}
+
+// try_expand_one (board.rs:153-176)
+AGB_FN bool try_expand_one(const Frame& F, const BoardState& B, const int q[4], int out[4]) {
+  int a0[3], a1[3], a2[3], a3[3], n0, n1, n2, n3;
+  find_closest(F, B, q[0], q[1], a0, &n0, a1, &n1);
+  if (n0 == 0 || n1 == 0) return false;  // the nested loops below would be empty
+  find_closest(F, B, q[3], q[2], a3, &n3, a2, &n2);
+  for (int i0 = 0; i0 < n0; ++i0)
+    for (int i1 = 0; i1 < n1; ++i1)
+      for (int i2 = 0; i2 < n2; ++i2)
+        for (int i3 = 0; i3 < n3; ++i3)
+          if (is_valid_quad(F, a0[i0], a1[i1], a2[i2], a3[i3])) {
+            out[0] = a0[i0]; out[1] = a1[i1]; out[2] = a2[i2]; out[3] = a3[i3];
+            return true;
+          }
+  return false;
+}
+
+// Board::new + try_expand (board.rs:27-48, :114-152); the recursion runs on an explicit stack.
+AGB_FN void board_build(Frame& F, BoardState& B, const int quad[4]) {
+  board_reset(F, B);
+  const int c0 = cell_index(0, 0);
+  if (F.lane == 0) {
+    for (int j = 1; j < 4; ++j) B.active[quad[j]] = 0;  // quad[0] stays active, as in :35-37
+    for (int j = 0; j < 4; ++j) B.quads[j] = (int16_t)quad[j];
+    B.cell[c0] = 1;
+    B.touched[0] = (int16_t)c0;
+    F.stack[0] = (int16_t)c0;
+    F.stack[1] = 0;
+  }
+  B.n_quads = 1;
+  B.n_touched = 1;
+  B.score = 1;
+  int depth = 1;
+  AGB_SYNC();
+  while (depth > 0) {
+    const int ci = F.stack[2 * (depth - 1)];
+    const int i = F.stack[2 * (depth - 1) + 1];
+    AGB_SYNC();
+    if (i == 4) {
+      --depth;
+      continue;
+    }
+    if (F.lane == 0) F.stack[2 * (depth - 1) + 1] = (int16_t)(i + 1);
+    const int bx = cell_x(ci), by = cell_y(ci);
+    const int qi = B.cell[ci] - 1;
+    int qs[4];
+    for (int j = 0; j < 4; ++j) qs[j] = B.quads[qi * 4 + ((j + i) & 3)];  // rotate_left(i)
+    int nx = bx, ny = by;
+    if (i == 0) nx = bx + 1;
+    else if (i == 1) ny = by - 1;
+    else if (i == 2) nx = bx - 1;
+    else ny = by + 1;
+    AGB_SYNC();
+    if (!cell_in_range(nx, ny)) {
+      F.status |= 4u;  // AG_FRAME_BOARD_OVERFLOW
+      continue;
+    }
+    const int nci = cell_index(nx, ny);
+    const int cur = B.cell[nci];
+    if (cur > 0) continue;  // already Some (board.rs:131-135)
+    int nq[4];
+    const bool ok = (B.n_quads < F.max_quads) && try_expand_one(F, B, qs, nq);
+    AGB_SYNC();
+    if (cur == 0) {
+      if (F.lane == 0) B.touched[B.n_touched] = (int16_t)nci;
+      ++B.n_touched;
+    }
+    if (ok) {
+      int v[4];
+      for (int j = 0; j < 4; ++j) v[(j + i) & 3] = nq[j];  // rotate_right(i)
+      if (F.lane == 0) {
+        for (int j = 0; j < 4; ++j) {
+          B.active[v[j]] = 0;
+          B.quads[B.n_quads * 4 + j] = (int16_t)v[j];
+        }
+        B.cell[nci] = (int16_t)(B.n_quads + 1);
+        F.stack[2 * depth] = (int16_t)nci;
+        F.stack[2 * depth + 1] = 0;
+      }
+      ++B.n_quads;
+      ++B.score;
+      ++depth;
+    } else {
+      if (F.lane == 0) B.cell[nci] = -1;
+    }
+    AGB_SYNC();
+  }
+}
+
+// try_fix_missing (board.rs:52-112).  The reference first lists the fixable holes, then
+// fills them; a hole filled in this pass must therefore not serve as a neighbour of another
+// hole ("was Some when the list was built" == quad index below fix_base).
+AGB_FN void board_fix_missing(Frame& F, BoardState& B) {
+  const int n_t = B.n_touched;
+  const int fix_base = B.n_quads;
+  for (int t = 0; t < n_t; ++t) {
+    const int ci = B.touched[t];
+    const int cv = B.cell[ci];
+    if (cv != -1) continue;
+    const int x = cell_x(ci), y = cell_y(ci);
+    const int e0 = cell_in_range(x + 1, y) ? B.cell[cell_index(x + 1, y)] : 0;
+    const int e1 = cell_in_range(x - 1, y) ? B.cell[cell_index(x - 1, y)] : 0;
+    int qa = -1, qb = -1;
+    if (e0 != 0 && e1 != 0) {  // contains_key(b0) && contains_key(b1)
+      if (e0 > 0 && e0 - 1 < fix_base && e1 > 0 && e1 - 1 < fix_base) { qa = e0 - 1; qb = e1 - 1; }
+    } else {
+      const int e2 = cell_in_range(x, y + 1) ? B.cell[cell_index(x, y + 1)] : 0;
+      const int e3 = cell_in_range(x, y - 1) ? B.cell[cell_index(x, y - 1)] : 0;
+      if (e2 > 0 && e2 - 1 < fix_base && e3 > 0 && e3 - 1 < fix_base) { qa = e2 - 1; qb = e3 - 1; }
+    }
+    if (qa < 0) continue;
+    int sidx[4];
+    for (int j = 0; j < 4; ++j) {
+      const int ia = B.quads[qa * 4 + j], ib = B.quads[qb * 4 + j];
+      float mx = fdiv(fadd(F.sx[ia], F.sx[ib]), 2.0f);
+      float my = fdiv(fadd(F.sy[ia], F.sy[ib]), 2.0f);
+      sidx[j] = nearest1(F, mx, my);
+    }
+    if (B.n_quads < F.max_quads && is_valid_quad(F, sidx[0], sidx[1], sidx[2], sidx[3])) {
+      AGB_SYNC();
+      if (F.lane == 0) {
+        for (int j = 0; j < 4; ++j) B.quads[B.n_quads * 4 + j] = (int16_t)sidx[j];
+        B.cell[ci] = (int16_t)(B.n_quads + 1);
+      }
+      ++B.n_quads;
+      AGB_SYNC();
+    }
+  }
+}
+
+// (i, j), i < j, of the c-th 2-combination of n items in lexicographic order (itertools).
+AGB_FN void unrank_pair(int c, int n, int* i, int* j) {
+  int a = 0;
+  while (c >= n - 1 - a) {
+    c -= n - 1 - a;
+    ++a;
+  }
+  *i = a;
+  *j = a + 1 + c;
+}
+
+// try_find_best_board (detector.rs:588-639) incl. init_quads (:543-586).  Returns the index
+// (0/1) of the BoardState holding the best board, or -1 for None.
+AGB_FN int find_best_board(Frame& F) {
+  if (F.n == 0) return -1;
+  // histogram of round(theta)
+  for (int b = F.lane; b < kHistBins; b += AGB_LANES) F.hist[b] = 0;
+  AGB_SYNC();
+  for (int i = F.lane; i < F.n; i += AGB_LANES) {
+    int key = sat_i32(roundf(F.st[i])) + 90;
+    key = key < 0 ? 0 : (key >= kHistBins ? kHistBins - 1 : key);
+#if AGB_DEVICE
+    atomicAdd(&F.hist[key], 1);
+#else
+    F.hist[key] += 1;
+#endif
+  }
+  AGB_SYNC();
+  int best_cnt = -1, best_key = -1;
+  for (int b = F.lane; b < kHistBins; b += AGB_LANES) {
+    int c = F.hist[b];
+    if (c > best_cnt || (c == best_cnt && b > best_key)) { best_cnt = c; best_key = b; }
+  }
+#if AGB_DEVICE
+  for (int o = 16; o > 0; o >>= 1) {
+    int oc = __shfl_xor_sync(0xffffffffu, best_cnt, o);
+    int ok = __shfl_xor_sync(0xffffffffu, best_key, o);
+    if (oc > best_cnt || (oc == best_cnt && ok > best_key)) { best_cnt = oc; best_key = ok; }
+  }
+#endif
+  // seeds: members of that bin in ascending index order
+  int n_seeds = 0;
+  for (int base = 0; base < F.n; base += AGB_LANES) {
+    int i = base + F.lane;
+    bool in = false;
+    if (i < F.n) {
+      int key = sat_i32(roundf(F.st[i])) + 90;
+      key = key < 0 ? 0 : (key >= kHistBins ? kHistBins - 1 : key);
+      in = key == best_key;
+    }
+    unsigned m = agb_ballot(in);
+#if AGB_DEVICE
+    if (in) F.seeds[n_seeds + __popc(m & ((1u << F.lane) - 1u))] = (int16_t)i;
+    n_seeds += __popc(m);
+#else
+    if (in) F.seeds[n_seeds] = (int16_t)i;
+    n_seeds += (int)m;
+#endif
+  }
+  AGB_SYNC();
+
+  int cur = 0, best = -1, best_score = 0, count = 0;
+  while (n_seeds > 0 && count < 30) {
+    const int s0 = F.seeds[--n_seeds];  // pop from the back
+    // ---- init_quads(refined, s0, tree) ----
+    const int n_nn = nearest_k(F, F.sx[s0], F.sy[s0], 50);
+    int n_same = 0, n_diff = 0;
+    for (int j = 1; j < n_nn; ++j) {  // nearest[1..]: the first hit is the seed itself
+      const int si = F.nn_idx[j];
+      const float td = theta_distance_degree(F.st[s0], F.st[si]);
+      if (td < 5.0f) {
+        if (F.lane == 0) F.same[n_same] = (int16_t)si;
+        ++n_same;
+      } else if (td > 80.0f) {
+        if (F.lane == 0) F.diff[n_diff] = (int16_t)si;
+        ++n_diff;
+      }
+    }
+    AGB_SYNC();
+    const int n_pairs = n_diff * (n_diff - 1) / 2;
+    for (int a = 0; a < n_same; ++a) {
+      const int s1 = F.same[a];
+      if (!quad_diag_ok(F, s0, s1)) continue;  // every quad with this (s0, s1) fails :31
+      for (int base = 0; base < n_pairs; base += AGB_LANES) {
+        const int c = base + F.lane;
+        bool valid = false;
+        if (c < n_pairs) {
+          int i, j;
+          unrank_pair(c, n_diff, &i, &j);
+          valid = quad_rest_ok(F, s0, F.diff[i], s1, F.diff[j]);
+        }
+        unsigned m = agb_ballot(valid);
+        while (m) {
+          const int b = agb_ffs(m);
+          m &= m - 1;
+          int i, j;
+          unrank_pair(base + b, n_diff, &i, &j);
+          const int d0 = F.diff[i], d1 = F.diff[j];
+          const float c0 = cross2(fsub(F.sx[d0], F.sx[s0]), fsub(F.sy[d0], F.sy[s0]),
+                                  fsub(F.sx[s1], F.sx[s0]), fsub(F.sy[s1], F.sy[s0]));
+          int quad[4];
+          quad[0] = s0; quad[2] = s1;
+          if (c0 > 0.0f) { quad[1] = d0; quad[3] = d1; }
+          else { quad[1] = d1; quad[3] = d0; }
+          // ---- Board::new(refined, active_mask, &q, 0.3, tree) ----
+          board_build(F, F.bs[cur], quad);
+          if (F.bs[cur].score > best_score) {
+            best_score = F.bs[cur].score;
+            best = cur;
+            cur ^= 1;
+          }
+        }
+      }
+    }
+    if (best_score >= 36) break;
+    ++count;
+  }
+  if (best < 0) return -1;
+  board_fix_missing(F, F.bs[best]);
+  return best;
+}
+
+// ---- decoding (detector.rs:42-169, :448-476) ---------------------------------------------------
+AGB_FN int luma8_at(const Frame& F, uint32_t x, uint32_t y) {  // image 0.25 to_luma8
+  const uint8_t* row = F.img + (size_t)y * F.row_stride;
+  if (F.format == 0) return row[x];
+  if (F.format == 1) return (int)((((uint32_t)((const uint16_t*)row)[x]) + 128u) / 257u);
+  const uint8_t* p = row + 3 * (size_t)x;
+  return (int)((2126u * p[0] + 7152u * p[1] + 722u * p[2]) / 10000u);
+}
+
+// rotate_bits (detector.rs:124-140)
+AGB_FN uint64_t rotate_bits(uint64_t bits, int edge) {
+  uint64_t b = 0;
+  int count = 0;
+  for (int r = edge - 1; r >= 0; --r)
+    for (int c = 0; c < edge; ++c) {
+      int idx = r + c * edge;
+      b |= ((bits >> idx) & 1ull) << count;
+      ++count;
+    }
+  return b;
+}
+
+// try_decode_quad: on success fills *out (id + rotated, reversed corners).
+AGB_FN bool decode_quad(Frame& F, const int q[4], TagRec* out) {
+  float qx[4], qy[4];
+  for (int j = 0; j < 4; ++j) {
+    qx[j] = F.sx[q[j]];
+    qy[j] = F.sy[q[j]];
+  }
+  // decode_positions :50-56
+  for (int j = 0; j < 4; ++j) {
+    uint32_t x = sat_u32(roundf(qx[j])), y = sat_u32(roundf(qy[j]));
+    if (x >= (uint32_t)F.w || y >= (uint32_t)F.h) return false;
+  }
+  // tag_affine (image_util.rs:39-70): least-squares affine from the tag frame to the image.
+  // The four source corners form a square, so the centred normal equations are diagonal.
+  const int side = F.border * 2 + F.edge;
+  const float lo = -0.5f, hi = (float)side - 1.0f + 0.5f;
+  const double sxs[4] = {lo, lo, hi, hi};
+  const double sys[4] = {lo, hi, hi, lo};
+  double mx = 0, my = 0, mcx = 0, mcy = 0;
+  for (int p = 0; p < 4; ++p) { mx += sxs[p]; my += sys[p]; mcx += qx[p]; mcy += qy[p]; }
+  mx /= 4; my /= 4; mcx /= 4; mcy /= 4;
+  double sxx = 0, syy = 0, axx = 0, axy = 0, ayx = 0, ayy = 0;
+  for (int p = 0; p < 4; ++p) {
+    double dx = sxs[p] - mx, dy = sys[p] - my;
+    sxx += dx * dx; syy += dy * dy;
+    axx += dx * qx[p]; axy += dy * qx[p];
+    ayx += dx * qy[p]; ayy += dy * qy[p];
+  }
+  const double h0d = axx / sxx, h1d = axy / syy, h3d = ayx / sxx, h4d = ayy / syy;
+  const float h0 = (float)h0d, h1 = (float)h1d, h2 = (float)(mcx - h0d * mx - h1d * my);
+  const float h3 = (float)h3d, h4 = (float)h4d, h5 = (float)(mcy - h3d * mx - h4d * my);
+  // sample (bit_code :80-93): sample s = (x - border) * edge + (y - border), x outer
+  const int ns = F.edge * F.edge;
+  for (int s = F.lane; s < ns; s += AGB_LANES) {
+    const float fx = (float)(F.border + s / F.edge), fy = (float)(F.border + s % F.edge);
+    const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
+    const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
+    const uint32_t x = sat_u32(roundf(px)), y = sat_u32(roundf(py));
+    int v = -1;
+    if (x < (uint32_t)F.w && y < (uint32_t)F.h) v = luma8_at(F, x, y);
+    F.samp[s] = (int16_t)v;
+  }
+  AGB_SYNC();
+  int min_b = 255, max_b = 0;
+  bool oob = false;
+  for (int s = 0; s < ns; ++s) {
+    const int v = F.samp[s];
+    if (v < 0) oob = true;
+    min_b = v < min_b ? v : min_b;
+    max_b = v > max_b ? v : max_b;
+  }
+  AGB_SYNC();
+  if (oob) return false;
+  if (max_b - min_b < 50) return false;  // :97
+  const int mid_b = (int)sat_u32(roundf(fdiv(fadd((float)min_b, (float)max_b), 2.0f)));
+  uint64_t bits = 0;
+  int invalid = 0;
+  for (int i = 0; i < ns; ++i) {  // iter().rev().enumerate(): the last sample is bit 0
+    const int v = F.samp[ns - 1 - i];
+    const int dlt = mid_b - v;
+    if ((dlt < 0 ? -dlt : dlt) < 10) ++invalid;
+    if (v > mid_b) bits |= (1ull << i);
+  }
+  AGB_SYNC();
+  if (invalid > 3) return false;
+  // best_tag :142-169
+  int id = -1, rot = 0;
+  for (int rotated = 0; rotated < 4; ++rotated) {
+    float bs = 1.0e9f;  // score as float so warp_argmin can be reused; popcount <= 64 is exact
+    int bi = kNone;
+    for (int c = F.lane; c < F.n_codes; c += AGB_LANES) {
+      const float sc = (float)agb_popcll(F.codes[c] ^ bits);
+      if (nn_less(sc, c, bs, bi)) { bs = sc; bi = c; }
+    }
+    warp_argmin(bs, bi);
+    if (bs < (float)F.hamming) {
+      id = bi;
+      rot = rotated;
+      break;
+    }
+    if (rotated == 3) break;
+    bits = rotate_bits(bits, F.edge);
+  }
+  if (id < 0) return false;
+  out->id = (uint32_t)id;
+  for (int j = 0; j < 4; ++j) {  // rotate_left(rot) then reverse() (:467-469)
+    const int src = ((3 - j) + rot) & 3;
+    out->xy[2 * j] = qx[src];
+    out->xy[2 * j + 1] = qy[src];
+  }
+  return true;
+}
+
+// TagDetector::detect from the refined saddle list on (detector.rs:510-538).
+// Workspace arrays must be initialised by the caller: cells 0, active 1, tag_valid 0.
+AGB_FN void detect_boards(Frame& F, int max_boards) {
+  for (int round = 0; round < max_boards; ++round) {
+    const int best = find_best_board(F);
+    if (best < 0) continue;
+    BoardState& B = F.bs[best];
+    for (int i = F.lane; i < F.n; i += AGB_LANES) F.remove[i] = 0;
+    AGB_SYNC();
+    int n_tap = 0;
+    // all_tag_indexes in ascending (x, y) order
+    for (int base = 0; base < kCells; base += AGB_LANES) {
+      const int ci = base + F.lane;
+      unsigned m = agb_ballot(B.cell[ci] > 0);
+      while (m) {
+        const int b = agb_ffs(m);
+        m &= m - 1;
+        const int qi = B.cell[base + b] - 1;
+        int q[4];
+        for (int j = 0; j < 4; ++j) q[j] = B.quads[qi * 4 + j];
+        if (round == 0 && F.tap_quads) {
+          if (F.lane == 0 && n_tap < F.tap_cap)
+            for (int j = 0; j < 4; ++j) F.tap_quads[n_tap * 4 + j] = q[j];
+          ++n_tap;
+        }
+        TagRec t;
+        if (decode_quad(F, q, &t)) {
+          if (F.lane == 0) {
+            F.tag_by_id[t.id] = t;  // HashMap::insert: a repeated id overwrites
+            F.tag_valid[t.id] = 1;
+            for (int j = 0; j < 4; ++j) F.remove[q[j]] = 1;
+          }
+          AGB_SYNC();
+        }
+      }
+    }
+    if (round == 0 && F.tap_n_quads && F.lane == 0) *F.tap_n_quads = n_tap;
+    AGB_SYNC();
+    // refined.retain(not removed), order kept (:526-536); the board states are reset because
+    // saddle indices change.
+    board_reset(F, F.bs[0]);
+    board_reset(F, F.bs[1]);
+    int n_new = 0;
+    for (int base = 0; base < F.n; base += AGB_LANES) {
+      const int i = base + F.lane;
+      const bool keep = i < F.n && !F.remove[i];
+      unsigned m = agb_ballot(keep);
+#if AGB_DEVICE
+      const int dst = n_new + __popc(m & ((1u << F.lane) - 1u));
+      const int cnt = __popc(m);
+#else
+      const int dst = n_new;
+      const int cnt = (int)m;
+#endif
+      if (keep) {
+        F.sx2[dst] = F.sx[i];
+        F.sy2[dst] = F.sy[i];
+        F.st2[dst] = F.st[i];
+      }
+      n_new += cnt;
+    }
+    AGB_SYNC();
+    float* t;
+    t = F.sx; F.sx = F.sx2; F.sx2 = t;
+    t = F.sy; F.sy = F.sy2; F.sy2 = t;
+    t = F.st; F.st = F.st2; F.st2 = t;
+    F.n = n_new;
+  }
+}
+
+}  // namespace agb

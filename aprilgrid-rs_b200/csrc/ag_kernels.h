@@ -1,0 +1,57 @@
+// Host-callable launchers of the aprilgrid kernels (internal to the library).
+// Every launcher returns the number of kernel launches it enqueued.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ag_common.cuh"
+
+namespace ag {
+
+struct BoardWsLayout {
+  int max_saddles, max_quads;
+  size_t off_pos[6];
+  size_t off_cell[2], off_quads[2], off_touched[2], off_active[2];
+  size_t off_stack, off_seeds, off_nn, off_same, off_diff, off_samp, off_hist, off_remove;
+  size_t off_tag_valid, off_tag_by_id;
+  size_t bytes_per_frame;
+};
+BoardWsLayout make_board_layout(int max_saddles);
+
+// ag_dense.cu
+int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames, float* blur,
+                        float* resp, uint32_t* frame_min, bool write_blur, int variant,
+                        cudaStream_t s);
+int launch_threshold(const float* resp, const FrameGeom& g, int n_frames, const uint32_t* frame_min,
+                     uint32_t* mask, cudaStream_t s);
+int launch_blur_f32(const float* in, float* tmp, float* out, int w, int h, const float* d_taps,
+                    int radius, cudaStream_t s);
+int launch_hessian_f32(const float* in, float* out, int w, int h, cudaStream_t s);
+int launch_unorm_table(float* out8, float* out16, float* ref8, float* ref16, cudaStream_t s);
+
+// ag_sparse.cu
+int upload_rochade_tables(const float* cone25, const float* pinv150);
+int launch_label_clusters(const uint32_t* mask, const FrameGeom& g, int n_frames, int* parent,
+                          int max_clusters, int* acc, float2* centers, int* n_clusters,
+                          uint32_t* frame_status, cudaStream_t s);
+int launch_labels_tap(const uint32_t* mask, const FrameGeom& g, const int* parent, int32_t* labels,
+                      uint8_t* mask_u8, cudaStream_t s);
+int launch_refine_filter(const float* blur, const FrameGeom& g, int n_frames, const float2* centers,
+                         const int* n_clusters, int max_clusters, ag_saddle* raw, uint8_t* raw_valid,
+                         float min_angle, float max_angle, int max_saddles, ag_saddle* refined,
+                         int* n_refined, uint32_t* frame_status, cudaStream_t s);
+
+// ag_board.cu
+int upload_codes(const uint64_t* codes, int n);
+int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames,
+                         const ag_saddle* refined, const int* n_refined, uint8_t* ws,
+                         const BoardWsLayout& L, int n_codes, int edge, int border, int hamming,
+                         int max_boards, ag_tag* out, int cap, int* n_out, uint32_t* frame_status,
+                         int32_t* tap_quads, int* tap_n_quads, int tap_cap, cudaStream_t s);
+
+// ag_render.cu
+int launch_render_boards(uint8_t* frames, int n_frames, int w, int h, int cols, int rows,
+                         const uint64_t* d_codes, int edge, int border, uint64_t seed,
+                         cudaStream_t s);
+
+}  // namespace ag

@@ -1,0 +1,421 @@
+// Sparse stages of the aprilgrid front end, sm_100a: everything between the threshold mask
+// and the refined saddle list.  One CTA per frame; the data are a few hundred KB per frame
+// and live in L2.
+//
+//   K3  k_label_clusters   4-connected components of the mask by union-find whose roots are
+//                          the minimum raster index of each component, numbered in ascending
+//                          root order (== the reference's raster-scan discovery order), plus
+//                          the per-cluster centroid.
+//                          reference: src/detector.rs:171-187 (init_saddle_clusters),
+//                          src/image_util.rs:208-236 (pixel_bfs), src/detector.rs:421-429.
+//   K4  k_refine_filter    one warp per candidate: 9x9 window of the blurred image -> 5x5
+//                          cone convolution -> 6-parameter quadratic fit -> saddle test;
+//                          then the k / phi filter with order-preserving compaction.
+//                          reference: src/detector.rs:194-361 (rochade_refine), :432-445.
+#include "ag_common.cuh"
+#include "ag_kernels.h"
+
+namespace ag {
+
+// ----------------------------------------------------------------------------------------
+// union-find helpers on the sparse parent array (only mask pixels are ever touched).
+// Loads bypass L1 (ld.cg): parents are modified concurrently with atomicMin at L2.
+// ----------------------------------------------------------------------------------------
+AG_D int uf_find(const int* P, int p) {
+  int q;
+  while ((q = __ldcg(P + p)) != p) p = q;
+  return p;
+}
+AG_D void uf_union(int* P, int a, int b) {
+  while (true) {
+    a = uf_find(P, a);
+    b = uf_find(P, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    int old = atomicMin(P + a, b);  // hang the larger root under the smaller one
+    if (old == a) return;
+    a = old;
+  }
+}
+
+constexpr int kCclThreads = 1024;
+
+// Block-wide exclusive scan of one int per thread (kCclThreads threads). Returns the
+// exclusive prefix; *total receives the block sum.
+AG_D int block_exclusive_scan(int v, int* s_warp /*[32]*/, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;  // exclusive prefix of warp sums
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  int r = s_warp[warp] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kCclThreads)
+k_label_clusters(const uint32_t* __restrict__ mask, FrameGeom g, int* __restrict__ parent,
+                 int max_clusters, int* __restrict__ acc /*[F][max_clusters][3]*/,
+                 float2* __restrict__ centers, int* __restrict__ n_clusters,
+                 uint32_t* __restrict__ frame_status) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int f = blockIdx.x;
+  const uint32_t* M = mask + (size_t)f * g.n_words;
+  int* P = parent + (size_t)f * g.n_px;
+  int* A = acc + (size_t)f * max_clusters * 3;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int wpr = g.wpr, w = g.w;
+
+  // P0: every mask pixel points at its left neighbour if that is set, else at itself.
+  for (int wi = tid; wi < g.n_words; wi += nt) {
+    uint32_t m = M[wi];
+    if (!m) continue;
+    int row = wi / wpr, wc = wi - row * wpr;
+    int base = row * w + wc * 32;
+    uint32_t left = (m << 1) | (wc > 0 ? (M[wi - 1] >> 31) : 0u);
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      int p = base + b;
+      P[p] = ((left >> b) & 1u) ? p - 1 : p;
+    }
+  }
+  __syncthreads();
+  // P1: union with the pixel above.  A pixel whose left and upper-left neighbours are both
+  // set is already connected to its upper neighbour through them, so it is skipped.
+  for (int wi = tid; wi < g.n_words; wi += nt) {
+    uint32_t m = M[wi];
+    if (!m || wi < wpr) continue;
+    int row = wi / wpr, wc = wi - row * wpr;
+    uint32_t up = M[wi - wpr];
+    uint32_t u = m & up;
+    if (!u) continue;
+    uint32_t left = (m << 1) | (wc > 0 ? (M[wi - 1] >> 31) : 0u);
+    uint32_t upleft = (up << 1) | (wc > 0 ? (M[wi - wpr - 1] >> 31) : 0u);
+    u &= ~(left & upleft);
+    int base = row * w + wc * 32;
+    while (u) {
+      int b = __ffs(u) - 1;
+      u &= u - 1;
+      uf_union(P, base + b, base + b - w);
+    }
+  }
+  __syncthreads();
+  // P2: flatten so that every pixel stores its root (= min raster index of the component).
+  for (int wi = tid; wi < g.n_words; wi += nt) {
+    uint32_t m = M[wi];
+    if (!m) continue;
+    int row = wi / wpr, wc = wi - row * wpr;
+    int base = row * w + wc * 32;
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      int p = base + b;
+      int r = uf_find(P, p);
+      if (r != p) P[p] = r;
+    }
+  }
+  __syncthreads();
+  // P3: number the roots in ascending raster order.  Thread t owns a contiguous word range.
+  const int per = (g.n_words + nt - 1) / nt;
+  const int w_begin = min(tid * per, g.n_words), w_end = min(w_begin + per, g.n_words);
+  int my_roots = 0;
+  for (int wi = w_begin; wi < w_end; ++wi) {
+    uint32_t m = M[wi];
+    if (!m) continue;
+    int row = wi / wpr, wc = wi - row * wpr;
+    int base = row * w + wc * 32;
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      int p = base + b;
+      if (__ldcg(P + p) == p) ++my_roots;
+    }
+  }
+  int offset = block_exclusive_scan(my_roots, s_warp, &s_total);
+  const int total = s_total;
+  for (int wi = w_begin; wi < w_end; ++wi) {
+    uint32_t m = M[wi];
+    if (!m) continue;
+    int row = wi / wpr, wc = wi - row * wpr;
+    int base = row * w + wc * 32;
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      int p = base + b;
+      if (__ldcg(P + p) == p) {
+        P[p] = -(offset + 1);  // root now carries its cluster id, encoded negative
+        ++offset;
+      }
+    }
+  }
+  const int n_used = min(total, max_clusters);
+  for (int i = tid; i < n_used * 3; i += nt) A[i] = 0;
+  __syncthreads();
+  // P4: accumulate (sum x, sum y, count) per cluster with integer atomics.  The reference
+  // sums the coordinates in f32 (detector.rs:424-426); integer sums below 2^24 are exact
+  // in f32 whatever the order, so one int->float conversion reproduces them bit for bit.
+  for (int wi = tid; wi < g.n_words; wi += nt) {
+    uint32_t m = M[wi];
+    if (!m) continue;
+    int row = wi / wpr, wc = wi - row * wpr;
+    int base = row * w + wc * 32;
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      int p = base + b;
+      int v = __ldcg(P + p);
+      int cid = v < 0 ? -v - 1 : -__ldcg(P + v) - 1;
+      if (cid < max_clusters) {
+        atomicAdd(A + 3 * cid + 0, wc * 32 + b);
+        atomicAdd(A + 3 * cid + 1, row);
+        atomicAdd(A + 3 * cid + 2, 1);
+      }
+    }
+  }
+  __syncthreads();
+  float2* Cn = centers + (size_t)f * max_clusters;
+  for (int c = tid; c < n_used; c += nt) {
+    float n = (float)__ldcg(A + 3 * c + 2);
+    float sx = (float)__ldcg(A + 3 * c + 0), sy = (float)__ldcg(A + 3 * c + 1);
+    Cn[c] = make_float2(__fdiv_rn(sx, n), __fdiv_rn(sy, n));  // detector.rs:427
+  }
+  if (tid == 0) {
+    n_clusters[f] = n_used;
+    if (total > max_clusters) atomicOr(frame_status + f, (uint32_t)AG_FRAME_CLUSTER_OVERFLOW);
+  }
+}
+
+// Test tap: dense label image (cluster id or -1) from the mask and the parent array.
+__global__ void k_labels_tap(const uint32_t* __restrict__ mask, FrameGeom g,
+                             const int* __restrict__ parent, int32_t* __restrict__ labels,
+                             uint8_t* __restrict__ mask_u8) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.n_px) return;
+  int row = p / g.w, x = p - row * g.w;
+  uint32_t m = mask[row * g.wpr + (x >> 5)];
+  bool set = (m >> (x & 31)) & 1u;
+  if (mask_u8) mask_u8[p] = set ? 1 : 0;
+  if (labels) {
+    int lab = -1;
+    if (set) {
+      int v = parent[p];
+      lab = v < 0 ? -v - 1 : -parent[v] - 1;
+    }
+    labels[p] = lab;
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// K4: rochade refine + filter
+// ----------------------------------------------------------------------------------------
+__constant__ float c_cone[25];      // normalised cone kernel, detector.rs:240-254
+__constant__ float c_pinv[6 * 25];  // pseudo-inverse of [x^2, xy, y^2, x, y, 1], :208-237
+
+int upload_rochade_tables(const float* cone25, const float* pinv150) {
+  cudaError_t e = cudaMemcpyToSymbol(c_cone, cone25, sizeof(float) * 25);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyToSymbol(c_pinv, pinv150, sizeof(float) * 150);
+  return (int)e;
+}
+
+constexpr int kRefineThreads = 512;
+constexpr int kRefineWarps = kRefineThreads / 32;
+
+// libm-compatible transcendental results for f32 arguments: evaluate in f64 and round once.
+AG_D float acosf_cr(float x) { return (float)acos((double)x); }
+AG_D float atan2f_cr(float y, float x) { return (float)atan2((double)y, (double)x); }
+
+// Rust f32::round (half away from zero) followed by `as i32` (saturating).
+AG_D int round_to_i32(float v) {
+  float r = roundf(v);
+  if (r != r) return 0;
+  if (r >= 2147483648.0f) return 2147483647;
+  if (r <= -2147483648.0f) return (int)0x80000000;
+  return (int)r;
+}
+
+__global__ void __launch_bounds__(kRefineThreads)
+k_refine_filter(const float* __restrict__ blur, FrameGeom g, const float2* __restrict__ centers,
+                const int* __restrict__ n_clusters, int max_clusters,
+                ag_saddle* __restrict__ raw, uint8_t* __restrict__ raw_valid,
+                float min_angle, float max_angle, int max_saddles,
+                ag_saddle* __restrict__ refined, int* __restrict__ n_refined,
+                uint32_t* __restrict__ frame_status) {
+  __shared__ float s_win[kRefineWarps][81];
+  __shared__ float s_smooth[kRefineWarps][25];
+  __shared__ float s_cone[25];
+  __shared__ float s_pinv[150];
+  __shared__ float s_redf[kRefineWarps];
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  __shared__ float s_kmax;
+
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* B = blur + (size_t)f * g.n_px;
+  const float2* Cn = centers + (size_t)f * max_clusters;
+  ag_saddle* R = raw + (size_t)f * max_clusters;
+  uint8_t* V = raw_valid + (size_t)f * max_clusters;
+  const int n = n_clusters[f];
+  if (tid < 25) s_cone[tid] = c_cone[tid];
+  if (tid < 150) s_pinv[tid] = c_pinv[tid];
+  __syncthreads();
+
+  float kmax = -3.40282347e+38f;  // f32::MIN, detector.rs:436
+  for (int c = warp; c < n; c += kRefineWarps) {
+    const float2 ic = Cn[c];
+    const float rxf = roundf(ic.x), ryf = roundf(ic.y);
+    const int rx = round_to_i32(ic.x), ry = round_to_i32(ic.y);
+    bool ok = !(ry - 4 < 0 || ry + 4 >= g.h || rx - 4 < 0 || rx + 4 >= g.w);  // :268-274
+    ag_saddle out;
+    bool valid = false;
+    if (ok) {  // warp-uniform
+      const float* src = B + (size_t)(ry - 4) * g.w + (rx - 4);
+      for (int i = lane; i < 81; i += 32) {
+        int r = i / 9, cc = i - r * 9;
+        s_win[warp][i] = src[(size_t)r * g.w + cc];
+      }
+      __syncwarp();
+      if (lane < 25) {  // 5x5 cone convolution, accumulation order of :283-297
+        int r = lane / 5, cc = lane - r * 5;
+        float conv = 0.0f;
+#pragma unroll
+        for (int pr = 0; pr < 5; ++pr)
+#pragma unroll
+          for (int pc = 0; pc < 5; ++pc)
+            conv = __fadd_rn(conv, __fmul_rn(s_win[warp][(r + pr) * 9 + cc + pc], s_cone[pr * 5 + pc]));
+        s_smooth[warp][lane] = conv;
+      }
+      __syncwarp();
+      float prm = 0.0f;
+      if (lane < 6) {  // params[j] = sum_i pinv[j][i] * smooth[i], i ascending (:321-328)
+#pragma unroll
+        for (int i = 0; i < 25; ++i)
+          prm = __fadd_rn(prm, __fmul_rn(s_pinv[lane * 25 + i], s_smooth[warp][i]));
+      }
+      const float a1 = __shfl_sync(0xffffffffu, prm, 0), a2 = __shfl_sync(0xffffffffu, prm, 1),
+                  a3 = __shfl_sync(0xffffffffu, prm, 2), a4 = __shfl_sync(0xffffffffu, prm, 3),
+                  a5 = __shfl_sync(0xffffffffu, prm, 4);
+      const float fxx = __fmul_rn(2.0f, a1), fyy = __fmul_rn(2.0f, a3), fxy = a2;
+      const float d = __fsub_rn(__fmul_rn(fxx, fyy), __fmul_rn(fxy, fxy));
+      if (d < 0.0f) {
+        // math_util::find_xy(2a1, a2, a4, a2, 2a3, a5): 2x2 LU with row pivoting, f32.
+        float m00 = fxx, m01 = a2, m10 = a2, m11 = fyy, r0 = -a4, r1 = -a5;
+        if (fabsf(m10) > fabsf(m00)) {
+          float t;
+          t = m00; m00 = m10; m10 = t;
+          t = m01; m01 = m11; m11 = t;
+          t = r0; r0 = r1; r1 = t;
+        }
+        const float l = __fdiv_rn(m10, m00);
+        const float u11 = __fsub_rn(m11, __fmul_rn(l, m01));
+        const float z1 = __fsub_rn(r1, __fmul_rn(l, r0));
+        const float y0 = __fdiv_rn(z1, u11);
+        const float x0 = __fdiv_rn(__fsub_rn(r0, __fmul_rn(m01, y0)), m00);
+        if (fabsf(x0) <= 1.0f && fabsf(y0) <= 1.0f) {
+          const float c5 = __fdiv_rn(__fadd_rn(a1, a3), 2.0f);
+          const float c4 = __fdiv_rn(__fsub_rn(a1, a3), 2.0f);
+          const float c3 = __fdiv_rn(a2, 2.0f);
+          const float k = __fsqrt_rn(__fadd_rn(__fmul_rn(c4, c4), __fmul_rn(c3, c3)));
+          if (fabsf(c5) < k) {
+            const float kPi = 3.14159274101257324f;
+            float phi = __fmul_rn(__fdiv_rn(__fdiv_rn(acosf_cr(__fdiv_rn(-c5, k)), 2.0f), kPi), 180.0f);
+            float theta = __fmul_rn(__fdiv_rn(__fdiv_rn(atan2f_cr(c3, c4), 2.0f), kPi), 180.0f);
+            out.x = __fadd_rn(rxf, x0);
+            out.y = __fadd_rn(ryf, y0);
+            out.k = k;
+            out.theta = theta;
+            out.phi = phi;
+            valid = true;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      V[c] = valid ? 1 : 0;
+      if (valid) {
+        R[c] = out;
+        kmax = fmaxf(kmax, out.k);
+      }
+    }
+  }
+  // block max of k
+  if (lane == 0) s_redf[warp] = kmax;
+  __syncthreads();
+  if (tid == 0) {
+    float m = s_redf[0];
+    for (int i = 1; i < kRefineWarps; ++i) m = fmaxf(m, s_redf[i]);
+    s_kmax = __fdiv_rn(m, 10.0f);  // detector.rs:436
+  }
+  __syncthreads();
+  const float kthr = s_kmax;
+  // order-preserving compaction of the survivors (detector.rs:437-444)
+  const int per = (n + kRefineThreads - 1) / kRefineThreads;
+  const int c_begin = min(tid * per, n), c_end = min(c_begin + per, n);
+  int mine = 0;
+  for (int c = c_begin; c < c_end; ++c) {
+    if (V[c]) {
+      const ag_saddle s = R[c];
+      if (s.k >= kthr && s.phi >= min_angle && s.phi <= max_angle) ++mine;
+    }
+  }
+  int offset = block_exclusive_scan(mine, s_warp, &s_total);
+  ag_saddle* O = refined + (size_t)f * max_saddles;
+  for (int c = c_begin; c < c_end; ++c) {
+    if (V[c]) {
+      const ag_saddle s = R[c];
+      if (s.k >= kthr && s.phi >= min_angle && s.phi <= max_angle) {
+        if (offset < max_saddles) O[offset] = s;
+        ++offset;
+      }
+    }
+  }
+  if (tid == 0) {
+    n_refined[f] = min(s_total, max_saddles);
+    if (s_total > max_saddles) atomicOr(frame_status + f, (uint32_t)AG_FRAME_SADDLE_OVERFLOW);
+  }
+}
+
+int launch_label_clusters(const uint32_t* mask, const FrameGeom& g, int n_frames, int* parent,
+                          int max_clusters, int* acc, float2* centers, int* n_clusters,
+                          uint32_t* frame_status, cudaStream_t s) {
+  k_label_clusters<<<n_frames, kCclThreads, 0, s>>>(mask, g, parent, max_clusters, acc, centers,
+                                                    n_clusters, frame_status);
+  return 1;
+}
+
+int launch_labels_tap(const uint32_t* mask, const FrameGeom& g, const int* parent, int32_t* labels,
+                      uint8_t* mask_u8, cudaStream_t s) {
+  k_labels_tap<<<(g.n_px + 255) / 256, 256, 0, s>>>(mask, g, parent, labels, mask_u8);
+  return 1;
+}
+
+int launch_refine_filter(const float* blur, const FrameGeom& g, int n_frames, const float2* centers,
+                         const int* n_clusters, int max_clusters, ag_saddle* raw, uint8_t* raw_valid,
+                         float min_angle, float max_angle, int max_saddles, ag_saddle* refined,
+                         int* n_refined, uint32_t* frame_status, cudaStream_t s) {
+  k_refine_filter<<<n_frames, kRefineThreads, 0, s>>>(blur, g, centers, n_clusters, max_clusters, raw,
+                                                      raw_valid, min_angle, max_angle, max_saddles,
+                                                      refined, n_refined, frame_status);
+  return 1;
+}
+
+}  // namespace ag

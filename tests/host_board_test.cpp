@@ -1,0 +1,65 @@
+// TEST-ONLY host build of the product's board/decode control logic
+// (aprilgrid-rs_b200/csrc/ag_board_core.h compiled with a warp of one lane).
+// It lets the CPU test-suite compare that logic with the oracle without a GPU.  It is never
+// linked into the shipped library and is not a CPU path of the product.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ag_board_core.h"
+
+extern "C" {
+
+// saddles: n x {x, y, k, theta, phi}.  Returns number of tags written (ascending id).
+int hb_detect_from_saddles(const float* saddles, int n, const uint8_t* img, int w, int h,
+                           size_t row_stride, int format, const uint64_t* codes, int n_codes,
+                           int edge, int border, int hamming, int max_boards, int max_saddles,
+                           agb::TagRec* out, int cap, int32_t* tap_quads, int* tap_n, int tap_cap,
+                           uint32_t* status) {
+  using namespace agb;
+  if (n > max_saddles) return -1;
+  const int N = max_saddles, Q = N / 4 + 2;
+  std::vector<float> pos(6 * (size_t)N, 0.0f);
+  std::vector<int16_t> cell[2] = {std::vector<int16_t>(kCells, 0), std::vector<int16_t>(kCells, 0)};
+  std::vector<int16_t> quads[2] = {std::vector<int16_t>(4 * Q), std::vector<int16_t>(4 * Q)};
+  std::vector<int16_t> touched[2] = {std::vector<int16_t>(kCells), std::vector<int16_t>(kCells)};
+  std::vector<uint8_t> active[2] = {std::vector<uint8_t>(N, 1), std::vector<uint8_t>(N, 1)};
+  std::vector<int16_t> stack(2 * (Q + 1)), seeds(N), nn(64), same(64), diff(64), samp(64);
+  std::vector<int> hist(kHistBins);
+  std::vector<uint8_t> remove(N), tag_valid(kMaxCodes, 0);
+  std::vector<TagRec> tag_by_id(kMaxCodes);
+  Frame F;
+  memset(&F, 0, sizeof F);
+  F.lane = 0;
+  F.n = n;
+  F.sx = &pos[0]; F.sy = &pos[N]; F.st = &pos[2 * (size_t)N];
+  F.sx2 = &pos[3 * (size_t)N]; F.sy2 = &pos[4 * (size_t)N]; F.st2 = &pos[5 * (size_t)N];
+  for (int i = 0; i < n; ++i) {
+    F.sx[i] = saddles[5 * i]; F.sy[i] = saddles[5 * i + 1]; F.st[i] = saddles[5 * i + 3];
+  }
+  for (int b = 0; b < 2; ++b) {
+    F.bs[b].cell = cell[b].data(); F.bs[b].quads = quads[b].data();
+    F.bs[b].touched = touched[b].data(); F.bs[b].active = active[b].data();
+    F.bs[b].n_quads = F.bs[b].n_touched = F.bs[b].score = 0;
+  }
+  F.stack = stack.data(); F.seeds = seeds.data(); F.nn_idx = nn.data(); F.same = same.data();
+  F.diff = diff.data(); F.samp = samp.data(); F.hist = hist.data(); F.remove = remove.data();
+  F.max_quads = Q;
+  F.img = img; F.w = w; F.h = h; F.format = format; F.row_stride = row_stride;
+  F.codes = codes; F.n_codes = n_codes; F.edge = edge; F.border = border; F.hamming = hamming;
+  F.tag_valid = tag_valid.data(); F.tag_by_id = tag_by_id.data();
+  F.tap_quads = tap_quads; F.tap_n_quads = tap_n; F.tap_cap = tap_cap;
+  if (tap_n) *tap_n = 0;
+  detect_boards(F, max_boards);
+  int cnt = 0;
+  for (int id = 0; id < n_codes; ++id)
+    if (tag_valid[id]) {
+      if (cnt < cap) out[cnt] = tag_by_id[id];
+      ++cnt;
+    }
+  if (status) *status = F.status;
+  return cnt;
+}
+
+}  // extern "C"

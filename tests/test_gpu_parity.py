@@ -1,0 +1,187 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200: -m gpu.
+
+Bars (BASELINE.json north_star): blurred image, response, threshold mask, component labels and
+tag ids bit-exact; refined corner coordinates within 1e-3 px (they come out bit-identical too;
+the tolerance is written where it is used)."""
+import numpy as np
+import pytest
+
+import synth
+from conftest import FIXTURE_NAMES
+
+pytestmark = pytest.mark.gpu
+CORNER_TOL = 1e-3  # px, north_star
+
+
+def assert_tags_match(got, want):
+    assert sorted(got) == sorted(want), (sorted(got), sorted(want))
+    for k in want:
+        assert np.abs(got[k] - want[k]).max() <= CORNER_TOL, (k, got[k], want[k])
+
+
+def assert_saddles_match(g, o):
+    """g: structured array from the GPU, o: N x 5 oracle array."""
+    assert len(g) == len(o)
+    if len(o) == 0:
+        return
+    # positions and k use +,-,*,/,sqrt only: bit-identical.  theta/phi pass through acos/atan2:
+    # glibc's f32 versions vs f64-evaluated-and-rounded on the GPU may differ in the last ulp.
+    assert np.array_equal(g["x"], o[:, 0]) and np.array_equal(g["y"], o[:, 1])
+    assert np.array_equal(g["k"], o[:, 2])
+    assert np.abs(g["theta"] - o[:, 3]).max() <= 2e-5 and np.abs(g["phi"] - o[:, 4]).max() <= 2e-5
+
+
+def check_stages(det, oracle, img, check_board=True):
+    g = det.stages(img)
+    o = oracle.front_end(img)
+    assert np.array_equal(g["blur"].view(np.uint32), o["blur"].view(np.uint32)), "blur not bit-exact"
+    assert np.array_equal(g["resp"].view(np.uint32), o["resp"].view(np.uint32)), "response not bit-exact"
+    assert np.float32(g["min"]) == np.float32(o["min"]) and np.float32(g["thr"]) == np.float32(o["thr"])
+    assert np.array_equal(g["mask"].astype(bool), o["resp"] < np.float32(o["thr"]))
+    assert np.array_equal(g["labels"], o["labels"]), "labels differ"
+    assert np.array_equal(g["centers"].view(np.uint32), o["centers"].view(np.uint32))
+    assert_saddles_match(g["raw"], o["raw"])
+    assert_saddles_match(g["refined"], o["refined"])
+    if check_board:
+        oq = oracle.try_find_best_board(o["refined"])
+        if oq is None:
+            assert len(g["quads"]) == 0
+        else:
+            assert np.array_equal(g["quads"], oq)
+        assert_tags_match(g["tags"], oracle.detect(img))
+    return g, o
+
+
+def test_unorm_conversion_exhaustive(detector):
+    o8, o16, r8, r16 = detector._unorm_tables()
+    assert np.array_equal(o8.view(np.uint32), r8.view(np.uint32))
+    assert np.array_equal(o16.view(np.uint32), r16.view(np.uint32))
+    assert np.array_equal(r8, (np.arange(256, dtype=np.float32) / np.float32(255)))
+    assert np.array_equal(r16, (np.arange(65536, dtype=np.float32) / np.float32(65535)))
+
+
+@pytest.mark.parametrize("name", FIXTURE_NAMES)
+def test_fixture_stage_parity(detector, oracle, images, name):
+    check_stages(detector, oracle, images[name])
+
+
+@pytest.mark.parametrize("name,count", [("iphone", 66), ("EuRoC", 36), ("TUM_VI", 36), ("right", 36),
+                                        ("r45", 36), ("top", 36), ("two_boards", 72)])
+def test_reference_counts_through_detect(detector, oracle, images, name, count):
+    """tests/test_detector.rs:26-32 run against the CUDA path."""
+    tags = detector.detect(images[name])
+    assert len(tags) == count
+    assert_tags_match(tags, oracle.detect(images[name]))
+
+
+def test_detect_kornia(detector, oracle, images):
+    """tests/test_detector.rs:35-43"""
+    img = images["iphone"]
+    assert len(detector.detect_kornia(img)) == 66
+    gray = oracle.to_luma_u8(images["EuRoC"])[:, :, None]
+    assert_tags_match(detector.detect_kornia(gray), oracle.detect(images["EuRoC"]))
+    with pytest.raises(ValueError):
+        detector.detect_kornia(np.zeros((8, 8, 4), np.uint8))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 3), (5, 7), (8, 9), (9, 33), (31, 65), (40, 130)])
+def test_tiny_and_odd_shapes(detector, oracle, shape):
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    check_stages(detector, oracle, img)
+
+
+def test_constant_image_gives_empty_map(detector, oracle):
+    for v in (0, 128, 255):
+        img = np.full((48, 64), v, np.uint8)
+        g, o = check_stages(detector, oracle, img)
+        assert g["tags"] == {} and (g["mask"] == 0).all()  # min = 0 -> nothing below threshold
+        assert detector.detect(img) == {}
+
+
+@pytest.mark.parametrize("fmt", ["l8", "l16", "rgb8"])
+def test_random_noise_dense_and_labels(detector, oracle, fmt):
+    """iid noise: worst case for the labeller (large ragged components)."""
+    rng = np.random.default_rng(11)
+    if fmt == "l8":
+        img = rng.integers(0, 256, (200, 333), dtype=np.uint8)
+    elif fmt == "l16":
+        img = rng.integers(0, 65536, (200, 333), dtype=np.uint16)
+    else:
+        img = rng.integers(0, 256, (200, 333, 3), dtype=np.uint8)
+    check_stages(detector, oracle, img, check_board=False)
+
+
+def test_row_stride(detector, oracle, images):
+    """Padded rows: the image is a view into a wider buffer."""
+    base = images["EuRoC"]
+    h, w = base.shape
+    buf = np.zeros((h, w + 40), np.uint8)
+    buf[:, :w] = base
+    view = buf[:, :w]
+    assert not view.flags.c_contiguous
+    assert_tags_match(detector.detect(view), oracle.detect(base))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(dtype=np.uint16), dict(rgb=True)])
+def test_synthetic_formats(detector, oracle, kw):
+    img = synth.render_board_numpy(640, 480, seed=5, tag_px=44.0, **kw)
+    g, o = check_stages(detector, oracle, img)
+    assert sorted(g["tags"]) == list(range(36))
+
+
+def test_detect_batch_matches_oracle_per_frame(detector, oracle):
+    frames = synth.fixture_like_frames(7, 640, 480, seed=20, tag_px=42.0)
+    frames[3] = 77  # one empty frame in the middle of the batch
+    detector.set_option("chunk_frames", 3)  # ragged chunks: 3 + 3 + 1, both pipeline slots used
+    try:
+        got, status = detector.detect_batch(frames, return_status=True)
+    finally:
+        detector.set_option("chunk_frames", 32)
+    assert (status == 0).all()
+    want = oracle.detect_batch(frames)
+    assert len(got) == 7 and got[3] == {}
+    for g, w in zip(got, want):
+        assert_tags_match(g, w)
+    assert detector.detect_batch(frames[:0]) == []
+
+
+def test_capacity_error_is_reported(detector, pkg, images):
+    with pytest.raises(RuntimeError):
+        detector.detect(images["EuRoC"], cap=5)
+
+
+def test_operators_blur_and_hessian(detector, oracle):
+    """image_util::gaussian_blur_f32 / hessian_response as standalone f32 -> f32 operators."""
+    rng = np.random.default_rng(2)
+    for shape in [(5, 5), (37, 61), (480, 752)]:
+        img = rng.random(shape, dtype=np.float32)
+        for sigma in (1.5, 0.8, 2.6):
+            assert np.array_equal(detector.gaussian_blur_f32(img, sigma).view(np.uint32),
+                                  oracle.gaussian_blur(img, sigma).view(np.uint32))
+        assert np.array_equal(detector.hessian_response(img).view(np.uint32),
+                              oracle.hessian_response(img).view(np.uint32))
+    imp = np.zeros((5, 5), np.float32)
+    imp[2, 2] = 10.0
+    assert detector.hessian_response(imp)[2, 2] == 400.0  # image_util.rs:284-288
+
+
+def test_refined_saddle_points_api(detector, oracle, images):
+    g = detector.refined_saddle_points(images["TUM_VI"])
+    assert_saddles_match(g, oracle.front_end(images["TUM_VI"], want_labels=False)["refined"])
+
+
+def test_other_families(pkg, oracle):
+    """T16H5 / T25H7 / T25H9 / T36H11B1: parameters + tables only (detector.rs:369-405)."""
+    for fam, name in [(pkg.TagFamily.T25H9, "t25h9"), (pkg.TagFamily.T16H5, "t16h5"),
+                      (pkg.TagFamily.T25H7, "t25h7"), (pkg.TagFamily.T36H11B1, "t36h11b1")]:
+        img = synth.render_board_numpy(640, 480, cols=5, rows=4, seed=9, tag_px=52.0,
+                                       family=name)
+        det = pkg.TagDetector(fam)
+        try:
+            got = det.detect(img)
+        finally:
+            det.close()
+        want = oracle.detect(img, family=name)
+        assert_tags_match(got, want)
+        assert len(want) >= 15, (name, len(want))
