@@ -106,6 +106,7 @@ def lib():
         L.ag_stage_tags.argtypes = [vp, vp, ci, vp]
         L.ag_launch_count.restype = C.c_uint64
         L.ag_launch_count.argtypes = [vp]
+        L.ag_stage_times.argtypes = [vp, vp, vp, ci]
         L.ag_render_boards_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, C.c_uint64, vp]
         L.ag_test_unorm_tables.argtypes = [vp, vp, vp, vp, vp]
         _lib = L
@@ -181,6 +182,15 @@ class TagDetector:
     @property
     def launch_count(self):
         return int(lib().ag_launch_count(self._h))
+
+    STAGE_NAMES = ("blur_hessian_min", "threshold", "label_centroid", "refine_filter", "boards_decode")
+
+    def stage_times(self, reset=True):
+        """{stage: (total_ms, launches)} accumulated while option "profile" is 1."""
+        ms = np.zeros(8, np.float64)
+        cnt = np.zeros(8, np.uint64)
+        self._check(lib().ag_stage_times(self._h, _p(ms), _p(cnt), 1 if reset else 0))
+        return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(self.STAGE_NAMES)}
 
     # -- reference API -----------------------------------------------------------------
     def detect(self, img, cap=1024):
@@ -290,7 +300,7 @@ class TagDetector:
             labels = np.empty((h, w), np.int32)
             self._check(L.ag_stage_labels(self._h, _p(labels)))
         n = C.c_int(0)
-        cap = 1 << 16
+        cap = max(1 << 16, w * h // 4)
         centers = np.zeros((cap, 2), np.float32)
         self._check(L.ag_stage_centers(self._h, _p(centers), cap, C.byref(n)))
         centers = centers[:n.value].copy()

@@ -39,6 +39,8 @@ std::string g_create_error;
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  cudaEvent_t ev_front = nullptr, ev_boards = nullptr;  // device-batch pipeline hand-offs
+  bool boards_pending = false;
   int cap_frames = 0;
   size_t cap_px = 0, cap_words = 0, cap_in_bytes = 0;
   int cap_clusters = 0, cap_saddles = 0, cap_tags = 0;
@@ -71,13 +73,23 @@ struct ag_detector {
   std::string err;
   Slot slot[2];
   uint64_t launches = 0;
-  long chunk_frames = 32;
+  long chunk_frames = 256;
   long max_clusters = 16384;
   long max_saddles = 2048;
   uint64_t* d_codes = nullptr;  // family table in global memory (renderer)
+  cudaStream_t board_stream = nullptr;  // boards+decode of chunk i overlap the dense stages of i+1
   // stage-tap state
   FrameGeom tap_geom{};
   bool tap_valid = false;
+  // optional per-stage timing (ag_set_option "profile"): CUDA events between the kernels
+  long board_lattice = 64;  // side of the tag lattice a board may span (16 / 32 / 64)
+  bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_stage;  // stage id of the interval ENDING at event i, -1 = interval start
+  size_t ev_used = 0;
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t stage_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // scratch for the standalone operators
   float *d_f32_a = nullptr, *d_f32_b = nullptr, *d_f32_c = nullptr, *d_taps = nullptr;
   size_t f32_cap = 0;
@@ -139,11 +151,21 @@ int regrow(ag_detector* det, T** p, size_t count) {
 
 // Make sure a slot can hold `frames` frames of geometry g with `cap_tags` tags per frame.
 int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int cap_tags,
-                bool need_input) {
+                bool need_input, bool keep_pending = false) {
   int rc;
   if (!S.stream) {
     AG_CUDA(det, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
     AG_CUDA(det, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    AG_CUDA(det, cudaEventCreateWithFlags(&S.ev_front, cudaEventDisableTiming));
+    AG_CUDA(det, cudaEventCreateWithFlags(&S.ev_boards, cudaEventDisableTiming));
+  }
+  const bool will_realloc = frames > S.cap_frames || (size_t)g.n_px > S.cap_px ||
+                            (size_t)g.n_words > S.cap_words || (int)det->max_clusters != S.cap_clusters ||
+                            (int)det->max_saddles != S.cap_saddles || cap_tags > S.cap_tags;
+  if (S.boards_pending && (will_realloc || !keep_pending)) {
+    // a previous device-batch call may still be using these buffers on the board stream
+    AG_CUDA(det, cudaEventSynchronize(S.ev_boards));
+    S.boards_pending = false;
   }
   const bool grow_frames = frames > S.cap_frames;
   const int F = std::max(frames, S.cap_frames);
@@ -172,7 +194,7 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     if ((rc = regrow(det, &S.d_raw, (size_t)F * ncl))) return rc;
     if ((rc = regrow(det, &S.d_raw_valid, (size_t)F * ncl))) return rc;
     if ((rc = regrow(det, &S.d_refined, (size_t)F * nsd))) return rc;
-    S.layout = make_board_layout(nsd);
+    S.layout = make_board_layout(nsd, (int)det->board_lattice);
     if ((rc = regrow(det, &S.d_board_ws, (size_t)F * S.layout.bytes_per_frame))) return rc;
     if ((rc = regrow(det, &S.d_tap_quads, (size_t)F * S.layout.max_quads * 4))) return rc;
     if ((rc = regrow(det, &S.d_tap_nquads, (size_t)F))) return rc;
@@ -213,15 +235,35 @@ void free_slot(Slot& S) {
   if (S.h_ntags) cudaFreeHost(S.h_ntags);
   if (S.h_status) cudaFreeHost(S.h_status);
   if (S.done) cudaEventDestroy(S.done);
+  if (S.ev_front) cudaEventDestroy(S.ev_front);
+  if (S.ev_boards) cudaEventDestroy(S.ev_boards);
   if (S.stream) cudaStreamDestroy(S.stream);
   S = Slot();
+}
+
+// Stage ids for the optional timing: 0 K1 blur+hessian+min, 1 K2 threshold, 2 K3 label+centroid,
+// 3 K4 refine+filter, 4 K6 boards+decode.
+void prof_mark(ag_detector* det, int stage, cudaStream_t s) {
+  if (!det->profile) return;
+  if (det->ev_used == det->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    det->ev_pool.push_back(e);
+    det->ev_stage.push_back(-1);
+  }
+  det->ev_stage[det->ev_used] = stage;
+  cudaEventRecord(det->ev_pool[det->ev_used], s);
+  ++det->ev_used;
 }
 
 // Dense front end of one chunk on stream s: K1 + K2.
 int run_dense(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
               bool write_blur, cudaStream_t s) {
+  prof_mark(det, -1, s);
   det->launches += launch_blur_hessian(d_frames, g, n, S.d_blur, S.d_resp, S.d_min, write_blur, 0, s);
+  prof_mark(det, 0, s);
   det->launches += launch_threshold(S.d_resp, g, n, S.d_min, S.d_mask, s);
+  prof_mark(det, 1, s);
   AG_CUDA(det, cudaGetLastError());
   return AG_OK;
 }
@@ -230,12 +272,15 @@ int run_dense(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeo
 int run_sparse(ag_detector* det, Slot& S, const FrameGeom& g, int n, uint32_t* d_status,
                cudaStream_t s) {
   AG_CUDA(det, cudaMemsetAsync(d_status, 0, sizeof(uint32_t) * n, s));
+  prof_mark(det, -1, s);
   det->launches += launch_label_clusters(S.d_mask, g, n, S.d_parent, S.cap_clusters, S.d_acc,
                                          S.d_centers, S.d_ncl, d_status, s);
+  prof_mark(det, 2, s);
   det->launches += launch_refine_filter(S.d_blur, g, n, S.d_centers, S.d_ncl, S.cap_clusters, S.d_raw,
                                         S.d_raw_valid, det->params.min_saddle_angle,
                                         det->params.max_saddle_angle, S.cap_saddles, S.d_refined,
                                         S.d_nref, d_status, s);
+  prof_mark(det, 3, s);
   AG_CUDA(det, cudaGetLastError());
   return AG_OK;
 }
@@ -243,11 +288,13 @@ int run_sparse(ag_detector* det, Slot& S, const FrameGeom& g, int n, uint32_t* d
 int run_boards(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
                ag_tag* d_tags, int cap, int* d_ntags, uint32_t* d_status, bool taps,
                cudaStream_t s) {
+  prof_mark(det, -1, s);
   det->launches += launch_boards_decode(
       d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, S.layout, det->fam.n_codes, det->fam.edge,
       det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
       d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout.max_quads,
-      s);
+      det->board_grid ? 1 : 0, s);
+  prof_mark(det, 4, s);
   AG_CUDA(det, cudaGetLastError());
   return AG_OK;
 }
@@ -409,6 +456,8 @@ void ag_destroy(ag_detector* det) {
   cudaDeviceSynchronize();
   free_slot(det->slot[0]);
   free_slot(det->slot[1]);
+  if (det->board_stream) cudaStreamDestroy(det->board_stream);
+  for (auto e : det->ev_pool) cudaEventDestroy(e);
   cudaFree(det->d_codes);
   cudaFree(det->d_f32_a); cudaFree(det->d_f32_b); cudaFree(det->d_f32_c); cudaFree(det->d_taps);
   delete det;
@@ -426,6 +475,14 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "max_saddles")) {
     if (value < 16 || value > 16384) return fail(det, AG_ERR_INVALID, "max_saddles out of range");
     det->max_saddles = value;
+  } else if (!strcmp(key, "board_lattice")) {
+    if (value != 16 && value != 32 && value != 64) return fail(det, AG_ERR_INVALID, "board_lattice must be 16, 32 or 64");
+    det->board_lattice = value;
+    det->slot[0].cap_saddles = det->slot[1].cap_saddles = -1;  // force the board workspace to be rebuilt
+  } else if (!strcmp(key, "board_grid")) {
+    det->board_grid = value != 0;
+  } else if (!strcmp(key, "profile")) {
+    det->profile = value != 0;
   } else {
     return fail(det, AG_ERR_INVALID, "unknown option");
   }
@@ -433,6 +490,32 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
 }
 
 uint64_t ag_launch_count(const ag_detector* det) { return det ? det->launches : 0; }
+
+int ag_stage_times(ag_detector* det, double* ms_out, uint64_t* n_out, int reset) {
+  if (!det) return AG_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  AG_CUDA(det, cudaDeviceSynchronize());
+  for (size_t i = 1; i < det->ev_used; ++i) {
+    int st = det->ev_stage[i];
+    if (st < 0 || st >= 8) continue;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, det->ev_pool[i - 1], det->ev_pool[i]) == cudaSuccess) {
+      det->stage_ms[st] += ms;
+      det->stage_n[st] += 1;
+    }
+  }
+  det->ev_used = 0;
+  for (int i = 0; i < 8; ++i) {
+    if (ms_out) ms_out[i] = det->stage_ms[i];
+    if (n_out) n_out[i] = det->stage_n[i];
+    if (reset) {
+      det->stage_ms[i] = 0;
+      det->stage_n[i] = 0;
+    }
+  }
+  return AG_OK;
+}
 
 int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_stride, int n_frames,
                            int width, int height, size_t row_stride, int format, ag_tag* d_out,
@@ -446,18 +529,41 @@ int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
-  Slot& S = det->slot[0];
   const int chunk = (int)std::min<long>(det->chunk_frames, std::max(n_frames, 1));
-  if ((rc = ensure_slot(det, S, g, chunk, 1, false))) return rc;
-  cudaStream_t s = stream ? (cudaStream_t)stream : S.stream;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+  const int n_slots = n_frames > chunk ? 2 : 1;
+  for (int i = 0; i < n_slots; ++i)
+    if ((rc = ensure_slot(det, det->slot[i], g, chunk, 1, false, true))) return rc;
+  if (n_slots == 1 && det->slot[1].boards_pending) {
+    AG_CUDA(det, cudaEventSynchronize(det->slot[1].ev_boards));
+    det->slot[1].boards_pending = false;
+  }
+  if (!det->board_stream)
+    AG_CUDA(det, cudaStreamCreateWithFlags(&det->board_stream, cudaStreamNonBlocking));
+  cudaStream_t s = stream ? (cudaStream_t)stream : det->slot[0].stream;
+  cudaStream_t sb = det->board_stream;
+  // Two-deep software pipeline: the dense + sparse front end of chunk i+1 (stream s) overlaps
+  // the latency-bound board search of chunk i (stream sb).  Slots alternate; a slot is reused
+  // only after its board kernel has finished.
+  int which = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk, which ^= 1) {
+    Slot& S = det->slot[which];
     const int n = std::min(chunk, n_frames - f0);
     const uint8_t* in = (const uint8_t*)d_frames + (size_t)f0 * g.frame_stride;
     uint32_t* st = d_frame_status ? d_frame_status + f0 : S.d_status;
-    if ((rc = run_chunk(det, S, in, g, n, d_out + (size_t)f0 * cap_per_frame, cap_per_frame,
-                        d_n_per_frame + f0, st, false, s)))
+    if (S.boards_pending) AG_CUDA(det, cudaStreamWaitEvent(s, S.ev_boards, 0));
+    if ((rc = run_dense(det, S, in, g, n, true, s))) return rc;
+    if ((rc = run_sparse(det, S, g, n, st, s))) return rc;
+    AG_CUDA(det, cudaEventRecord(S.ev_front, s));
+    AG_CUDA(det, cudaStreamWaitEvent(sb, S.ev_front, 0));
+    if ((rc = run_boards(det, S, in, g, n, d_out + (size_t)f0 * cap_per_frame, cap_per_frame,
+                         d_n_per_frame + f0, st, false, sb)))
       return rc;
+    AG_CUDA(det, cudaEventRecord(S.ev_boards, sb));
+    S.boards_pending = true;
   }
+  // results become visible in the caller's stream order
+  for (int i = 0; i < n_slots; ++i)
+    if (det->slot[i].boards_pending) AG_CUDA(det, cudaStreamWaitEvent(s, det->slot[i].ev_boards, 0));
   return AG_OK;
 }
 

@@ -15,76 +15,144 @@ int upload_codes(const uint64_t* codes, int n) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-BoardWsLayout make_board_layout(int max_saddles) {
+constexpr int kBoardWarps = 4;  // warps per frame (one block per frame)
+
+BoardWsLayout make_board_layout(int max_saddles, int lattice) {
   BoardWsLayout L;
   const int N = max_saddles;
   const int Q = N / 4 + 2;
   L.max_saddles = N;
   L.max_quads = Q;
+  L.lattice = lattice;
+  L.warps = kBoardWarps;
+  const int cells = lattice * lattice;
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t r = o;
     o = align_up(o + bytes, 16);
     return r;
   };
-  for (int i = 0; i < 6; ++i) L.off_pos[i] = take(sizeof(float) * N);
-  for (int i = 0; i < 2; ++i) {
-    L.off_cell[i] = take(sizeof(int16_t) * agb::kCells);
-    L.off_quads[i] = take(sizeof(int16_t) * 4 * Q);
-    L.off_touched[i] = take(sizeof(int16_t) * agb::kCells);
-    L.off_active[i] = take(N);
-  }
-  L.off_stack = take(sizeof(int16_t) * 2 * (Q + 1));
+  // global workspace, per frame
+  for (int i = 0; i < 3; ++i) L.off_pos[i] = take(sizeof(float) * N);
+  L.off_best_quads = take(sizeof(int16_t) * 4 * Q);
+  L.off_best_touched = take(sizeof(int16_t) * cells);
+  L.off_best_vals = take(sizeof(int16_t) * cells);
   L.off_seeds = take(sizeof(int16_t) * N);
-  L.off_nn = take(sizeof(int16_t) * 64);
-  L.off_same = take(sizeof(int16_t) * 64);
-  L.off_diff = take(sizeof(int16_t) * 64);
-  L.off_samp = take(sizeof(int16_t) * 64);
-  L.off_hist = take(sizeof(int) * agb::kHistBins);
   L.off_remove = take(N);
   L.off_tag_valid = take(agb::kMaxCodes);
   L.off_tag_by_id = take(sizeof(agb::TagRec) * agb::kMaxCodes);
-  L.bytes_per_frame = align_up(o, 256);
+  // ... and per warp of the frame's block
+  L.off_warp0 = o;
+  size_t w = 0;
+  auto wtake = [&](size_t bytes) {
+    size_t r = w;
+    w = align_up(w + bytes, 16);
+    return r;
+  };
+  L.woff_quads = wtake(sizeof(int16_t) * 4 * Q);
+  L.woff_touched = wtake(sizeof(int16_t) * cells);
+  L.woff_sb_quads = wtake(sizeof(int16_t) * 4 * Q);
+  L.woff_sb_touched = wtake(sizeof(int16_t) * cells);
+  L.woff_sb_vals = wtake(sizeof(int16_t) * cells);
+  L.woff_stack = wtake(sizeof(int16_t) * 2 * (Q + 1));
+  L.bytes_per_warp = align_up(w, 64);
+  L.bytes_per_frame = align_up(L.off_warp0 + L.bytes_per_warp * kBoardWarps, 256);
+  // shared memory of the block: frame-wide part, then one part per warp
+  L.smem_saddles = 512;
+  L.grid_cap_cells = 1408;  // 1280x1024 at 32 px buckets = 1280 buckets
+  size_t sm = 0;
+  auto stake = [&](size_t bytes) {
+    size_t r = sm;
+    sm = align_up(sm + bytes, 16);
+    return r;
+  };
+  L.sm_pos = stake(sizeof(float) * 3 * L.smem_saddles);
+  L.sm_gstart = stake(sizeof(uint16_t) * (L.grid_cap_cells + 1));
+  L.sm_gitem = stake(sizeof(uint16_t) * L.smem_saddles);
+  L.sm_hist = stake(sizeof(int) * agb::kHistBins);
+  L.sm_ctl = stake(sizeof(int) * 16);
+  L.sm_warp0 = sm;
+  size_t sw = 0;
+  auto swtake = [&](size_t bytes) {
+    size_t r = sw;
+    sw = align_up(sw + bytes, 16);
+    return r;
+  };
+  L.smw_cell = swtake(sizeof(int16_t) * cells);
+  L.smw_active = swtake(sizeof(uint32_t) * ((N + 31) / 32));
+  L.smw_small = swtake(sizeof(int16_t) * 64 * 4);  // nn_idx, same, diff, samp
+  L.smem_per_warp = sw;
+  L.smem_per_block = L.sm_warp0 + sw * kBoardWarps;
   return L;
 }
 
-constexpr int kBoardWarpsPerBlock = 4;
-
-__global__ void __launch_bounds__(kBoardWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kBoardWarps * 32)
 k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
                 const ag_saddle* __restrict__ refined, const int* __restrict__ n_refined,
                 uint8_t* __restrict__ ws, BoardWsLayout L, int n_codes, int edge, int border,
                 int hamming, int max_boards, ag_tag* __restrict__ out, int cap,
                 int* __restrict__ n_out, uint32_t* __restrict__ frame_status,
-                int32_t* __restrict__ tap_quads, int* __restrict__ tap_n_quads, int tap_cap) {
+                int32_t* __restrict__ tap_quads, int* __restrict__ tap_n_quads, int tap_cap,
+                int use_grid) {
+  extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
-  const int f = blockIdx.x * kBoardWarpsPerBlock + (threadIdx.x >> 5);
-  if (f >= n_frames) return;
+  const int warp = threadIdx.x >> 5;
+  const int f = blockIdx.x;  // one block per frame
   uint8_t* W = ws + (size_t)f * L.bytes_per_frame;
+  uint8_t* WW = W + L.off_warp0 + (size_t)warp * L.bytes_per_warp;
+  uint8_t* SW = smem + L.sm_warp0 + (size_t)warp * L.smem_per_warp;
 
   agb::Frame F;
   F.lane = lane;
+  F.warp = warp;
+  F.n_warps = kBoardWarps;
+  F.lat = L.lattice;
+  F.lat_off = L.lattice / 2;
   F.n = n_refined[f];
-  F.sx = (float*)(W + L.off_pos[0]);
-  F.sy = (float*)(W + L.off_pos[1]);
-  F.st = (float*)(W + L.off_pos[2]);
-  F.sx2 = (float*)(W + L.off_pos[3]);
-  F.sy2 = (float*)(W + L.off_pos[4]);
-  F.st2 = (float*)(W + L.off_pos[5]);
-  for (int i = 0; i < 2; ++i) {
-    F.bs[i].cell = (int16_t*)(W + L.off_cell[i]);
-    F.bs[i].quads = (int16_t*)(W + L.off_quads[i]);
-    F.bs[i].touched = (int16_t*)(W + L.off_touched[i]);
-    F.bs[i].active = W + L.off_active[i];
-    F.bs[i].n_quads = F.bs[i].n_touched = F.bs[i].score = 0;
+  if (F.n <= L.smem_saddles) {  // the usual case: the saddle list lives in shared memory
+    F.sx = (float*)(smem + L.sm_pos);
+    F.sy = F.sx + L.smem_saddles;
+    F.st = F.sy + L.smem_saddles;
+  } else {
+    F.sx = (float*)(W + L.off_pos[0]);
+    F.sy = (float*)(W + L.off_pos[1]);
+    F.st = (float*)(W + L.off_pos[2]);
   }
-  F.stack = (int16_t*)(W + L.off_stack);
+  F.bs.cell = (int16_t*)(SW + L.smw_cell);
+  F.bs.active = (uint32_t*)(SW + L.smw_active);
+  F.bs.quads = (int16_t*)(WW + L.woff_quads);
+  F.bs.touched = (int16_t*)(WW + L.woff_touched);
+  F.bs.n_quads = F.bs.n_touched = F.bs.score = 0;
+  F.seedbest.quads = (int16_t*)(WW + L.woff_sb_quads);
+  F.seedbest.touched = (int16_t*)(WW + L.woff_sb_touched);
+  F.seedbest.vals = (int16_t*)(WW + L.woff_sb_vals);
+  F.seedbest.n_quads = F.seedbest.n_touched = F.seedbest.score = 0;
+  F.best.quads = (int16_t*)(W + L.off_best_quads);
+  F.best.touched = (int16_t*)(W + L.off_best_touched);
+  F.best.vals = (int16_t*)(W + L.off_best_vals);
+  F.best.n_quads = F.best.n_touched = F.best.score = 0;
+  F.stack = (int16_t*)(WW + L.woff_stack);
   F.seeds = (int16_t*)(W + L.off_seeds);
-  F.nn_idx = (int16_t*)(W + L.off_nn);
-  F.same = (int16_t*)(W + L.off_same);
-  F.diff = (int16_t*)(W + L.off_diff);
-  F.samp = (int16_t*)(W + L.off_samp);
-  F.hist = (int*)(W + L.off_hist);
+  // bucket grid: 32 px buckets, doubled until the grid fits its shared-memory budget
+  {
+    int bucket = 32;
+    while (((g.w + bucket - 1) / bucket) * ((g.h + bucket - 1) / bucket) > L.grid_cap_cells) bucket *= 2;
+    F.g_start = use_grid ? (uint16_t*)(smem + L.sm_gstart) : nullptr;
+    F.g_item = (uint16_t*)(smem + L.sm_gitem);
+    F.g_nx = (g.w + bucket - 1) / bucket;
+    F.g_ny = (g.h + bucket - 1) / bucket;
+    F.g_cap_cells = L.grid_cap_cells;
+    F.g_cap_items = L.smem_saddles;
+    F.g_inv = 1.0f / (float)bucket;
+    F.g_on = 0;
+  }
+  F.hist = (int*)(smem + L.sm_hist);
+  F.ctl = (int*)(smem + L.sm_ctl);
+  F.w_score = F.ctl + 8;
+  F.nn_idx = (int16_t*)(SW + L.smw_small);
+  F.same = F.nn_idx + 64;
+  F.diff = F.same + 64;
+  F.samp = F.diff + 64;
   F.remove = W + L.off_remove;
   F.max_quads = L.max_quads;
   F.img = frames + (size_t)f * g.frame_stride;
@@ -104,31 +172,32 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.tap_cap = tap_cap;
   F.status = 0;
 
-  // workspace init: lattice cells 0, every saddle active, no tags
+  // init: every warp clears its lattice and activates every saddle; warp 0 clears the tag map
   {
-    uint4 z = make_uint4(0, 0, 0, 0);
-    for (int b = 0; b < 2; ++b) {
-      uint4* c = (uint4*)F.bs[b].cell;
-      for (int i = lane; i < agb::kCells * 2 / 16; i += 32) c[i] = z;
-      uint32_t* a = (uint32_t*)F.bs[b].active;
-      for (int i = lane; i < (L.max_saddles + 3) / 4; i += 32) a[i] = 0x01010101u;
+    const int cells = L.lattice * L.lattice;
+    uint32_t* c = (uint32_t*)F.bs.cell;
+    for (int i = lane; i < cells / 2; i += 32) c[i] = 0u;
+    for (int i = lane; i < (L.max_saddles + 31) / 32; i += 32) F.bs.active[i] = 0xffffffffu;
+    if (warp == 0) {
+      uint32_t* tv = (uint32_t*)F.tag_valid;
+      for (int i = lane; i < agb::kMaxCodes / 4; i += 32) tv[i] = 0;
+      if (F.tap_n_quads && lane == 0) *F.tap_n_quads = 0;
+      if (lane < 16) F.ctl[lane] = 0;
     }
-    uint32_t* tv = (uint32_t*)F.tag_valid;
-    for (int i = lane; i < agb::kMaxCodes / 4; i += 32) tv[i] = 0;
-    if (F.tap_n_quads && lane == 0) *F.tap_n_quads = 0;
   }
-  // saddles AoS -> SoA
+  // saddles AoS -> SoA (block-wide)
   const ag_saddle* S = refined + (size_t)f * L.max_saddles;
-  for (int i = lane; i < F.n; i += 32) {
+  for (int i = threadIdx.x; i < F.n; i += kBoardWarps * 32) {
     ag_saddle s = S[i];
     F.sx[i] = s.x;
     F.sy[i] = s.y;
     F.st[i] = s.theta;
   }
-  __syncwarp();
+  __syncthreads();
 
   agb::detect_boards(F, max_boards);
 
+  if (warp != 0) return;
   // emit the map in ascending id order
   ag_tag* O = out + (size_t)f * cap;
   int n = 0;
@@ -159,11 +228,21 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
                          const ag_saddle* refined, const int* n_refined, uint8_t* ws,
                          const BoardWsLayout& L, int n_codes, int edge, int border, int hamming,
                          int max_boards, ag_tag* out, int cap, int* n_out, uint32_t* frame_status,
-                         int32_t* tap_quads, int* tap_n_quads, int tap_cap, cudaStream_t s) {
-  int blocks = (n_frames + kBoardWarpsPerBlock - 1) / kBoardWarpsPerBlock;
-  k_boards_decode<<<blocks, kBoardWarpsPerBlock * 32, 0, s>>>(
+                         int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid,
+                         cudaStream_t s) {
+  const int blocks = n_frames;
+  if (blocks == 0) return 0;
+  const size_t smem = L.smem_per_block;
+  static size_t smem_configured = 0;
+  if (smem > smem_configured) {
+    if (cudaFuncSetAttribute(k_boards_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return 0;
+    smem_configured = smem;
+  }
+  k_boards_decode<<<blocks, kBoardWarps * 32, smem, s>>>(
       frames, g, n_frames, refined, n_refined, ws, L, n_codes, edge, border, hamming, max_boards,
-      out, cap, n_out, frame_status, tap_quads, tap_n_quads, tap_cap);
+      out, cap, n_out, frame_status, tap_quads, tap_n_quads, tap_cap, use_grid);
   return 1;
 }
 

@@ -1,9 +1,11 @@
 // Board assembly and tag decoding for ONE frame, written once for two compilation modes:
 //
-//   * device (nvcc, __CUDA_ARCH__): executed by one warp per frame.  All 32 lanes run the
-//     same control flow on the same data ("warp-uniform"); the lanes split the data-parallel
-//     inner loops (nearest-neighbour scans, candidate-quad tests, bit sampling, Hamming
-//     search) and lane 0 performs the stores.
+//   * device (nvcc, __CUDA_ARCH__): one thread block of a few warps per frame.  Inside a warp
+//     all 32 lanes run the same control flow on the same data ("warp-uniform"); the lanes
+//     split the data-parallel inner loops (neighbour searches, candidate-quad tests, bit
+//     sampling, Hamming search) and lane 0 performs the stores.  The warps of a block work on
+//     different seed saddles of try_find_best_board at the same time (speculatively: seeds are
+//     independent until their results are merged in the reference's order).
 //   * host (tests/host_board_test.cpp): the same source with a warp of one lane, so the
 //     control logic can be unit-tested against the oracle in a container without a GPU.
 //     That build is test-only; the shipped library has no CPU path.
@@ -27,15 +29,16 @@
 
 #if defined(__CUDACC__)
 #define AGB_FN __host__ __device__ inline
+#define AGB_NOINLINE __host__ __device__ __noinline__
 #else
 #define AGB_FN inline
+#define AGB_NOINLINE __attribute__((noinline))
 #endif
 
 namespace agb {
 
-constexpr int kGrid = 64;  // lattice of tag positions, coordinates -32..31 on both axes
-constexpr int kGridOff = kGrid / 2;
-constexpr int kCells = kGrid * kGrid;
+constexpr int kMaxLattice = 64;  // lattice of tag positions: at most 64 x 64 (-32..31 per axis)
+constexpr int kCells = kMaxLattice * kMaxLattice;
 constexpr int kHistBins = 192;  // round(theta) + 90 in [0, 180]
 constexpr int kMaxCodes = 640;  // >= 587
 constexpr float kPi = 3.14159274101257324f;
@@ -46,21 +49,40 @@ struct TagRec {  // == ag_tag
   float xy[8];
 };
 
-// One board under construction (board.rs:18-25).  Arrays live in the per-frame workspace;
-// the counters are warp-uniform registers.
+// The board under construction (board.rs:18-25).  The lattice and the active mask are the
+// randomly accessed structures (shared memory on the device); the counters are warp-uniform
+// registers.
 struct BoardState {
   int16_t* cell;     // [kCells] 0 = never visited, -1 = None, q+1 = Some(quad q)
+  uint32_t* active;  // [max_saddles / 32] bit i = active_idxs[i]
   int16_t* quads;    // [max_quads][4] saddle indices
   int16_t* touched;  // [kCells] indices of non-zero cells (cheap reset)
-  uint8_t* active;   // [max_saddles] active_idxs
+  int n_quads, n_touched, score;
+};
+// Copy of the best board so far (what `best_board_option` holds in detector.rs:599-626).
+struct BoardRecord {
+  int16_t* quads;    // [max_quads][4]
+  int16_t* touched;  // [kCells] cell indices
+  int16_t* vals;     // [kCells] cell values
   int n_quads, n_touched, score;
 };
 
 struct Frame {
   int n;                 // saddles in the current round
-  float *sx, *sy, *st;   // current round (SoA): position, theta
-  float *sx2, *sy2, *st2;  // the other half of the ping-pong
-  BoardState bs[2];
+  float *sx, *sy, *st;   // saddles (SoA): position, theta
+  BoardState bs;        // this warp's live board
+  BoardRecord seedbest; // this warp's best board of the seed it is processing
+  BoardRecord best;     // the frame's best board so far (arrays shared by the block)
+  int lat, lat_off;     // lattice side (power of two <= kMaxLattice) and its centre offset
+  int warp, n_warps;    // warp index inside the frame's block (0 / 1 on the host)
+  int* w_score;         // [n_warps] shared: per-warp result of the current wave of seeds
+  int* ctl;             // [8] shared: 0 n_seeds, 1 n after compaction, 2..4 best n_quads/n_touched/score
+  // uniform bucket grid over the saddles of the current round (null = brute-force search)
+  uint16_t* g_start;  // [g_nx * g_ny + 1] first entry of each bucket in g_item
+  uint16_t* g_item;   // [n] saddle indices sorted by bucket
+  int g_nx, g_ny, g_cap_cells, g_cap_items;
+  int g_on;           // 1 = the grid holds the current round's saddles (block-uniform)
+  float g_inv;        // 1 / bucket size in pixels
   int16_t* stack;   // [2 * (max_quads + 1)] DFS stack: cell index, next direction
   int16_t* seeds;   // [max_saddles]
   int16_t* nn_idx;  // [64] 50-NN result
@@ -91,10 +113,12 @@ struct Frame {
 // ---- warp plumbing ---------------------------------------------------------------------
 #if AGB_DEVICE
 #define AGB_SYNC() __syncwarp()
+#define AGB_BLOCK_SYNC() __syncthreads()
 #define AGB_LANES 32
 AGB_FN unsigned agb_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 #else
 #define AGB_SYNC() ((void)0)
+#define AGB_BLOCK_SYNC() ((void)0)
 #define AGB_LANES 1
 AGB_FN unsigned agb_ballot(bool p) { return p ? 1u : 0u; }
 #endif
@@ -157,15 +181,42 @@ AGB_FN float angle_degree(float ax, float ay, float bx, float by) {
   return fdiv(fmul(atan2_cr(y, x), 180.0f), kPi);
 }
 
+// Cheap f32 evaluation of the same angle (same exact y, x operands; atan2f instead of the f64
+// route).  Its error is below 1e-4 degree, so a comparison against a threshold is decided by it
+// with certainty unless the value lies within kGuardDeg of the threshold; only then is the
+// exact expression evaluated.  The verdicts are therefore identical to the exact path.
+constexpr float kGuardDeg = 4.0e-3f;
+AGB_FN float angle_degree_fast(float ax, float ay, float bx, float by) {
+  float y = fsub(fmul(by, ax), fmul(bx, ay));
+  float x = fadd(fmul(ax, bx), fmul(ay, by));
+  return atan2f(y, x) * 57.2957795f;
+}
+// |angle(a) - angle(b)| > limit ?  with a = angle(p, q), b = angle(r, s)
+AGB_NOINLINE bool angle_gap_exceeds(float px, float py, float qx, float qy, float rx, float ry,
+                                    float sx, float sy, float limit) {
+  const float fa = angle_degree_fast(px, py, qx, qy), fb = angle_degree_fast(rx, ry, sx, sy);
+  const float g = fabsf(fa - fb);
+  if (g > limit + kGuardDeg) return true;
+  if (g < limit - kGuardDeg) return false;
+  return fabsf(fsub(angle_degree(px, py, qx, qy), angle_degree(rx, ry, sx, sy))) > limit;
+}
+
 // ---- saddle.rs:17-67, split in two so the (s0, s1)-only test can be hoisted ---------------
-AGB_FN bool quad_diag_ok(const Frame& F, int s0, int s1) {  // "filter white block", :26-38
+AGB_NOINLINE bool quad_diag_ok(const Frame& F, int s0, int s1) {  // "filter white block", :26-38
   float v02x = fsub(F.sx[s1], F.sx[s0]), v02y = fsub(F.sy[s1], F.sy[s0]);
   float th = fmul(fdiv(F.st[s0], 180.0f), kPi);
+  {
+    const float fa = fabsf(angle_degree_fast(v02x, v02y, cosf(th), sinf(th)));
+    if (fa > 60.0f + kGuardDeg && fa < 120.0f - kGuardDeg) return true;
+    if (fa < 60.0f - kGuardDeg || fa > 120.0f + kGuardDeg) return false;
+  }
   float vx = cos_cr(th), vy = sin_cr(th);
   float a = fabsf(angle_degree(v02x, v02y, vx, vy));
   return a >= 60.0f && a <= 120.0f;
 }
-AGB_FN bool quad_rest_ok(const Frame& F, int s0, int d0, int s1, int d1) {
+// The remaining gates of is_valid_quad.  They only ever reject, so they are evaluated
+// cheapest-first; the verdict equals the reference's (saddle.rs:18-66).
+AGB_NOINLINE bool quad_rest_ok(const Frame& F, int s0, int d0, int s1, int d1) {
   if (theta_distance_degree(F.st[d0], F.st[d1]) > 5.0f) return false;
   float v01x = fsub(F.sx[d0], F.sx[s0]), v01y = fsub(F.sy[d0], F.sy[s0]);
   float v03x = fsub(F.sx[d1], F.sx[s0]), v03y = fsub(F.sy[d1], F.sy[s0]);
@@ -178,13 +229,10 @@ AGB_FN bool quad_rest_ok(const Frame& F, int s0, int d0, int s1, int d1) {
   float c01 = cross2(v01x, v01y, v12x, v12y);
   float c12 = cross2(v12x, v12y, v23x, v23y);
   if (fmul(c01, c12) < 0.0f) return false;
-  float v30x = fsub(F.sx[s0], F.sx[d1]), v30y = fsub(F.sy[s0], F.sy[d1]);
-  float a0 = angle_degree(v01x, v01y, v12x, v12y);
-  float a1 = angle_degree(v12x, v12y, v23x, v23y);
-  float a2 = angle_degree(v23x, v23y, v30x, v30y);
-  float a3 = angle_degree(v30x, v30y, v01x, v01y);
-  if (fabsf(fsub(a0, a2)) > 10.0f || fabsf(fsub(a1, a3)) > 10.0f) return false;
   if (dot2(v01x, v01y, v02x, v02y) < 0.0f || dot2(v03x, v03y, v02x, v02y) < 0.0f) return false;
+  float v30x = fsub(F.sx[s0], F.sx[d1]), v30y = fsub(F.sy[s0], F.sy[d1]);
+  if (angle_gap_exceeds(v01x, v01y, v12x, v12y, v23x, v23y, v30x, v30y, 10.0f)) return false;  // a0, a2
+  if (angle_gap_exceeds(v12x, v12y, v23x, v23y, v30x, v30y, v01x, v01y, 10.0f)) return false;  // a1, a3
   return true;
 }
 AGB_FN bool is_valid_quad(const Frame& F, int s0, int d0, int s1, int d1) {
@@ -215,13 +263,56 @@ AGB_FN void warp_argmin(float& d, int& i) {
 AGB_FN void warp_argmin(float&, int&) {}
 #endif
 
+// Bucket grid: saddles counting-sorted by (floor(y * inv), floor(x * inv)).  A radius query
+// then only visits the buckets overlapping the query square, which still contains every point
+// within the radius, so results are identical to the exhaustive search.
+AGB_FN int grid_bucket(const Frame& F, float x, float y) {
+  int bx = (int)(x * F.g_inv), by = (int)(y * F.g_inv);
+  bx = bx < 0 ? 0 : (bx >= F.g_nx ? F.g_nx - 1 : bx);
+  by = by < 0 ? 0 : (by >= F.g_ny ? F.g_ny - 1 : by);
+  return by * F.g_nx + bx;
+}
+AGB_NOINLINE void grid_build(Frame& F) {
+  F.g_on = 0;
+  if (!F.g_start) return;
+  const int nc = F.g_nx * F.g_ny;
+  // too large for the on-chip grid: queries fall back to the exhaustive scan
+  if (F.n > F.g_cap_items || nc > F.g_cap_cells || F.n > 65535) return;
+  F.g_on = 1;
+  for (int c = F.lane; c <= nc; c += AGB_LANES) F.g_start[c] = 0;
+  AGB_SYNC();
+  // histogram into g_start[bucket + 1]
+  if (F.lane == 0)
+    for (int i = 0; i < F.n; ++i) F.g_start[grid_bucket(F, F.sx[i], F.sy[i]) + 1] += 1;
+  AGB_SYNC();
+  // inclusive scan (lane 0; a few thousand adds at most, once per round)
+  if (F.lane == 0) {
+    unsigned run = 0;
+    for (int c = 1; c <= nc; ++c) {
+      run += F.g_start[c];
+      F.g_start[c] = (uint16_t)run;
+    }
+    // fill from the back so that every bucket ends up in ascending saddle order
+    for (int i = F.n - 1; i >= 0; --i) {
+      const int b = grid_bucket(F, F.sx[i], F.sy[i]);
+      // entries of bucket b occupy [start[b], start[b+1]); use start[b+1] as a moving cursor
+      F.g_item[--F.g_start[b + 1]] = (uint16_t)i;
+    }
+    // the cursors now equal the bucket starts shifted by one slot: g_start[b + 1] == start of b
+    // restore the canonical layout g_start[b] = start of b
+    for (int c = 0; c < nc; ++c) F.g_start[c] = F.g_start[c + 1];
+    F.g_start[nc] = (uint16_t)F.n;
+  }
+  AGB_SYNC();
+}
+
 // The (up to) 3 nearest saddles with d2 <= r2, ascending.  Equals "3 nearest overall, then
 // drop those outside the radius" (board.rs:192-200): points inside the radius always precede
 // points outside it in the distance order.
-AGB_FN int nearest3_within(const Frame& F, float qx, float qy, float r2, int out[3]) {
+AGB_NOINLINE int nearest3_within(const Frame& F, float qx, float qy, float r2, int out[3]) {
   float bd[3] = {3.0e38f, 3.0e38f, 3.0e38f};
   int bi[3] = {kNone, kNone, kNone};
-  for (int i = F.lane; i < F.n; i += AGB_LANES) {
+  auto consider = [&](int i) {
     float d = dist2(F, qx, qy, i);
     if (d <= r2 && nn_less(d, i, bd[2], bi[2])) {
       bd[2] = d; bi[2] = i;
@@ -234,12 +325,34 @@ AGB_FN int nearest3_within(const Frame& F, float qx, float qy, float r2, int out
         int u = bi[0]; bi[0] = bi[1]; bi[1] = u;
       }
     }
+  };
+  if (F.g_on && r2 >= 0.0f && r2 < 1.0e12f) {
+    // conservative square around the query: r slightly enlarged, bucket range clamped
+    const float r = sqrtf(r2) * 1.0001f + 0.01f;
+    int x0 = (int)floorf((qx - r) * F.g_inv), x1 = (int)floorf((qx + r) * F.g_inv);
+    int y0 = (int)floorf((qy - r) * F.g_inv), y1 = (int)floorf((qy + r) * F.g_inv);
+    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
+    x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    if (bw > 0 && bh > 0) {
+      // rows of buckets are contiguous in g_item: one (start, end) range per bucket row
+      for (int row = F.lane; row < bh; row += AGB_LANES) {
+        const int b0 = (y0 + row) * F.g_nx + x0;
+        const int e0 = F.g_start[b0], e1 = F.g_start[b0 + bw];
+        for (int e = e0; e < e1; ++e) consider(F.g_item[e]);
+      }
+    }
+  } else {
+    for (int i = F.lane; i < F.n; i += AGB_LANES) consider(i);
   }
   int cnt = 0;
   // merge the per-lane sorted triples: three rounds of warp arg-min over the lanes' heads
   for (int r = 0; r < 3; ++r) {
     float d = bd[0];
     int i = bi[0];
+#if AGB_DEVICE
+    if (__ballot_sync(0xffffffffu, i != kNone) == 0u) break;
+#endif
     warp_argmin(d, i);
     if (i == kNone) break;  // warp-uniform
     out[cnt++] = i;
@@ -252,8 +365,49 @@ AGB_FN int nearest3_within(const Frame& F, float qx, float qy, float r2, int out
   return cnt;
 }
 
+// Same query evaluated by ONE lane without warp collectives (four of them run side by side in
+// try_expand_one).  Returns the count; out[] ascending by (d2, idx).
+AGB_FN int nearest3_within_single(const Frame& F, float qx, float qy, float r2, int out[3]) {
+  float bd[3] = {3.0e38f, 3.0e38f, 3.0e38f};
+  int bi[3] = {kNone, kNone, kNone};
+  auto consider = [&](int i) {
+    float d = dist2(F, qx, qy, i);
+    if (d <= r2 && nn_less(d, i, bd[2], bi[2])) {
+      bd[2] = d; bi[2] = i;
+      if (nn_less(bd[2], bi[2], bd[1], bi[1])) {
+        float t = bd[1]; bd[1] = bd[2]; bd[2] = t;
+        int u = bi[1]; bi[1] = bi[2]; bi[2] = u;
+      }
+      if (nn_less(bd[1], bi[1], bd[0], bi[0])) {
+        float t = bd[0]; bd[0] = bd[1]; bd[1] = t;
+        int u = bi[0]; bi[0] = bi[1]; bi[1] = u;
+      }
+    }
+  };
+  if (F.g_on && r2 >= 0.0f && r2 < 1.0e12f) {
+    const float r = sqrtf(r2) * 1.0001f + 0.01f;
+    int x0 = (int)floorf((qx - r) * F.g_inv), x1 = (int)floorf((qx + r) * F.g_inv);
+    int y0 = (int)floorf((qy - r) * F.g_inv), y1 = (int)floorf((qy + r) * F.g_inv);
+    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
+    x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+    const int bw = x1 - x0 + 1;
+    if (bw > 0)
+      for (int by = y0; by <= y1; ++by) {
+        const int b0 = by * F.g_nx + x0;
+        const int e1 = F.g_start[b0 + bw];
+        for (int e = F.g_start[b0]; e < e1; ++e) consider(F.g_item[e]);
+      }
+  } else {
+    for (int i = 0; i < F.n; ++i) consider(i);
+  }
+  int cnt = 0;
+  for (int r = 0; r < 3; ++r)
+    if (bi[r] != kNone) out[cnt++] = bi[r];
+  return cnt;
+}
+
 // Nearest single saddle (board.rs:88).
-AGB_FN int nearest1(const Frame& F, float qx, float qy) {
+AGB_NOINLINE int nearest1(const Frame& F, float qx, float qy) {
   float bd = 3.0e38f;
   int bi = kNone;
   for (int i = F.lane; i < F.n; i += AGB_LANES) {
@@ -267,7 +421,7 @@ AGB_FN int nearest1(const Frame& F, float qx, float qy) {
 // The k (<= 64) nearest saddles of a point, ascending, written to F.nn_idx; returns the count.
 // Selection by repeated extraction: each round takes the smallest (d2, idx) strictly greater
 // than the previous pick.
-AGB_FN int nearest_k(Frame& F, float qx, float qy, int k) {
+AGB_NOINLINE int nearest_k(Frame& F, float qx, float qy, int k) {
   int cnt = 0;
   float last_d = -1.0f;
   int last_i = -1;
@@ -292,68 +446,140 @@ AGB_FN int nearest_k(Frame& F, float qx, float qy, int k) {
 
 // ---- Board (board.rs) -----------------------------------------------------------------------
 // x is the major axis so that ascending cell index == ascending (x, y).
-AGB_FN int cell_index(int x, int y) { return (x + kGridOff) * kGrid + (y + kGridOff); }
-AGB_FN int cell_x(int ci) { return ci / kGrid - kGridOff; }
-AGB_FN int cell_y(int ci) { return ci % kGrid - kGridOff; }
-AGB_FN bool cell_in_range(int x, int y) {
-  return x >= -kGridOff && x < kGridOff && y >= -kGridOff && y < kGridOff;
+AGB_FN int cell_index(const Frame& F, int x, int y) { return (x + F.lat_off) * F.lat + (y + F.lat_off); }
+AGB_FN int cell_x(const Frame& F, int ci) { return ci / F.lat - F.lat_off; }
+AGB_FN int cell_y(const Frame& F, int ci) { return ci % F.lat - F.lat_off; }
+AGB_FN bool cell_in_range(const Frame& F, int x, int y) {
+  return x >= -F.lat_off && x < F.lat_off && y >= -F.lat_off && y < F.lat_off;
 }
+
+AGB_FN bool is_active(const BoardState& B, int i) { return (B.active[i >> 5] >> (i & 31)) & 1u; }
+// single-writer (lane 0) updates
+AGB_FN void clear_active(BoardState& B, int i) { B.active[i >> 5] &= ~(1u << (i & 31)); }
 
 // Undo everything the previous build on this state did (cells back to 0, saddles active).
 AGB_FN void board_reset(Frame& F, BoardState& B) {
   for (int t = F.lane; t < B.n_touched; t += AGB_LANES) B.cell[B.touched[t]] = 0;
-  for (int t = F.lane; t < B.n_quads * 4; t += AGB_LANES) B.active[B.quads[t]] = 1;
+  AGB_SYNC();
+  if (F.lane == 0)
+    for (int t = 0; t < B.n_quads * 4; ++t) {
+      const int i = B.quads[t];
+      B.active[i >> 5] |= 1u << (i & 31);
+    }
   AGB_SYNC();
   B.n_touched = 0;
   B.n_quads = 0;
   B.score = 0;
 }
 
-// find_closest_potential_saddle_idxs (board.rs:177-234) for the edge s0 -> s1.
-AGB_FN void find_closest(const Frame& F, const BoardState& B, int s0, int s1, int out0[3], int* n0,
-                         int out1[3], int* n1) {
-  const float ratio0 = fadd(1.0f, 0.3f);  // 1.0 + spacing_ratio; detector.rs:621 passes 0.3
-  float dx = fsub(F.sx[s0], F.sx[s1]), dy = fsub(F.sy[s0], F.sy[s1]);
-  float radius_sq = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
-  float v10x = fsub(F.sx[s1], F.sx[s0]), v10y = fsub(F.sy[s1], F.sy[s0]);
-  float nv0x = fadd(F.sx[s0], fmul(v10x, ratio0)), nv0y = fadd(F.sy[s0], fmul(v10y, ratio0));
-  float nv1x = fadd(F.sx[s1], fmul(v10x, ratio0)), nv1y = fadd(F.sy[s1], fmul(v10y, ratio0));
-  int nn[3];
-  int c = nearest3_within(F, nv0x, nv0y, radius_sq, nn);
-  int k0 = 0;
-  for (int j = 0; j < c; ++j)
-    if (B.active[nn[j]] && theta_distance_degree(F.st[s0], F.st[nn[j]]) < 5.0f) out0[k0++] = nn[j];
-  c = nearest3_within(F, nv1x, nv1y, radius_sq, nn);
-  int k1 = 0;
-  for (int j = 0; j < c; ++j)
-    if (B.active[nn[j]] && theta_distance_degree(F.st[s1], F.st[nn[j]]) < 5.0f) out1[k1++] = nn[j];
-  *n0 = k0;
-  *n1 = k1;
+// best_board_option = Some(board): keep a copy of the live board.
+AGB_FN void board_save(Frame& F, const BoardState& B, BoardRecord& R) {
+  for (int t = F.lane; t < B.n_quads * 4; t += AGB_LANES) R.quads[t] = B.quads[t];
+  for (int t = F.lane; t < B.n_touched; t += AGB_LANES) {
+    const int ci = B.touched[t];
+    R.touched[t] = (int16_t)ci;
+    R.vals[t] = B.cell[ci];
+  }
+  R.n_quads = B.n_quads;
+  R.n_touched = B.n_touched;
+  R.score = B.score;
+  AGB_SYNC();
+}
+// Make the saved board the live one again (its active mask is not needed any more).
+AGB_FN void board_load(Frame& F, BoardState& B, const BoardRecord& R) {
+  board_reset(F, B);
+  for (int t = F.lane; t < R.n_quads * 4; t += AGB_LANES) B.quads[t] = R.quads[t];
+  for (int t = F.lane; t < R.n_touched; t += AGB_LANES) {
+    B.touched[t] = R.touched[t];
+    B.cell[R.touched[t]] = R.vals[t];
+  }
+  B.n_quads = R.n_quads;
+  B.n_touched = R.n_touched;
+  B.score = R.score;
+  AGB_SYNC();
 }
 
-// try_expand_one (board.rs:153-176)
-AGB_FN bool try_expand_one(const Frame& F, const BoardState& B, const int q[4], int out[4]) {
-  int a0[3], a1[3], a2[3], a3[3], n0, n1, n2, n3;
-  find_closest(F, B, q[0], q[1], a0, &n0, a1, &n1);
-  if (n0 == 0 || n1 == 0) return false;  // the nested loops below would be empty
-  find_closest(F, B, q[3], q[2], a3, &n3, a2, &n2);
-  for (int i0 = 0; i0 < n0; ++i0)
-    for (int i1 = 0; i1 < n1; ++i1)
-      for (int i2 = 0; i2 < n2; ++i2)
-        for (int i3 = 0; i3 < n3; ++i3)
-          if (is_valid_quad(F, a0[i0], a1[i1], a2[i2], a3[i3])) {
-            out[0] = a0[i0]; out[1] = a1[i1]; out[2] = a2[i2]; out[3] = a3[i3];
-            return true;
-          }
+// One of the four neighbour searches of try_expand_one: find_closest_potential_saddle_idxs
+// (board.rs:177-234) for the edge a -> b, candidates for the successor of `self_is_b ? b : a`.
+// Runs on a single lane.
+AGB_FN int closest_candidates_single(const Frame& F, const BoardState& B, int a, int b, bool self_is_b,
+                                     int out[3]) {
+  const float ratio0 = fadd(1.0f, 0.3f);  // 1.0 + spacing_ratio; detector.rs:621 passes 0.3
+  float dx = fsub(F.sx[a], F.sx[b]), dy = fsub(F.sy[a], F.sy[b]);
+  float radius_sq = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
+  float v10x = fsub(F.sx[b], F.sx[a]), v10y = fsub(F.sy[b], F.sy[a]);
+  const int self = self_is_b ? b : a;
+  float px = fadd(F.sx[self], fmul(v10x, ratio0)), py = fadd(F.sy[self], fmul(v10y, ratio0));
+  int nn[3];
+  const int c = nearest3_within_single(F, px, py, radius_sq, nn);
+  int k = 0;
+  for (int j = 0; j < c; ++j)
+    if (is_active(B, nn[j]) && theta_distance_degree(F.st[self], F.st[nn[j]]) < 5.0f) out[k++] = nn[j];
+  return k;
+}
+
+// try_expand_one (board.rs:153-176).  The four neighbour searches are independent: lanes 0..3
+// run one each; the candidate 4-tuples are then tested in the reference's nested-loop order
+// (i0 outermost, i3 innermost), 32 at a time, and the first valid one wins.
+AGB_NOINLINE bool try_expand_one(const Frame& F, const BoardState& B, const int q[4], int out[4]) {
+  int cand[4][3], cnt[4];
+#if AGB_DEVICE
+  {
+    int mine[3] = {0, 0, 0}, mycnt = 0;
+    if (F.lane < 4) {
+      // lane 0: new_s0s (edge s0->s1, from s0)   lane 1: new_s1s (edge s0->s1, from s1)
+      // lane 2: new_s2s (edge s3->s2, from s2)   lane 3: new_s3s (edge s3->s2, from s3)
+      const int a = F.lane < 2 ? q[0] : q[3], b = F.lane < 2 ? q[1] : q[2];
+      const bool self_is_b = (F.lane == 1) || (F.lane == 2);
+      mycnt = closest_candidates_single(F, B, a, b, self_is_b, mine);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      cnt[k] = __shfl_sync(0xffffffffu, mycnt, k);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) cand[k][j] = __shfl_sync(0xffffffffu, mine[j], k);
+    }
+  }
+#else
+  cnt[0] = closest_candidates_single(F, B, q[0], q[1], false, cand[0]);
+  cnt[1] = closest_candidates_single(F, B, q[0], q[1], true, cand[1]);
+  cnt[2] = closest_candidates_single(F, B, q[3], q[2], true, cand[2]);
+  cnt[3] = closest_candidates_single(F, B, q[3], q[2], false, cand[3]);
+#endif
+  const int total = cnt[0] * cnt[1] * cnt[2] * cnt[3];
+  for (int base = 0; base < total; base += AGB_LANES) {
+    const int c = base + F.lane;
+    bool valid = false;
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    if (c < total) {
+      int r = c;
+      i3 = r % cnt[3]; r /= cnt[3];
+      i2 = r % cnt[2]; r /= cnt[2];
+      i1 = r % cnt[1]; r /= cnt[1];
+      i0 = r;
+      valid = is_valid_quad(F, cand[0][i0], cand[1][i1], cand[2][i2], cand[3][i3]);
+    }
+    const unsigned m = agb_ballot(valid);
+    if (m) {
+      const int first = base + agb_ffs(m);
+      int r = first;
+      i3 = r % cnt[3]; r /= cnt[3];
+      i2 = r % cnt[2]; r /= cnt[2];
+      i1 = r % cnt[1]; r /= cnt[1];
+      i0 = r;
+      out[0] = cand[0][i0]; out[1] = cand[1][i1]; out[2] = cand[2][i2]; out[3] = cand[3][i3];
+      return true;
+    }
+  }
   return false;
 }
 
 // Board::new + try_expand (board.rs:27-48, :114-152); the recursion runs on an explicit stack.
-AGB_FN void board_build(Frame& F, BoardState& B, const int quad[4]) {
+AGB_NOINLINE void board_build(Frame& F, BoardState& B, const int quad[4]) {
   board_reset(F, B);
-  const int c0 = cell_index(0, 0);
+  const int c0 = cell_index(F, 0, 0);
   if (F.lane == 0) {
-    for (int j = 1; j < 4; ++j) B.active[quad[j]] = 0;  // quad[0] stays active, as in :35-37
+    for (int j = 1; j < 4; ++j) clear_active(B, quad[j]);  // quad[0] stays active, as in :35-37
     for (int j = 0; j < 4; ++j) B.quads[j] = (int16_t)quad[j];
     B.cell[c0] = 1;
     B.touched[0] = (int16_t)c0;
@@ -374,7 +600,7 @@ AGB_FN void board_build(Frame& F, BoardState& B, const int quad[4]) {
       continue;
     }
     if (F.lane == 0) F.stack[2 * (depth - 1) + 1] = (int16_t)(i + 1);
-    const int bx = cell_x(ci), by = cell_y(ci);
+    const int bx = cell_x(F, ci), by = cell_y(F, ci);
     const int qi = B.cell[ci] - 1;
     int qs[4];
     for (int j = 0; j < 4; ++j) qs[j] = B.quads[qi * 4 + ((j + i) & 3)];  // rotate_left(i)
@@ -384,11 +610,11 @@ AGB_FN void board_build(Frame& F, BoardState& B, const int quad[4]) {
     else if (i == 2) nx = bx - 1;
     else ny = by + 1;
     AGB_SYNC();
-    if (!cell_in_range(nx, ny)) {
+    if (!cell_in_range(F, nx, ny)) {
       F.status |= 4u;  // AG_FRAME_BOARD_OVERFLOW
       continue;
     }
-    const int nci = cell_index(nx, ny);
+    const int nci = cell_index(F, nx, ny);
     const int cur = B.cell[nci];
     if (cur > 0) continue;  // already Some (board.rs:131-135)
     int nq[4];
@@ -403,7 +629,7 @@ AGB_FN void board_build(Frame& F, BoardState& B, const int quad[4]) {
       for (int j = 0; j < 4; ++j) v[(j + i) & 3] = nq[j];  // rotate_right(i)
       if (F.lane == 0) {
         for (int j = 0; j < 4; ++j) {
-          B.active[v[j]] = 0;
+          clear_active(B, v[j]);
           B.quads[B.n_quads * 4 + j] = (int16_t)v[j];
         }
         B.cell[nci] = (int16_t)(B.n_quads + 1);
@@ -423,22 +649,22 @@ AGB_FN void board_build(Frame& F, BoardState& B, const int quad[4]) {
 // try_fix_missing (board.rs:52-112).  The reference first lists the fixable holes, then
 // fills them; a hole filled in this pass must therefore not serve as a neighbour of another
 // hole ("was Some when the list was built" == quad index below fix_base).
-AGB_FN void board_fix_missing(Frame& F, BoardState& B) {
+AGB_NOINLINE void board_fix_missing(Frame& F, BoardState& B) {
   const int n_t = B.n_touched;
   const int fix_base = B.n_quads;
   for (int t = 0; t < n_t; ++t) {
     const int ci = B.touched[t];
     const int cv = B.cell[ci];
     if (cv != -1) continue;
-    const int x = cell_x(ci), y = cell_y(ci);
-    const int e0 = cell_in_range(x + 1, y) ? B.cell[cell_index(x + 1, y)] : 0;
-    const int e1 = cell_in_range(x - 1, y) ? B.cell[cell_index(x - 1, y)] : 0;
+    const int x = cell_x(F, ci), y = cell_y(F, ci);
+    const int e0 = cell_in_range(F, x + 1, y) ? B.cell[cell_index(F, x + 1, y)] : 0;
+    const int e1 = cell_in_range(F, x - 1, y) ? B.cell[cell_index(F, x - 1, y)] : 0;
     int qa = -1, qb = -1;
     if (e0 != 0 && e1 != 0) {  // contains_key(b0) && contains_key(b1)
       if (e0 > 0 && e0 - 1 < fix_base && e1 > 0 && e1 - 1 < fix_base) { qa = e0 - 1; qb = e1 - 1; }
     } else {
-      const int e2 = cell_in_range(x, y + 1) ? B.cell[cell_index(x, y + 1)] : 0;
-      const int e3 = cell_in_range(x, y - 1) ? B.cell[cell_index(x, y - 1)] : 0;
+      const int e2 = cell_in_range(F, x, y + 1) ? B.cell[cell_index(F, x, y + 1)] : 0;
+      const int e3 = cell_in_range(F, x, y - 1) ? B.cell[cell_index(F, x, y - 1)] : 0;
       if (e2 > 0 && e2 - 1 < fix_base && e3 > 0 && e3 - 1 < fix_base) { qa = e2 - 1; qb = e3 - 1; }
     }
     if (qa < 0) continue;
@@ -472,115 +698,177 @@ AGB_FN void unrank_pair(int c, int n, int* i, int* j) {
   *j = a + 1 + c;
 }
 
-// try_find_best_board (detector.rs:588-639) incl. init_quads (:543-586).  Returns the index
-// (0/1) of the BoardState holding the best board, or -1 for None.
-AGB_FN int find_best_board(Frame& F) {
-  if (F.n == 0) return -1;
-  // histogram of round(theta)
-  for (int b = F.lane; b < kHistBins; b += AGB_LANES) F.hist[b] = 0;
+// One seed of try_find_best_board: init_quads (detector.rs:543-586) and Board::new for every
+// quad (:620-626).  Leaves the seed's best board in F.seedbest and returns its score (0 = the
+// seed produced no quad).  Within a seed the first board reaching the maximum wins, which is
+// what the reference's strict `board.score > best_score` keeps.
+AGB_NOINLINE int process_seed(Frame& F, int s0) {
+  F.seedbest.n_quads = F.seedbest.n_touched = F.seedbest.score = 0;
+  const int n_nn = nearest_k(F, F.sx[s0], F.sy[s0], 50);
+  int n_same = 0, n_diff = 0;
+  for (int j = 1; j < n_nn; ++j) {  // nearest[1..]: the first hit is the seed itself
+    const int si = F.nn_idx[j];
+    const float td = theta_distance_degree(F.st[s0], F.st[si]);
+    if (td < 5.0f) {
+      if (F.lane == 0) F.same[n_same] = (int16_t)si;
+      ++n_same;
+    } else if (td > 80.0f) {
+      if (F.lane == 0) F.diff[n_diff] = (int16_t)si;
+      ++n_diff;
+    }
+  }
   AGB_SYNC();
-  for (int i = F.lane; i < F.n; i += AGB_LANES) {
-    int key = sat_i32(roundf(F.st[i])) + 90;
-    key = key < 0 ? 0 : (key >= kHistBins ? kHistBins - 1 : key);
+  const int n_pairs = n_diff * (n_diff - 1) / 2;
+  // the (s0, s1)-only gate of is_valid_quad, for all candidates s1 at once (n_same <= 49)
+  unsigned diag_ok[2] = {0u, 0u};
+  for (int blk = 0; blk * AGB_LANES < n_same && blk < 64; ++blk) {
+    const int a = blk * AGB_LANES + F.lane;
+    const bool ok = a < n_same && quad_diag_ok(F, s0, F.same[a]);
+    const unsigned m = agb_ballot(ok);
 #if AGB_DEVICE
-    atomicAdd(&F.hist[key], 1);
+    diag_ok[blk & 1] = m;
 #else
-    F.hist[key] += 1;
+    if (m) diag_ok[a >> 5] |= 1u << (a & 31);
 #endif
   }
-  AGB_SYNC();
-  int best_cnt = -1, best_key = -1;
-  for (int b = F.lane; b < kHistBins; b += AGB_LANES) {
-    int c = F.hist[b];
-    if (c > best_cnt || (c == best_cnt && b > best_key)) { best_cnt = c; best_key = b; }
+  for (int a = 0; a < n_same; ++a) {
+    const int s1 = F.same[a];
+    if (!((diag_ok[a >> 5] >> (a & 31)) & 1u)) continue;  // every quad with this (s0, s1) fails :31
+    for (int base = 0; base < n_pairs; base += AGB_LANES) {
+      const int c = base + F.lane;
+      bool valid = false;
+      if (c < n_pairs) {
+        int i, j;
+        unrank_pair(c, n_diff, &i, &j);
+        valid = quad_rest_ok(F, s0, F.diff[i], s1, F.diff[j]);
+      }
+      unsigned m = agb_ballot(valid);
+      while (m) {
+        const int b = agb_ffs(m);
+        m &= m - 1;
+        int i, j;
+        unrank_pair(base + b, n_diff, &i, &j);
+        const int d0 = F.diff[i], d1 = F.diff[j];
+        const float c0 = cross2(fsub(F.sx[d0], F.sx[s0]), fsub(F.sy[d0], F.sy[s0]),
+                                fsub(F.sx[s1], F.sx[s0]), fsub(F.sy[s1], F.sy[s0]));
+        int quad[4];
+        quad[0] = s0; quad[2] = s1;
+        if (c0 > 0.0f) { quad[1] = d0; quad[3] = d1; }
+        else { quad[1] = d1; quad[3] = d0; }
+        board_build(F, F.bs, quad);  // Board::new(refined, active_mask, &q, 0.3, tree)
+        if (F.bs.score > F.seedbest.score) board_save(F, F.bs, F.seedbest);
+      }
+    }
   }
-#if AGB_DEVICE
-  for (int o = 16; o > 0; o >>= 1) {
-    int oc = __shfl_xor_sync(0xffffffffu, best_cnt, o);
-    int ok = __shfl_xor_sync(0xffffffffu, best_key, o);
-    if (oc > best_cnt || (oc == best_cnt && ok > best_key)) { best_cnt = oc; best_key = ok; }
-  }
-#endif
-  // seeds: members of that bin in ascending index order
-  int n_seeds = 0;
-  for (int base = 0; base < F.n; base += AGB_LANES) {
-    int i = base + F.lane;
-    bool in = false;
-    if (i < F.n) {
+  return F.seedbest.score;
+}
+
+// try_find_best_board (detector.rs:588-639).  Seeds are handed to the warps of the block in
+// waves; after each wave the per-seed results are merged in the reference's seed order, with
+// its `score > best_score` replacement, its `best_score >= 36` early exit and its limit of 30
+// seeds.  Work done for seeds past the early exit is discarded, so the outcome equals the
+// sequential loop.  Returns 1 with the best board (after try_fix_missing) live in warp 0's
+// F.bs, or -1 for None.  Every warp of the block must call it (block-wide barriers inside).
+AGB_NOINLINE int find_best_board(Frame& F) {
+  if (F.n == 0) return -1;
+  if (F.warp == 0) {
+    grid_build(F);
+    // histogram of round(theta)
+    for (int b = F.lane; b < kHistBins; b += AGB_LANES) F.hist[b] = 0;
+    AGB_SYNC();
+    for (int i = F.lane; i < F.n; i += AGB_LANES) {
       int key = sat_i32(roundf(F.st[i])) + 90;
       key = key < 0 ? 0 : (key >= kHistBins ? kHistBins - 1 : key);
-      in = key == best_key;
-    }
-    unsigned m = agb_ballot(in);
 #if AGB_DEVICE
-    if (in) F.seeds[n_seeds + __popc(m & ((1u << F.lane) - 1u))] = (int16_t)i;
-    n_seeds += __popc(m);
+      atomicAdd(&F.hist[key], 1);
 #else
-    if (in) F.seeds[n_seeds] = (int16_t)i;
-    n_seeds += (int)m;
+      F.hist[key] += 1;
 #endif
-  }
-  AGB_SYNC();
-
-  int cur = 0, best = -1, best_score = 0, count = 0;
-  while (n_seeds > 0 && count < 30) {
-    const int s0 = F.seeds[--n_seeds];  // pop from the back
-    // ---- init_quads(refined, s0, tree) ----
-    const int n_nn = nearest_k(F, F.sx[s0], F.sy[s0], 50);
-    int n_same = 0, n_diff = 0;
-    for (int j = 1; j < n_nn; ++j) {  // nearest[1..]: the first hit is the seed itself
-      const int si = F.nn_idx[j];
-      const float td = theta_distance_degree(F.st[s0], F.st[si]);
-      if (td < 5.0f) {
-        if (F.lane == 0) F.same[n_same] = (int16_t)si;
-        ++n_same;
-      } else if (td > 80.0f) {
-        if (F.lane == 0) F.diff[n_diff] = (int16_t)si;
-        ++n_diff;
-      }
     }
     AGB_SYNC();
-    const int n_pairs = n_diff * (n_diff - 1) / 2;
-    for (int a = 0; a < n_same; ++a) {
-      const int s1 = F.same[a];
-      if (!quad_diag_ok(F, s0, s1)) continue;  // every quad with this (s0, s1) fails :31
-      for (int base = 0; base < n_pairs; base += AGB_LANES) {
-        const int c = base + F.lane;
-        bool valid = false;
-        if (c < n_pairs) {
-          int i, j;
-          unrank_pair(c, n_diff, &i, &j);
-          valid = quad_rest_ok(F, s0, F.diff[i], s1, F.diff[j]);
-        }
-        unsigned m = agb_ballot(valid);
-        while (m) {
-          const int b = agb_ffs(m);
-          m &= m - 1;
-          int i, j;
-          unrank_pair(base + b, n_diff, &i, &j);
-          const int d0 = F.diff[i], d1 = F.diff[j];
-          const float c0 = cross2(fsub(F.sx[d0], F.sx[s0]), fsub(F.sy[d0], F.sy[s0]),
-                                  fsub(F.sx[s1], F.sx[s0]), fsub(F.sy[s1], F.sy[s0]));
-          int quad[4];
-          quad[0] = s0; quad[2] = s1;
-          if (c0 > 0.0f) { quad[1] = d0; quad[3] = d1; }
-          else { quad[1] = d1; quad[3] = d0; }
-          // ---- Board::new(refined, active_mask, &q, 0.3, tree) ----
-          board_build(F, F.bs[cur], quad);
-          if (F.bs[cur].score > best_score) {
-            best_score = F.bs[cur].score;
-            best = cur;
-            cur ^= 1;
-          }
-        }
+    int best_cnt = -1, best_key = -1;
+    for (int b = F.lane; b < kHistBins; b += AGB_LANES) {
+      int c = F.hist[b];
+      if (c > best_cnt || (c == best_cnt && b > best_key)) { best_cnt = c; best_key = b; }
+    }
+#if AGB_DEVICE
+    for (int o = 16; o > 0; o >>= 1) {
+      int oc = __shfl_xor_sync(0xffffffffu, best_cnt, o);
+      int ok = __shfl_xor_sync(0xffffffffu, best_key, o);
+      if (oc > best_cnt || (oc == best_cnt && ok > best_key)) { best_cnt = oc; best_key = ok; }
+    }
+#endif
+    // seeds: members of that bin in ascending index order
+    int n_seeds = 0;
+    for (int base = 0; base < F.n; base += AGB_LANES) {
+      int i = base + F.lane;
+      bool in = false;
+      if (i < F.n) {
+        int key = sat_i32(roundf(F.st[i])) + 90;
+        key = key < 0 ? 0 : (key >= kHistBins ? kHistBins - 1 : key);
+        in = key == best_key;
+      }
+      unsigned m = agb_ballot(in);
+#if AGB_DEVICE
+      if (in) F.seeds[n_seeds + __popc(m & ((1u << F.lane) - 1u))] = (int16_t)i;
+      n_seeds += __popc(m);
+#else
+      if (in) F.seeds[n_seeds] = (int16_t)i;
+      n_seeds += (int)m;
+#endif
+    }
+    if (F.lane == 0) {
+      F.ctl[0] = n_seeds;
+      F.ctl[5] = F.g_on;
+    }
+  }
+  AGB_BLOCK_SYNC();
+  int seeds_left = F.ctl[0];
+  F.g_on = F.ctl[5];  // the grid was (or was not) built by warp 0 for everybody
+  int best_score = 0, count = 0;
+  bool stop = false;
+  while (seeds_left > 0 && count < 30 && !stop) {
+    // s0_idxs.pop(): seeds are taken from the back; warp w of this wave gets the w-th pop
+    const int pos = seeds_left - 1 - F.warp;
+    const bool valid = pos >= 0 && count + F.warp < 30;
+    int sc = -1;
+    if (valid) sc = process_seed(F, F.seeds[pos]);
+    if (F.lane == 0) F.w_score[F.warp] = sc;
+    AGB_BLOCK_SYNC();
+    int winner = -1, consumed = 0;
+    for (int w = 0; w < F.n_warps; ++w) {
+      const int s = F.w_score[w];
+      if (s < 0) break;
+      ++consumed;
+      if (s > best_score) { best_score = s; winner = w; }
+      if (best_score >= 36) { stop = true; break; }
+      ++count;
+    }
+    if (winner == F.warp) {  // best_board_option = Some(board)
+      const BoardRecord& R = F.seedbest;
+      for (int t = F.lane; t < R.n_quads * 4; t += AGB_LANES) F.best.quads[t] = R.quads[t];
+      for (int t = F.lane; t < R.n_touched; t += AGB_LANES) {
+        F.best.touched[t] = R.touched[t];
+        F.best.vals[t] = R.vals[t];
+      }
+      if (F.lane == 0) {
+        F.ctl[2] = R.n_quads;
+        F.ctl[3] = R.n_touched;
+        F.ctl[4] = R.score;
       }
     }
-    if (best_score >= 36) break;
-    ++count;
+    seeds_left -= consumed;
+    AGB_BLOCK_SYNC();
   }
-  if (best < 0) return -1;
-  board_fix_missing(F, F.bs[best]);
-  return best;
+  if (best_score == 0) return -1;
+  if (F.warp == 0) {
+    F.best.n_quads = F.ctl[2];
+    F.best.n_touched = F.ctl[3];
+    F.best.score = F.ctl[4];
+    board_load(F, F.bs, F.best);
+    board_fix_missing(F, F.bs);
+  }
+  return 1;
 }
 
 // ---- decoding (detector.rs:42-169, :448-476) ---------------------------------------------------
@@ -606,7 +894,7 @@ AGB_FN uint64_t rotate_bits(uint64_t bits, int edge) {
 }
 
 // try_decode_quad: on success fills *out (id + rotated, reversed corners).
-AGB_FN bool decode_quad(Frame& F, const int q[4], TagRec* out) {
+AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
   float qx[4], qy[4];
   for (int j = 0; j < 4; ++j) {
     qx[j] = F.sx[q[j]];
@@ -699,72 +987,82 @@ AGB_FN bool decode_quad(Frame& F, const int q[4], TagRec* out) {
 }
 
 // TagDetector::detect from the refined saddle list on (detector.rs:510-538).
-// Workspace arrays must be initialised by the caller: cells 0, active 1, tag_valid 0.
+// Workspace must be initialised by the caller: cells 0, active bits 1, tag_valid 0, counters 0.
+// Every warp of the frame's block calls it; warp 0 decodes and compacts.
 AGB_FN void detect_boards(Frame& F, int max_boards) {
   for (int round = 0; round < max_boards; ++round) {
-    const int best = find_best_board(F);
-    if (best < 0) continue;
-    BoardState& B = F.bs[best];
-    for (int i = F.lane; i < F.n; i += AGB_LANES) F.remove[i] = 0;
-    AGB_SYNC();
-    int n_tap = 0;
-    // all_tag_indexes in ascending (x, y) order
-    for (int base = 0; base < kCells; base += AGB_LANES) {
-      const int ci = base + F.lane;
-      unsigned m = agb_ballot(B.cell[ci] > 0);
-      while (m) {
-        const int b = agb_ffs(m);
-        m &= m - 1;
-        const int qi = B.cell[base + b] - 1;
-        int q[4];
-        for (int j = 0; j < 4; ++j) q[j] = B.quads[qi * 4 + j];
-        if (round == 0 && F.tap_quads) {
-          if (F.lane == 0 && n_tap < F.tap_cap)
-            for (int j = 0; j < 4; ++j) F.tap_quads[n_tap * 4 + j] = q[j];
-          ++n_tap;
-        }
-        TagRec t;
-        if (decode_quad(F, q, &t)) {
-          if (F.lane == 0) {
-            F.tag_by_id[t.id] = t;  // HashMap::insert: a repeated id overwrites
-            F.tag_valid[t.id] = 1;
-            for (int j = 0; j < 4; ++j) F.remove[q[j]] = 1;
+    if (find_best_board(F) < 0) continue;  // block-uniform
+    if (F.warp == 0) {
+      BoardState& B = F.bs;
+      for (int i = F.lane; i < F.n; i += AGB_LANES) F.remove[i] = 0;
+      AGB_SYNC();
+      int n_tap = 0;
+      // all_tag_indexes in ascending (x, y) order
+      const int n_cells = F.lat * F.lat;
+      for (int base = 0; base < n_cells; base += AGB_LANES) {
+        const int ci = base + F.lane;
+        unsigned m = agb_ballot(B.cell[ci] > 0);
+        while (m) {
+          const int b = agb_ffs(m);
+          m &= m - 1;
+          const int qi = B.cell[base + b] - 1;
+          int q[4];
+          for (int j = 0; j < 4; ++j) q[j] = B.quads[qi * 4 + j];
+          if (round == 0 && F.tap_quads) {
+            if (F.lane == 0 && n_tap < F.tap_cap)
+              for (int j = 0; j < 4; ++j) F.tap_quads[n_tap * 4 + j] = q[j];
+            ++n_tap;
           }
-          AGB_SYNC();
+          TagRec t;
+          if (decode_quad(F, q, &t)) {
+            if (F.lane == 0) {
+              F.tag_by_id[t.id] = t;  // HashMap::insert: a repeated id overwrites
+              F.tag_valid[t.id] = 1;
+              for (int j = 0; j < 4; ++j) F.remove[q[j]] = 1;
+            }
+            AGB_SYNC();
+          }
         }
       }
-    }
-    if (round == 0 && F.tap_n_quads && F.lane == 0) *F.tap_n_quads = n_tap;
-    AGB_SYNC();
-    // refined.retain(not removed), order kept (:526-536); the board states are reset because
-    // saddle indices change.
-    board_reset(F, F.bs[0]);
-    board_reset(F, F.bs[1]);
-    int n_new = 0;
-    for (int base = 0; base < F.n; base += AGB_LANES) {
-      const int i = base + F.lane;
-      const bool keep = i < F.n && !F.remove[i];
-      unsigned m = agb_ballot(keep);
+      if (round == 0 && F.tap_n_quads && F.lane == 0) *F.tap_n_quads = n_tap;
+      AGB_SYNC();
+      // refined.retain(not removed), order kept (:526-536).  In-place, order-preserving
+      // compaction: block after block, every lane reads its element before any lane of the
+      // block writes, and writes only go to indices at or below the block.
+      int n_new = 0;
+      for (int base = 0; base < F.n; base += AGB_LANES) {
+        const int i = base + F.lane;
+        const bool keep = i < F.n && !F.remove[i];
+        float kx = 0.0f, ky = 0.0f, kt = 0.0f;
+        if (keep) {
+          kx = F.sx[i];
+          ky = F.sy[i];
+          kt = F.st[i];
+        }
+        unsigned m = agb_ballot(keep);
 #if AGB_DEVICE
-      const int dst = n_new + __popc(m & ((1u << F.lane) - 1u));
-      const int cnt = __popc(m);
+        const int dst = n_new + __popc(m & ((1u << F.lane) - 1u));
+        const int cnt = __popc(m);
 #else
-      const int dst = n_new;
-      const int cnt = (int)m;
+        const int dst = n_new;
+        const int cnt = (int)m;
 #endif
-      if (keep) {
-        F.sx2[dst] = F.sx[i];
-        F.sy2[dst] = F.sy[i];
-        F.st2[dst] = F.st[i];
+        AGB_SYNC();
+        if (keep) {
+          F.sx[dst] = kx;
+          F.sy[dst] = ky;
+          F.st[dst] = kt;
+        }
+        AGB_SYNC();
+        n_new += cnt;
       }
-      n_new += cnt;
+      if (F.lane == 0) F.ctl[1] = n_new;
     }
-    AGB_SYNC();
-    float* t;
-    t = F.sx; F.sx = F.sx2; F.sx2 = t;
-    t = F.sy; F.sy = F.sy2; F.sy2 = t;
-    t = F.st; F.st = F.st2; F.st2 = t;
-    F.n = n_new;
+    // saddle indices changed: every warp forgets its board
+    board_reset(F, F.bs);
+    AGB_BLOCK_SYNC();
+    F.n = F.ctl[1];
+    AGB_BLOCK_SYNC();
   }
 }
 

@@ -9,14 +9,20 @@
 namespace ag {
 
 struct BoardWsLayout {
-  int max_saddles, max_quads;
-  size_t off_pos[6];
-  size_t off_cell[2], off_quads[2], off_touched[2], off_active[2];
-  size_t off_stack, off_seeds, off_nn, off_same, off_diff, off_samp, off_hist, off_remove;
-  size_t off_tag_valid, off_tag_by_id;
+  int max_saddles, max_quads, lattice, warps;
+  // global workspace per frame: frame-wide part, then `warps` per-warp parts
+  size_t off_pos[3];
+  size_t off_best_quads, off_best_touched, off_best_vals;
+  size_t off_seeds, off_remove, off_tag_valid, off_tag_by_id;
+  size_t off_warp0, bytes_per_warp;
+  size_t woff_quads, woff_touched, woff_sb_quads, woff_sb_touched, woff_sb_vals, woff_stack;
   size_t bytes_per_frame;
+  // shared memory per block (= per frame in flight): frame-wide part, then per-warp parts
+  int smem_saddles, grid_cap_cells;
+  size_t sm_pos, sm_gstart, sm_gitem, sm_hist, sm_ctl, sm_warp0;
+  size_t smw_cell, smw_active, smw_small, smem_per_warp, smem_per_block;
 };
-BoardWsLayout make_board_layout(int max_saddles);
+BoardWsLayout make_board_layout(int max_saddles, int lattice);
 
 // ag_dense.cu
 int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames, float* blur,
@@ -47,7 +53,8 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
                          const ag_saddle* refined, const int* n_refined, uint8_t* ws,
                          const BoardWsLayout& L, int n_codes, int edge, int border, int hamming,
                          int max_boards, ag_tag* out, int cap, int* n_out, uint32_t* frame_status,
-                         int32_t* tap_quads, int* tap_n_quads, int tap_cap, cudaStream_t s);
+                         int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid,
+                         cudaStream_t s);
 
 // ag_render.cu
 int launch_render_boards(uint8_t* frames, int n_frames, int w, int h, int cols, int rows,

@@ -106,7 +106,7 @@ AG_API void ag_destroy(ag_detector* det);
 AG_API const char* ag_last_error(const ag_detector* det);
 
 /* Tunables.  key: "chunk_frames" (frames per pipeline chunk), "max_clusters",
- * "max_saddles" (per-frame capacities).  Must be set before the first detect call that
+ * "max_saddles" (per-frame capacities), "profile" (0/1, see ag_stage_times).  Must be set before the first detect call that
  * needs them larger. */
 AG_API int ag_set_option(ag_detector* det, const char* key, long value);
 
@@ -171,6 +171,12 @@ AG_API int ag_stage_tags(ag_detector* det, ag_tag* out, int cap, int* n);
 
 /* Number of kernel launches issued by this handle since creation (bench bookkeeping). */
 AG_API uint64_t ag_launch_count(const ag_detector* det);
+
+/* Per-stage device time, accumulated with CUDA events on the launching stream while the
+ * option "profile" is 1.  ms_out[8] / n_out[8]: total milliseconds and number of launches of
+ * stage 0 = blur+Hessian+min, 1 = threshold, 2 = label+centroid, 3 = refine+filter,
+ * 4 = boards+decode.  Synchronises the device.  reset != 0 clears the accumulators.       */
+AG_API int ag_stage_times(ag_detector* det, double* ms_out, uint64_t* n_out, int reset);
 
 /* Synthetic AprilGrid renderer (benchmark / test data generator, runs on the GPU):
  * renders n_frames u8 gray frames of a cols x rows board of `family` tags (ids from 0,

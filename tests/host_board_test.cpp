@@ -16,15 +16,14 @@ int hb_detect_from_saddles(const float* saddles, int n, const uint8_t* img, int 
                            size_t row_stride, int format, const uint64_t* codes, int n_codes,
                            int edge, int border, int hamming, int max_boards, int max_saddles,
                            agb::TagRec* out, int cap, int32_t* tap_quads, int* tap_n, int tap_cap,
-                           uint32_t* status) {
+                           uint32_t* status, int use_grid, int lattice) {
   using namespace agb;
   if (n > max_saddles) return -1;
   const int N = max_saddles, Q = N / 4 + 2;
-  std::vector<float> pos(6 * (size_t)N, 0.0f);
-  std::vector<int16_t> cell[2] = {std::vector<int16_t>(kCells, 0), std::vector<int16_t>(kCells, 0)};
-  std::vector<int16_t> quads[2] = {std::vector<int16_t>(4 * Q), std::vector<int16_t>(4 * Q)};
-  std::vector<int16_t> touched[2] = {std::vector<int16_t>(kCells), std::vector<int16_t>(kCells)};
-  std::vector<uint8_t> active[2] = {std::vector<uint8_t>(N, 1), std::vector<uint8_t>(N, 1)};
+  std::vector<float> pos(3 * (size_t)N, 0.0f);
+  std::vector<int16_t> cell(kCells, 0), quads(4 * Q), touched(kCells);
+  std::vector<int16_t> bquads(4 * Q), btouched(kCells), bvals(kCells);
+  std::vector<uint32_t> active((N + 31) / 32, 0xffffffffu);
   std::vector<int16_t> stack(2 * (Q + 1)), seeds(N), nn(64), same(64), diff(64), samp(64);
   std::vector<int> hist(kHistBins);
   std::vector<uint8_t> remove(N), tag_valid(kMaxCodes, 0);
@@ -34,14 +33,30 @@ int hb_detect_from_saddles(const float* saddles, int n, const uint8_t* img, int 
   F.lane = 0;
   F.n = n;
   F.sx = &pos[0]; F.sy = &pos[N]; F.st = &pos[2 * (size_t)N];
-  F.sx2 = &pos[3 * (size_t)N]; F.sy2 = &pos[4 * (size_t)N]; F.st2 = &pos[5 * (size_t)N];
   for (int i = 0; i < n; ++i) {
     F.sx[i] = saddles[5 * i]; F.sy[i] = saddles[5 * i + 1]; F.st[i] = saddles[5 * i + 3];
   }
-  for (int b = 0; b < 2; ++b) {
-    F.bs[b].cell = cell[b].data(); F.bs[b].quads = quads[b].data();
-    F.bs[b].touched = touched[b].data(); F.bs[b].active = active[b].data();
-    F.bs[b].n_quads = F.bs[b].n_touched = F.bs[b].score = 0;
+  F.bs.cell = cell.data(); F.bs.quads = quads.data(); F.bs.touched = touched.data();
+  F.bs.active = active.data();
+  F.bs.n_quads = F.bs.n_touched = F.bs.score = 0;
+  F.best.quads = bquads.data(); F.best.touched = btouched.data(); F.best.vals = bvals.data();
+  F.best.n_quads = F.best.n_touched = F.best.score = 0;
+  std::vector<int16_t> squads(4 * Q), stouched(kCells), svals(kCells);
+  F.seedbest.quads = squads.data(); F.seedbest.touched = stouched.data(); F.seedbest.vals = svals.data();
+  F.seedbest.n_quads = F.seedbest.n_touched = F.seedbest.score = 0;
+  int ctl[16] = {0};
+  F.ctl = ctl; F.w_score = ctl + 8;
+  F.warp = 0; F.n_warps = 1;
+  F.lat = lattice; F.lat_off = lattice / 2;
+  // bucket grid (the device kernel sizes it the same way); use_grid = 0 tests the exhaustive scan
+  int bucket = 32;
+  const int grid_cap = 1408;
+  while (((w + bucket - 1) / bucket) * ((h + bucket - 1) / bucket) > grid_cap) bucket *= 2;
+  std::vector<uint16_t> gstart(grid_cap + 1), gitem(N);
+  if (use_grid) {
+    F.g_start = gstart.data(); F.g_item = gitem.data();
+    F.g_nx = (w + bucket - 1) / bucket; F.g_ny = (h + bucket - 1) / bucket;
+    F.g_cap_cells = grid_cap; F.g_cap_items = 512;  // as on the device F.g_inv = 1.0f / (float)bucket;
   }
   F.stack = stack.data(); F.seeds = seeds.data(); F.nn_idx = nn.data(); F.same = same.data();
   F.diff = diff.data(); F.samp = samp.data(); F.hist = hist.data(); F.remove = remove.data();

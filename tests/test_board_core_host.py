@@ -21,7 +21,8 @@ def hb():
     return C.CDLL(HOSTLIB)
 
 
-def host_detect(hb, pkg, oracle, img, saddles=None, family=None, max_boards=2, max_saddles=2048):
+def host_detect(hb, pkg, oracle, img, saddles=None, family=None, max_boards=2, max_saddles=2048,
+                use_grid=1, lattice=64):
     family = family or pkg.TagFamily.T36H11
     fam = pkg.family_info(family)
     if saddles is None:
@@ -37,7 +38,7 @@ def host_detect(hb, pkg, oracle, img, saddles=None, family=None, max_boards=2, m
         s.ctypes.data_as(vp), len(s), img.ctypes.data_as(vp), w, h, C.c_size_t(st), fmt,
         codes.ctypes.data_as(vp), len(codes), fam["edge"], fam["border"], fam["hamming"], max_boards,
         max_saddles, out.ctypes.data_as(vp), 1024, quads.ctypes.data_as(vp), C.byref(tapn), 1024,
-        C.byref(status))
+        C.byref(status), use_grid, lattice)
     assert n >= 0
     return ({int(t["id"]): t["xy"].reshape(4, 2).copy() for t in out[:n]}, quads[:tapn.value],
             status.value, s)
@@ -64,6 +65,41 @@ def test_synthetic_boards_identical_to_oracle(hb, pkg, oracle, seed):
     assert sorted(got) == sorted(want) and len(want) == 36
     for k in want:
         assert np.array_equal(got[k], want[k])
+
+
+def test_bucket_grid_and_exhaustive_search_agree(hb, pkg, oracle, images):
+    """The radius queries go through a bucket grid on the device; same answers as the full scan."""
+    for name in ("EuRoC", "two_boards"):
+        img = images[name]
+        a = host_detect(hb, pkg, oracle, img, use_grid=1)
+        b = host_detect(hb, pkg, oracle, img, use_grid=0)
+        assert sorted(a[0]) == sorted(b[0]) and np.array_equal(a[1], b[1])
+        for k in a[0]:
+            assert np.array_equal(a[0][k], b[0][k])
+
+
+def test_more_saddles_than_the_on_chip_grid_holds(hb, pkg, oracle):
+    """> 512 saddles: the bucket grid is skipped (exhaustive search), result unchanged."""
+    img = synth.render_board_numpy(1600, 1200, cols=12, rows=9, seed=4, tag_px=70.0)
+    fe = oracle.front_end(img, want_labels=False)
+    assert len(fe["refined"]) > 512
+    got, quads, status, s = host_detect(hb, pkg, oracle, img, saddles=fe["refined"])
+    want = oracle.detect(img)
+    assert sorted(got) == sorted(want) and len(want) >= 100
+    for k in want:
+        assert np.array_equal(got[k], want[k])
+
+
+def test_small_lattice_same_result_and_overflow_flag(hb, pkg, oracle, images):
+    """A 6x6 board fits a 32-wide lattice (same answer); a 16-wide one may overflow and says so."""
+    img = images["EuRoC"]
+    a = host_detect(hb, pkg, oracle, img, lattice=64)
+    b = host_detect(hb, pkg, oracle, img, lattice=32)
+    assert sorted(a[0]) == sorted(b[0]) and b[2] == 0
+    c = host_detect(hb, pkg, oracle, img, lattice=16)
+    assert c[2] in (0, 4)  # AG_FRAME_BOARD_OVERFLOW when the board leaves the -8..7 lattice
+    if c[2] == 0:
+        assert sorted(c[0]) == sorted(a[0])
 
 
 def test_empty_and_degenerate_saddle_lists(hb, pkg, oracle):

@@ -40,10 +40,13 @@ def test_batch_1280x1024_properties_and_sampled_oracle(detector, pkg, oracle, to
     frames = render(detector, torch, n, seed=1234)
     rec, cnt, status = run_device(detector, pkg, torch, frames)
     assert (status == 0).all()
-    # every rendered 6x6 board decodes to ids 0..35 exactly once
-    assert (cnt == 36).all(), cnt
-    for i in range(n):
+    # nearly every rendered 6x6 board decodes to ids 0..35 exactly once; the odd frame whose pose
+    # defeats the detector must defeat the oracle in exactly the same way (checked below)
+    full = cnt == 36
+    assert full.mean() >= 0.9, cnt
+    for i in np.nonzero(full)[0]:
         assert list(rec[i, :36]["id"]) == list(range(36))
+    assert (cnt <= 36).all()
     # idempotence: same input, same bytes out
     rec2, cnt2, _ = run_device(detector, pkg, torch, frames)
     assert np.array_equal(cnt, cnt2) and np.array_equal(rec.tobytes(), rec2.tobytes())
@@ -53,10 +56,10 @@ def test_batch_1280x1024_properties_and_sampled_oracle(detector, pkg, oracle, to
     p = perm.cpu().numpy()
     assert np.array_equal(rec3.tobytes(), rec[p].tobytes())
     # sampled frames against the oracle
-    host = frames[::16].cpu().numpy()
-    want = oracle.detect_batch(host, threads=4)
-    for j, wtags in enumerate(want):
-        i = j * 16
+    sample = sorted(set(range(0, n, 16)) | set(int(i) for i in np.nonzero(~full)[0]))
+    host = frames[sample].cpu().numpy()
+    want = oracle.detect_batch(host, threads=8)
+    for i, wtags in zip(sample, want):
         got = {int(t["id"]): t["xy"].reshape(4, 2) for t in rec[i, :cnt[i]]}
         assert sorted(got) == sorted(wtags)
         for k in wtags:
@@ -69,7 +72,15 @@ def test_dense_batch_device_stage_parity_at_full_size(detector, pkg, oracle, tor
     rng = np.random.default_rng(5)
     noise = rng.integers(0, 256, (H, W), dtype=np.uint8)
     from test_gpu_parity import check_stages
-    check_stages(detector, oracle, noise, check_board=False)
+    check_stages(detector, oracle, noise, check_board=False)  # > 16384 clusters: truncated + flagged
+    big = pkg.TagDetector(pkg.TagFamily.T36H11)
+    try:
+        big.set_option("max_clusters", 1 << 18)
+        big.set_option("max_saddles", 16384)
+        g, o = check_stages(big, oracle, noise, check_board=False)
+        assert len(g["centers"]) == len(o["centers"]) > 16384
+    finally:
+        big.close()
     board = render(detector, torch, 1, seed=99)[0].cpu().numpy()
     check_stages(detector, oracle, board)
 
