@@ -82,6 +82,7 @@ struct ag_detector {
   FrameGeom tap_geom{};
   bool tap_valid = false;
   // optional per-stage timing (ag_set_option "profile"): CUDA events between the kernels
+  long dense_variant = 0;   // 0 = streaming K1 where applicable, 1 = always the generic tile kernel
   long board_lattice = 64;  // side of the tag lattice a board may span (16 / 32 / 64)
   bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
   bool profile = false;
@@ -260,7 +261,8 @@ void prof_mark(ag_detector* det, int stage, cudaStream_t s) {
 int run_dense(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
               bool write_blur, cudaStream_t s) {
   prof_mark(det, -1, s);
-  det->launches += launch_blur_hessian(d_frames, g, n, S.d_blur, S.d_resp, S.d_min, write_blur, 0, s);
+  det->launches += launch_blur_hessian(d_frames, g, n, S.d_blur, S.d_resp, S.d_min, write_blur,
+                                       (int)det->dense_variant, s);
   prof_mark(det, 0, s);
   det->launches += launch_threshold(S.d_resp, g, n, S.d_min, S.d_mask, s);
   prof_mark(det, 1, s);
@@ -475,6 +477,8 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "max_saddles")) {
     if (value < 16 || value > 16384) return fail(det, AG_ERR_INVALID, "max_saddles out of range");
     det->max_saddles = value;
+  } else if (!strcmp(key, "dense_variant")) {
+    det->dense_variant = value;
   } else if (!strcmp(key, "board_lattice")) {
     if (value != 16 && value != 32 && value != 64) return fail(det, AG_ERR_INVALID, "board_lattice must be 16, 32 or 64");
     det->board_lattice = value;

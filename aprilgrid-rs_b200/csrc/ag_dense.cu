@@ -139,6 +139,146 @@ k_blur_hessian_tile(const uint8_t* __restrict__ frames, FrameGeom g, float* __re
   }
 }
 
+// -----------------------------------------------------------------------------------------
+// K1, streaming version for 8-bit gray input (the benchmark path).
+//
+// One WARP owns a strip of 120 output columns (it computes 128: lanes 0 and 31 only provide the
+// blurred halo column their neighbours need) and marches down a chunk of rows.  Each lane owns
+// 4 adjacent columns, so the input is one coalesced 128-byte load per warp-row and the outputs
+// are 480-byte float4 stores.  Everything between load and store lives in registers:
+//   * horizontal pass: a 10-pixel window per lane, the 3 + 3 halo pixels come from the
+//     neighbouring lanes by warp shuffle;
+//   * vertical pass: 7 running partial sums per column.  A new horizontal-pass value t of row r
+//     is the tap-i term of output row r + 3 - i; rows arrive in increasing r, so each output
+//     row receives its terms in tap order 0..6 -- the reference's accumulation order -- and
+//     the symmetric taps need only 4 products;
+//   * Hessian: the last three blurred rows of the 4 columns plus one halo column per side.
+// No shared memory, no block barrier.  Clamp-to-edge is obtained by clamping the loaded row /
+// replicating the edge pixel.  Requires width % 4 == 0 and 4-byte aligned rows.
+// -----------------------------------------------------------------------------------------
+constexpr int S_COLS = 120;  // output columns per warp
+constexpr int S_ROWS = 128;  // output rows per warp (chunk)
+constexpr int S_WARPS = 4;   // warps per CTA (adjacent strips of one row chunk)
+
+AG_D float u8_lane(uint32_t word, int k) {  // byte k of a packed pixel word -> luma f32
+  return unorm8_to_f32((float)((word >> (8 * k)) & 0xffu));
+}
+
+template <bool WRITE_BLUR>
+__global__ void __launch_bounds__(S_WARPS * 32, 4)
+k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __restrict__ blur,
+                      float* __restrict__ resp, uint32_t* __restrict__ frame_min) {
+  const int lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * S_WARPS + (threadIdx.x >> 5);
+  const int X0 = strip * S_COLS;
+  if (X0 >= g.w) return;
+  const int f = blockIdx.z;
+  const int Y0 = blockIdx.y * S_ROWS, Y1 = min(Y0 + S_ROWS, g.h);
+  const int c0 = X0 - 4 + 4 * lane;  // first of this lane's 4 columns (may lie outside the image)
+  const uint8_t* frame = frames + (size_t)f * g.frame_stride;
+  const int cw = min(max(c0, 0), g.w - 4);  // column of the word actually loaded
+  const bool left_out = c0 < 0, right_out = c0 >= g.w;
+  const bool writer = lane >= 1 && lane <= 30 && !right_out;
+  const float k0 = c_taps[0], k1 = c_taps[1], k2 = c_taps[2], k3 = c_taps[3];
+
+  auto load_row = [&](int r) -> uint32_t {
+    const int rr = min(max(r, 0), g.h - 1);
+    uint32_t wd = __ldg(reinterpret_cast<const uint32_t*>(frame + (size_t)rr * g.row_stride + cw));
+    if (left_out) wd = (wd & 0xffu) * 0x01010101u;   // replicate pixel 0
+    if (right_out) wd = (wd >> 24) * 0x01010101u;    // replicate pixel w-1
+    return wd;
+  };
+
+  // vertical partial sums: a[j][c] = sum so far of the output row that still needs 7-j.. terms
+  float a1[4], a2[4], a3[4], a4[4], a5[4], a6[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) a1[c] = a2[c] = a3[c] = a4[c] = a5[c] = a6[c] = 0.0f;
+  // blurred rows: bm = row y-1, bc = row y, (new row = y+1); [0] = left halo column, [5] = right halo
+  float bm[6], bc[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) bm[c] = bc[c] = 0.0f;
+  float mn = 3.40282347e+38f;
+
+  const int r_begin = Y0 - 4, r_end = Y1 + 3;  // temp rows r_begin..r_end inclusive
+  uint32_t w_next = load_row(r_begin), w_next2 = load_row(r_begin + 1);
+  for (int r = r_begin; r <= r_end; ++r) {
+    const uint32_t wd = w_next;
+    w_next = w_next2;
+    w_next2 = load_row(r + 2);  // prefetch two rows ahead
+    // ---- gray conversion + halo exchange: p[0..9] = pixels c0-3 .. c0+6
+    float p[10];
+    p[3] = u8_lane(wd, 0); p[4] = u8_lane(wd, 1); p[5] = u8_lane(wd, 2); p[6] = u8_lane(wd, 3);
+    p[0] = __shfl_up_sync(0xffffffffu, p[4], 1);
+    p[1] = __shfl_up_sync(0xffffffffu, p[5], 1);
+    p[2] = __shfl_up_sync(0xffffffffu, p[6], 1);
+    p[7] = __shfl_down_sync(0xffffffffu, p[3], 1);
+    p[8] = __shfl_down_sync(0xffffffffu, p[4], 1);
+    p[9] = __shfl_down_sync(0xffffffffu, p[5], 1);
+    // ---- horizontal pass (image_util.rs:138-185): val = 0; val += px * k[i], i = 0..6
+    float t[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = __fmul_rn(p[c], k0);  // 0.0 + x*k0 == x*k0 (x >= 0)
+      v = __fadd_rn(v, __fmul_rn(p[c + 1], k1));
+      v = __fadd_rn(v, __fmul_rn(p[c + 2], k2));
+      v = __fadd_rn(v, __fmul_rn(p[c + 3], k3));
+      v = __fadd_rn(v, __fmul_rn(p[c + 4], k2));
+      v = __fadd_rn(v, __fmul_rn(p[c + 5], k1));
+      v = __fadd_rn(v, __fmul_rn(p[c + 6], k0));
+      t[c] = v;
+    }
+    // ---- vertical pass (image_util.rs:188-203): temp row r is tap i of output row r + 3 - i
+    float bn[6];  // completed blurred row r - 3
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float q0 = __fmul_rn(t[c], k0), q1 = __fmul_rn(t[c], k1), q2 = __fmul_rn(t[c], k2),
+                  q3 = __fmul_rn(t[c], k3);
+      bn[c + 1] = __fadd_rn(a6[c], q0);  // tap 6 completes row r - 3
+      a6[c] = __fadd_rn(a5[c], q1);      // tap 5 of row r - 2
+      a5[c] = __fadd_rn(a4[c], q2);      // tap 4 of row r - 1
+      a4[c] = __fadd_rn(a3[c], q3);      // tap 3 of row r
+      a3[c] = __fadd_rn(a2[c], q2);      // tap 2 of row r + 1
+      a2[c] = __fadd_rn(a1[c], q1);      // tap 1 of row r + 2
+      a1[c] = q0;                        // tap 0 of row r + 3 (0.0 + q0)
+    }
+    bn[0] = __shfl_up_sync(0xffffffffu, bn[4], 1);
+    bn[5] = __shfl_down_sync(0xffffffffu, bn[1], 1);
+    // ---- Hessian of row yh = r - 4 from blurred rows yh-1 (bm), yh (bc), yh+1 (bn)
+    const int yh = r - 4;
+    if (yh >= Y0) {  // warp-uniform
+      float out[4];
+      const bool row_interior = yh >= 1 && yh < g.h - 1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int x = c0 + c;
+        const float v11 = bm[c], v12 = bm[c + 1], v13 = bm[c + 2];
+        const float v21 = bc[c], v22 = bc[c + 1], v23 = bc[c + 2];
+        const float v31 = bn[c], v32 = bn[c + 1], v33 = bn[c + 2];
+        const float t2 = __fmul_rn(v22, 2.0f);
+        const float lxx = __fadd_rn(__fsub_rn(v21, t2), v23);
+        const float lyy = __fadd_rn(__fsub_rn(v12, t2), v32);
+        const float lxy = __fmul_rn(__fsub_rn(__fadd_rn(__fsub_rn(v13, v11), v31), v33), 0.25f);
+        const float rsp = __fsub_rn(__fmul_rn(lxx, lyy), __fmul_rn(lxy, lxy));
+        out[c] = (row_interior && x >= 1 && x < g.w - 1) ? rsp : 0.0f;
+      }
+      if (writer) {
+        const size_t o = (size_t)f * g.n_px + (size_t)yh * g.w + c0;
+        __stcs(reinterpret_cast<float4*>(resp + o), make_float4(out[0], out[1], out[2], out[3]));
+        if (WRITE_BLUR)
+          __stcs(reinterpret_cast<float4*>(blur + o), make_float4(bc[1], bc[2], bc[3], bc[4]));
+        mn = fminf(fminf(mn, fminf(out[0], out[1])), fminf(out[2], out[3]));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      bm[c] = bc[c];
+      bc[c] = bn[c];
+    }
+  }
+  mn = warp_min(mn);
+  if (lane == 0) atomicMin(&frame_min[f], float_to_ordered(mn));
+}
+
 __global__ void k_fill_u32(uint32_t* p, int n, uint32_t v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -259,7 +399,17 @@ int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames,
   int launches = 0;
   k_fill_u32<<<(n_frames + 255) / 256, 256, 0, s>>>(frame_min, n_frames, kOrderedFltMax);
   ++launches;
-  (void)variant;
+  const bool can_stream = g.format == AG_L8 && (g.w % 4) == 0 && g.w >= 8 && (g.row_stride % 4) == 0 &&
+                          (g.frame_stride % 4) == 0 && ((uintptr_t)frames % 4) == 0 && variant != 1;
+  if (can_stream) {
+    const int strips = (g.w + S_COLS - 1) / S_COLS;
+    dim3 grid((strips + S_WARPS - 1) / S_WARPS, (g.h + S_ROWS - 1) / S_ROWS, n_frames);
+    if (write_blur)
+      k_blur_hessian_stream<true><<<grid, S_WARPS * 32, 0, s>>>(frames, g, blur, resp, frame_min);
+    else
+      k_blur_hessian_stream<false><<<grid, S_WARPS * 32, 0, s>>>(frames, g, blur, resp, frame_min);
+    return launches + 1;
+  }
   switch (g.format) {
     case AG_L8: launch_tile<AG_L8>(frames, g, n_frames, blur, resp, frame_min, write_blur, s); break;
     case AG_L16: launch_tile<AG_L16>(frames, g, n_frames, blur, resp, frame_min, write_blur, s); break;

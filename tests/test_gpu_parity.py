@@ -107,6 +107,23 @@ def test_tiny_and_odd_shapes(detector, oracle, shape):
     check_stages(detector, oracle, img)
 
 
+@pytest.mark.parametrize("shape", [(5, 8), (3, 12), (17, 120), (9, 124), (130, 244), (33, 1280), (300, 364)])
+def test_streaming_dense_kernel_shapes(detector, oracle, shape):
+    """Widths that are multiples of 4 take the register-marching K1; strip / chunk edge cases."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    g, o = check_stages(detector, oracle, img, check_board=False)
+    # the generic tile kernel must give the same bits
+    detector.set_option("dense_variant", 1)
+    try:
+        g2 = detector.stages(img)
+    finally:
+        detector.set_option("dense_variant", 0)
+    assert np.array_equal(g["blur"].view(np.uint32), g2["blur"].view(np.uint32))
+    assert np.array_equal(g["resp"].view(np.uint32), g2["resp"].view(np.uint32))
+    assert g["min"] == g2["min"]
+
+
 def test_constant_image_gives_empty_map(detector, oracle):
     for v in (0, 128, 255):
         img = np.full((48, 64), v, np.uint8)
