@@ -164,8 +164,12 @@ AG_D float u8_lane(uint32_t word, int k) {  // byte k of a packed pixel word -> 
   return unorm8_to_f32((float)((word >> (8 * k)) & 0xffu));
 }
 
+struct BlurRow {  // one blurred row: v[1..4] = the lane's 4 columns, v[0] / v[5] = halo columns
+  float v[6];
+};
+
 template <bool WRITE_BLUR>
-__global__ void __launch_bounds__(S_WARPS * 32, 4)
+__global__ void __launch_bounds__(S_WARPS * 32, 5)
 k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __restrict__ blur,
                       float* __restrict__ resp, uint32_t* __restrict__ frame_min) {
   const int lane = threadIdx.x & 31;
@@ -175,36 +179,43 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
   const int f = blockIdx.z;
   const int Y0 = blockIdx.y * S_ROWS, Y1 = min(Y0 + S_ROWS, g.h);
   const int c0 = X0 - 4 + 4 * lane;  // first of this lane's 4 columns (may lie outside the image)
-  const uint8_t* frame = frames + (size_t)f * g.frame_stride;
   const int cw = min(max(c0, 0), g.w - 4);  // column of the word actually loaded
+  const uint8_t* src = frames + (size_t)f * g.frame_stride + cw;
   const bool left_out = c0 < 0, right_out = c0 >= g.w;
   const bool writer = lane >= 1 && lane <= 30 && !right_out;
+  const bool zero_first = c0 == 0, zero_last = c0 + 3 == g.w - 1;  // image border columns
   const float k0 = c_taps[0], k1 = c_taps[1], k2 = c_taps[2], k3 = c_taps[3];
+  const int h1 = g.h - 1;
+  const size_t rs = g.row_stride;
 
   auto load_row = [&](int r) -> uint32_t {
-    const int rr = min(max(r, 0), g.h - 1);
-    uint32_t wd = __ldg(reinterpret_cast<const uint32_t*>(frame + (size_t)rr * g.row_stride + cw));
-    if (left_out) wd = (wd & 0xffu) * 0x01010101u;   // replicate pixel 0
-    if (right_out) wd = (wd >> 24) * 0x01010101u;    // replicate pixel w-1
-    return wd;
+    const int rr = min(max(r, 0), h1);
+    return __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)rr * rs));
   };
 
-  // vertical partial sums: a[j][c] = sum so far of the output row that still needs 7-j.. terms
+  // vertical partial sums: aj[c] = what output row (r + 3 - j) has accumulated so far
   float a1[4], a2[4], a3[4], a4[4], a5[4], a6[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) a1[c] = a2[c] = a3[c] = a4[c] = a5[c] = a6[c] = 0.0f;
-  // blurred rows: bm = row y-1, bc = row y, (new row = y+1); [0] = left halo column, [5] = right halo
-  float bm[6], bc[6];
+  BlurRow R0, R1, R2;
 #pragma unroll
-  for (int c = 0; c < 6; ++c) bm[c] = bc[c] = 0.0f;
+  for (int c = 0; c < 6; ++c) R0.v[c] = R1.v[c] = R2.v[c] = 0.0f;
   float mn = 3.40282347e+38f;
+  float* resp_f = resp + (size_t)f * g.n_px + c0;
+  float* blur_f = blur + (size_t)f * g.n_px + c0;
 
   const int r_begin = Y0 - 4, r_end = Y1 + 3;  // temp rows r_begin..r_end inclusive
-  uint32_t w_next = load_row(r_begin), w_next2 = load_row(r_begin + 1);
-  for (int r = r_begin; r <= r_end; ++r) {
-    const uint32_t wd = w_next;
-    w_next = w_next2;
-    w_next2 = load_row(r + 2);  // prefetch two rows ahead
+  uint32_t w_cur = load_row(r_begin), w_n1 = load_row(r_begin + 1), w_n2 = load_row(r_begin + 2);
+
+  // One row step: consumes raw row r, completes blurred row r-3 into N, emits Hessian row r-4
+  // from M (row r-5), C (row r-4), N (row r-3).
+  auto step = [&](int r, const BlurRow& M, const BlurRow& C, BlurRow& N) {
+    uint32_t wd = w_cur;
+    w_cur = w_n1;
+    w_n1 = w_n2;
+    w_n2 = load_row(r + 3);  // three rows ahead
+    if (left_out) wd = (wd & 0xffu) * 0x01010101u;  // replicate pixel 0
+    if (right_out) wd = (wd >> 24) * 0x01010101u;   // replicate pixel w-1
     // ---- gray conversion + halo exchange: p[0..9] = pixels c0-3 .. c0+6
     float p[10];
     p[3] = u8_lane(wd, 0); p[4] = u8_lane(wd, 1); p[5] = u8_lane(wd, 2); p[6] = u8_lane(wd, 3);
@@ -214,66 +225,62 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
     p[7] = __shfl_down_sync(0xffffffffu, p[3], 1);
     p[8] = __shfl_down_sync(0xffffffffu, p[4], 1);
     p[9] = __shfl_down_sync(0xffffffffu, p[5], 1);
-    // ---- horizontal pass (image_util.rs:138-185): val = 0; val += px * k[i], i = 0..6
-    float t[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      float v = __fmul_rn(p[c], k0);  // 0.0 + x*k0 == x*k0 (x >= 0)
-      v = __fadd_rn(v, __fmul_rn(p[c + 1], k1));
-      v = __fadd_rn(v, __fmul_rn(p[c + 2], k2));
-      v = __fadd_rn(v, __fmul_rn(p[c + 3], k3));
-      v = __fadd_rn(v, __fmul_rn(p[c + 4], k2));
-      v = __fadd_rn(v, __fmul_rn(p[c + 5], k1));
-      v = __fadd_rn(v, __fmul_rn(p[c + 6], k0));
-      t[c] = v;
+      // ---- horizontal pass (image_util.rs:138-185): val = 0; val += px * k[i], i = 0..6
+      //      (0.0 + x*k0 == x*k0 for x >= 0)
+      float t = __fmul_rn(p[c], k0);
+      t = __fadd_rn(t, __fmul_rn(p[c + 1], k1));
+      t = __fadd_rn(t, __fmul_rn(p[c + 2], k2));
+      t = __fadd_rn(t, __fmul_rn(p[c + 3], k3));
+      t = __fadd_rn(t, __fmul_rn(p[c + 4], k2));
+      t = __fadd_rn(t, __fmul_rn(p[c + 5], k1));
+      t = __fadd_rn(t, __fmul_rn(p[c + 6], k0));
+      // ---- vertical pass (image_util.rs:188-203): temp row r is tap i of output row r + 3 - i
+      const float q0 = __fmul_rn(t, k0), q1 = __fmul_rn(t, k1), q2 = __fmul_rn(t, k2),
+                  q3 = __fmul_rn(t, k3);
+      N.v[c + 1] = __fadd_rn(a6[c], q0);  // tap 6 completes row r - 3
+      a6[c] = __fadd_rn(a5[c], q1);       // tap 5 of row r - 2
+      a5[c] = __fadd_rn(a4[c], q2);       // tap 4 of row r - 1
+      a4[c] = __fadd_rn(a3[c], q3);       // tap 3 of row r
+      a3[c] = __fadd_rn(a2[c], q2);       // tap 2 of row r + 1
+      a2[c] = __fadd_rn(a1[c], q1);       // tap 1 of row r + 2
+      a1[c] = q0;                         // tap 0 of row r + 3 (0.0 + q0)
     }
-    // ---- vertical pass (image_util.rs:188-203): temp row r is tap i of output row r + 3 - i
-    float bn[6];  // completed blurred row r - 3
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float q0 = __fmul_rn(t[c], k0), q1 = __fmul_rn(t[c], k1), q2 = __fmul_rn(t[c], k2),
-                  q3 = __fmul_rn(t[c], k3);
-      bn[c + 1] = __fadd_rn(a6[c], q0);  // tap 6 completes row r - 3
-      a6[c] = __fadd_rn(a5[c], q1);      // tap 5 of row r - 2
-      a5[c] = __fadd_rn(a4[c], q2);      // tap 4 of row r - 1
-      a4[c] = __fadd_rn(a3[c], q3);      // tap 3 of row r
-      a3[c] = __fadd_rn(a2[c], q2);      // tap 2 of row r + 1
-      a2[c] = __fadd_rn(a1[c], q1);      // tap 1 of row r + 2
-      a1[c] = q0;                        // tap 0 of row r + 3 (0.0 + q0)
-    }
-    bn[0] = __shfl_up_sync(0xffffffffu, bn[4], 1);
-    bn[5] = __shfl_down_sync(0xffffffffu, bn[1], 1);
-    // ---- Hessian of row yh = r - 4 from blurred rows yh-1 (bm), yh (bc), yh+1 (bn)
+    N.v[0] = __shfl_up_sync(0xffffffffu, N.v[4], 1);
+    N.v[5] = __shfl_down_sync(0xffffffffu, N.v[1], 1);
+    // ---- Hessian of row yh = r - 4 (image_util.rs:83-106)
     const int yh = r - 4;
     if (yh >= Y0) {  // warp-uniform
-      float out[4];
-      const bool row_interior = yh >= 1 && yh < g.h - 1;
+      float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (yh >= 1 && yh < h1) {  // warp-uniform; border rows stay 0
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int x = c0 + c;
-        const float v11 = bm[c], v12 = bm[c + 1], v13 = bm[c + 2];
-        const float v21 = bc[c], v22 = bc[c + 1], v23 = bc[c + 2];
-        const float v31 = bn[c], v32 = bn[c + 1], v33 = bn[c + 2];
-        const float t2 = __fmul_rn(v22, 2.0f);
-        const float lxx = __fadd_rn(__fsub_rn(v21, t2), v23);
-        const float lyy = __fadd_rn(__fsub_rn(v12, t2), v32);
-        const float lxy = __fmul_rn(__fsub_rn(__fadd_rn(__fsub_rn(v13, v11), v31), v33), 0.25f);
-        const float rsp = __fsub_rn(__fmul_rn(lxx, lyy), __fmul_rn(lxy, lxy));
-        out[c] = (row_interior && x >= 1 && x < g.w - 1) ? rsp : 0.0f;
+        for (int c = 0; c < 4; ++c) {
+          const float t2 = __fmul_rn(C.v[c + 1], 2.0f);
+          const float lxx = __fadd_rn(__fsub_rn(C.v[c], t2), C.v[c + 2]);
+          const float lyy = __fadd_rn(__fsub_rn(M.v[c + 1], t2), N.v[c + 1]);
+          const float lxy =
+              __fmul_rn(__fsub_rn(__fadd_rn(__fsub_rn(M.v[c + 2], M.v[c]), N.v[c]), N.v[c + 2]), 0.25f);
+          o[c] = __fsub_rn(__fmul_rn(lxx, lyy), __fmul_rn(lxy, lxy));
+        }
+        if (zero_first) o[0] = 0.0f;
+        if (zero_last) o[3] = 0.0f;
       }
       if (writer) {
-        const size_t o = (size_t)f * g.n_px + (size_t)yh * g.w + c0;
-        __stcs(reinterpret_cast<float4*>(resp + o), make_float4(out[0], out[1], out[2], out[3]));
+        const size_t off = (size_t)yh * g.w;
+        __stcs(reinterpret_cast<float4*>(resp_f + off), make_float4(o[0], o[1], o[2], o[3]));
         if (WRITE_BLUR)
-          __stcs(reinterpret_cast<float4*>(blur + o), make_float4(bc[1], bc[2], bc[3], bc[4]));
-        mn = fminf(fminf(mn, fminf(out[0], out[1])), fminf(out[2], out[3]));
+          __stcs(reinterpret_cast<float4*>(blur_f + off), make_float4(C.v[1], C.v[2], C.v[3], C.v[4]));
+        mn = fminf(fminf(mn, fminf(o[0], o[1])), fminf(o[2], o[3]));
       }
     }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      bm[c] = bc[c];
-      bc[c] = bn[c];
-    }
+  };
+
+  // the three blurred rows rotate roles, so no register copies are needed
+  for (int r = r_begin; r <= r_end; r += 3) {
+    step(r, R0, R1, R2);
+    if (r + 1 <= r_end) step(r + 1, R1, R2, R0);
+    if (r + 2 <= r_end) step(r + 2, R2, R0, R1);
   }
   mn = warp_min(mn);
   if (lane == 0) atomicMin(&frame_min[f], float_to_ordered(mn));
