@@ -73,7 +73,7 @@ struct ag_detector {
   std::string err;
   Slot slot[2];
   uint64_t launches = 0;
-  long chunk_frames = 256;
+  long chunk_frames = 512;
   long max_clusters = 16384;
   long max_saddles = 2048;
   uint64_t* d_codes = nullptr;  // family table in global memory (renderer)

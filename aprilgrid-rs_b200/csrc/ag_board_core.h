@@ -518,28 +518,99 @@ AGB_FN int closest_candidates_single(const Frame& F, const BoardState& B, int a,
   return k;
 }
 
-// try_expand_one (board.rs:153-176).  The four neighbour searches are independent: lanes 0..3
-// run one each; the candidate 4-tuples are then tested in the reference's nested-loop order
-// (i0 outermost, i3 innermost), 32 at a time, and the first valid one wins.
+#if AGB_DEVICE
+// The four neighbour searches of try_expand_one on one warp: 8 lanes per search, each lane
+// scanning one row of grid buckets, then a 3-round minimum extraction inside the 8-lane group.
+// A candidate is the 64-bit key (d2 bits << 32 | index): d2 >= 0, so unsigned key order is the
+// (d2, index) order of nn_less.  Same candidates, same order as closest_candidates_single.
+__device__ __forceinline__ void expand_queries_warp(const Frame& F, const BoardState& B, const int q[4],
+                                                    int cand[4][3], int cnt[4]) {
+  const int grp = F.lane >> 3, sub = F.lane & 7;
+  // group 0: new_s0s (edge s0->s1, from s0)   group 1: new_s1s (edge s0->s1, from s1)
+  // group 2: new_s2s (edge s3->s2, from s2)   group 3: new_s3s (edge s3->s2, from s3)
+  const int a = grp < 2 ? q[0] : q[3], b = grp < 2 ? q[1] : q[2];
+  const int self = (grp == 1 || grp == 2) ? b : a;
+  const float ratio0 = fadd(1.0f, 0.3f);
+  const float ax = F.sx[a], ay = F.sy[a], bx = F.sx[b], by = F.sy[b];
+  const float dx = fsub(ax, bx), dy = fsub(ay, by);
+  const float r2 = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
+  const float v10x = fsub(bx, ax), v10y = fsub(by, ay);
+  const float qx = fadd(F.sx[self], fmul(v10x, ratio0)), qy = fadd(F.sy[self], fmul(v10y, ratio0));
+  const unsigned long long kInf = ~0ull;
+  unsigned long long k0 = kInf, k1 = kInf, k2 = kInf;
+  auto consider = [&](int i) {
+    const float d = dist2(F, qx, qy, i);
+    if (d <= r2) {
+      unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
+      if (k < k2) {
+        k2 = k;
+        if (k2 < k1) { unsigned long long t = k1; k1 = k2; k2 = t; }
+        if (k1 < k0) { unsigned long long t = k0; k0 = k1; k1 = t; }
+      }
+    }
+  };
+  if (F.g_on && r2 >= 0.0f && r2 < 1.0e12f) {
+    const float r = sqrtf(r2) * 1.0001f + 0.01f;
+    int x0 = (int)floorf((qx - r) * F.g_inv), x1 = (int)floorf((qx + r) * F.g_inv);
+    int y0 = (int)floorf((qy - r) * F.g_inv), y1 = (int)floorf((qy + r) * F.g_inv);
+    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
+    x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+    const int bw = x1 - x0 + 1;
+    if (bw > 0)
+      for (int yy = y0 + sub; yy <= y1; yy += 8) {
+        const int b0 = yy * F.g_nx + x0;
+        const int e1 = F.g_start[b0 + bw];
+        for (int e = F.g_start[b0]; e < e1; ++e) consider(F.g_item[e]);
+      }
+  } else {
+    for (int i = sub; i < F.n; i += 8) consider(i);
+  }
+  // three rounds of group-minimum extraction (xor 1, 2, 4 stay inside the aligned 8-lane group)
+  unsigned long long res[3];
+#pragma unroll
+  for (int rnd = 0; rnd < 3; ++rnd) {
+    unsigned long long m = k0;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+      m = other < m ? other : m;
+    }
+    res[rnd] = m;
+    if (k0 == m && m != kInf) { k0 = k1; k1 = k2; k2 = kInf; }
+  }
+  // lanes 0..2 of each group filter one candidate each (active mask, theta), board.rs:199-210
+  bool ok = false;
+  if (sub < 3) {
+    const unsigned long long k = sub == 0 ? res[0] : (sub == 1 ? res[1] : res[2]);
+    if (k != kInf) {
+      const int i = (int)(unsigned)k;
+      ok = is_active(B, i) && theta_distance_degree(F.st[self], F.st[i]) < 5.0f;
+    }
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, ok);
+  const int i0 = (int)(unsigned)res[0], i1 = (int)(unsigned)res[1], i2 = (int)(unsigned)res[2];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c0 = __shfl_sync(0xffffffffu, i0, g * 8);
+    const int c1 = __shfl_sync(0xffffffffu, i1, g * 8);
+    const int c2 = __shfl_sync(0xffffffffu, i2, g * 8);
+    const unsigned m = (bal >> (g * 8)) & 7u;
+    int n = 0;
+    if (m & 1u) cand[g][n++] = c0;
+    if (m & 2u) cand[g][n++] = c1;
+    if (m & 4u) cand[g][n++] = c2;
+    cnt[g] = n;
+  }
+}
+#endif
+
+// try_expand_one (board.rs:153-176).  The four neighbour searches are independent and run side
+// by side; the candidate 4-tuples are then tested in the reference's nested-loop order (i0
+// outermost, i3 innermost), 32 at a time, and the first valid one wins.
 AGB_NOINLINE bool try_expand_one(const Frame& F, const BoardState& B, const int q[4], int out[4]) {
   int cand[4][3], cnt[4];
 #if AGB_DEVICE
-  {
-    int mine[3] = {0, 0, 0}, mycnt = 0;
-    if (F.lane < 4) {
-      // lane 0: new_s0s (edge s0->s1, from s0)   lane 1: new_s1s (edge s0->s1, from s1)
-      // lane 2: new_s2s (edge s3->s2, from s2)   lane 3: new_s3s (edge s3->s2, from s3)
-      const int a = F.lane < 2 ? q[0] : q[3], b = F.lane < 2 ? q[1] : q[2];
-      const bool self_is_b = (F.lane == 1) || (F.lane == 2);
-      mycnt = closest_candidates_single(F, B, a, b, self_is_b, mine);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      cnt[k] = __shfl_sync(0xffffffffu, mycnt, k);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) cand[k][j] = __shfl_sync(0xffffffffu, mine[j], k);
-    }
-  }
+  expand_queries_warp(F, B, q, cand, cnt);
 #else
   cnt[0] = closest_candidates_single(F, B, q[0], q[1], false, cand[0]);
   cnt[1] = closest_candidates_single(F, B, q[0], q[1], true, cand[1]);
