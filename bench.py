@@ -209,10 +209,8 @@ def main():
     clocks = sampler.finish() if sampler else None
     det.set_option("profile", 0)
     stage = det.stage_times(reset=True)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    from aprilgrid_rs_b200 import shard
+    ms_max = shard.max_over_ranks(ms, device="cuda")
     value = world * B * args.steps / (ms_max * 1e-3)
     cnt_host = d_cnt.cpu().numpy() if args.workload == "detect" else None
 
@@ -234,10 +232,7 @@ def main():
             det.detect_batch_into(hf, h_out, h_cnt, h_status)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = shard.max_over_ranks(dt, device="cuda")
         assert np.array_equal(h_cnt, cnt_host), "host-path and device-path results differ"
         e2e = {"value": world * B * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(world * B * W * H),
