@@ -153,7 +153,19 @@ def main():
         raise SystemExit("bench.py needs a B200; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout at the first collective; keep stdout for the
+        # single JSON line by pointing fd 1 at stderr until the communicator exists.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     pkg = entry.load_package()
     det = pkg.TagDetector(pkg.TagFamily.T36H11, None, device=local)
     if args.chunk:
