@@ -59,7 +59,8 @@ struct Slot {
   // taps
   int32_t* d_tap_quads = nullptr;
   int* d_tap_nquads = nullptr;
-  BoardWsLayout layout{};
+  BoardWsLayout layout{};       // sized for the largest warps-per-frame (allocation)
+  BoardWsLayout layout_batch{};  // layout used when many frames are in flight (1 warp per frame)
 };
 
 }  // namespace
@@ -84,6 +85,10 @@ struct ag_detector {
   // optional per-stage timing (ag_set_option "profile"): CUDA events between the kernels
   long dense_variant = 0;   // 0 = streaming K1 where applicable, 1 = always the generic tile kernel
   long board_lattice = 64;  // side of the tag lattice a board may span (16 / 32 / 64)
+  // warps per frame in the board kernel: 0 = automatic (1 when a launch has enough frames to
+  // fill the GPU with one-warp blocks, 4 otherwise), or 1 / 2 / 4 / 8
+  long board_warps = 0;
+  long board_batch_frames = 296;  // automatic mode: launches with at least this many frames use 1 warp
   bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -195,7 +200,8 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     if ((rc = regrow(det, &S.d_raw, (size_t)F * ncl))) return rc;
     if ((rc = regrow(det, &S.d_raw_valid, (size_t)F * ncl))) return rc;
     if ((rc = regrow(det, &S.d_refined, (size_t)F * nsd))) return rc;
-    S.layout = make_board_layout(nsd, (int)det->board_lattice);
+    S.layout = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 4);
+    S.layout_batch = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 1);
     if ((rc = regrow(det, &S.d_board_ws, (size_t)F * S.layout.bytes_per_frame))) return rc;
     if ((rc = regrow(det, &S.d_tap_quads, (size_t)F * S.layout.max_quads * 4))) return rc;
     if ((rc = regrow(det, &S.d_tap_nquads, (size_t)F))) return rc;
@@ -291,8 +297,10 @@ int run_boards(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGe
                ag_tag* d_tags, int cap, int* d_ntags, uint32_t* d_status, bool taps,
                cudaStream_t s) {
   prof_mark(det, -1, s);
+  // throughput mode: one warp per frame once the launch alone can occupy every SM several times
+  const BoardWsLayout& BL = (det->board_warps == 0 && n >= det->board_batch_frames) ? S.layout_batch : S.layout;
   det->launches += launch_boards_decode(
-      d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, S.layout, det->fam.n_codes, det->fam.edge,
+      d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->fam.n_codes, det->fam.edge,
       det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
       d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout.max_quads,
       det->board_grid ? 1 : 0, s);
@@ -483,6 +491,14 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     if (value != 16 && value != 32 && value != 64) return fail(det, AG_ERR_INVALID, "board_lattice must be 16, 32 or 64");
     det->board_lattice = value;
     det->slot[0].cap_saddles = det->slot[1].cap_saddles = -1;  // force the board workspace to be rebuilt
+  } else if (!strcmp(key, "board_warps")) {
+    if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
+      return fail(det, AG_ERR_INVALID, "board_warps must be 0 (auto), 1, 2, 4 or 8");
+    det->board_warps = value;
+    det->slot[0].cap_saddles = det->slot[1].cap_saddles = -1;
+  } else if (!strcmp(key, "board_batch_frames")) {
+    if (value < 1) return fail(det, AG_ERR_INVALID, "board_batch_frames must be positive");
+    det->board_batch_frames = value;
   } else if (!strcmp(key, "board_grid")) {
     det->board_grid = value != 0;
   } else if (!strcmp(key, "profile")) {

@@ -15,9 +15,10 @@ int upload_codes(const uint64_t* codes, int n) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-constexpr int kBoardWarps = 4;  // warps per frame (one block per frame)
+constexpr int kMaxBoardWarps = 8;  // warps per frame (one block per frame): 1, 2, 4 or 8
 
-BoardWsLayout make_board_layout(int max_saddles, int lattice) {
+BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps) {
+  const int kBoardWarps = warps < 1 ? 1 : (warps > kMaxBoardWarps ? kMaxBoardWarps : warps);
   BoardWsLayout L;
   const int N = max_saddles;
   const int Q = N / 4 + 2;
@@ -86,7 +87,7 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice) {
   return L;
 }
 
-__global__ void __launch_bounds__(kBoardWarps * 32)
+__global__ void __launch_bounds__(kMaxBoardWarps * 32)
 k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
                 const ag_saddle* __restrict__ refined, const int* __restrict__ n_refined,
                 uint8_t* __restrict__ ws, BoardWsLayout L, int n_codes, int edge, int border,
@@ -105,7 +106,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   agb::Frame F;
   F.lane = lane;
   F.warp = warp;
-  F.n_warps = kBoardWarps;
+  F.n_warps = L.warps;
   F.lat = L.lattice;
   F.lat_off = L.lattice / 2;
   F.n = n_refined[f];
@@ -187,7 +188,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   }
   // saddles AoS -> SoA (block-wide)
   const ag_saddle* S = refined + (size_t)f * L.max_saddles;
-  for (int i = threadIdx.x; i < F.n; i += kBoardWarps * 32) {
+  for (int i = threadIdx.x; i < F.n; i += blockDim.x) {
     ag_saddle s = S[i];
     F.sx[i] = s.x;
     F.sy[i] = s.y;
@@ -233,14 +234,13 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
   const int blocks = n_frames;
   if (blocks == 0) return 0;
   const size_t smem = L.smem_per_block;
-  static size_t smem_configured = 0;
-  if (smem > smem_configured) {
-    if (cudaFuncSetAttribute(k_boards_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess)
-      return 0;
-    smem_configured = smem;
-  }
-  k_boards_decode<<<blocks, kBoardWarps * 32, smem, s>>>(
+  // per-device function attributes (cheap host calls; a process may drive several devices)
+  if (cudaFuncSetAttribute(k_boards_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(k_boards_decode, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+    return 0;
+  k_boards_decode<<<blocks, L.warps * 32, smem, s>>>(
       frames, g, n_frames, refined, n_refined, ws, L, n_codes, edge, border, hamming, max_boards,
       out, cap, n_out, frame_status, tap_quads, tap_n_quads, tap_cap, use_grid);
   return 1;

@@ -35,6 +35,14 @@
 #define AGB_NOINLINE __attribute__((noinline))
 #endif
 
+// Optional work counters for the host build (tools/board_work_counts.py); no-ops otherwise.
+#if defined(AGB_WORK_COUNTERS) && !defined(__CUDA_ARCH__)
+extern "C" long long agb_work_counters[32];
+#define AGB_COUNT(slot, n) (agb_work_counters[(slot) + 12 * agb_work_counters[31]] += (n))
+#else
+#define AGB_COUNT(slot, n) ((void)0)
+#endif
+
 namespace agb {
 
 constexpr int kMaxLattice = 64;  // lattice of tag positions: at most 64 x 64 (-32..31 per axis)
@@ -607,8 +615,17 @@ __device__ __forceinline__ void expand_queries_warp(const Frame& F, const BoardS
 // try_expand_one (board.rs:153-176).  The four neighbour searches are independent and run side
 // by side; the candidate 4-tuples are then tested in the reference's nested-loop order (i0
 // outermost, i3 innermost), 32 at a time, and the first valid one wins.
+#if defined(AGB_WORK_COUNTERS) && !defined(__CUDA_ARCH__)
+extern "C" void agb_note_key(int kind, unsigned long long key);
+#define AGB_NOTE(kind, key) agb_note_key(kind, key)
+#else
+#define AGB_NOTE(kind, key) ((void)0)
+#endif
 AGB_NOINLINE bool try_expand_one(const Frame& F, const BoardState& B, const int q[4], int out[4]) {
   int cand[4][3], cnt[4];
+  AGB_NOTE(0, ((unsigned long long)q[0] << 16) | q[1]);
+  AGB_NOTE(0, ((unsigned long long)q[3] << 16) | q[2]);
+  AGB_NOTE(1, ((unsigned long long)q[0] << 48) | ((unsigned long long)q[1] << 32) | ((unsigned long long)q[2] << 16) | q[3]);
 #if AGB_DEVICE
   expand_queries_warp(F, B, q, cand, cnt);
 #else
@@ -618,6 +635,8 @@ AGB_NOINLINE bool try_expand_one(const Frame& F, const BoardState& B, const int 
   cnt[3] = closest_candidates_single(F, B, q[3], q[2], false, cand[3]);
 #endif
   const int total = cnt[0] * cnt[1] * cnt[2] * cnt[3];
+  AGB_COUNT(4, 1);
+  AGB_COUNT(6, total);
   for (int base = 0; base < total; base += AGB_LANES) {
     const int c = base + F.lane;
     bool valid = false;
@@ -629,6 +648,7 @@ AGB_NOINLINE bool try_expand_one(const Frame& F, const BoardState& B, const int 
       i1 = r % cnt[1]; r /= cnt[1];
       i0 = r;
       valid = is_valid_quad(F, cand[0][i0], cand[1][i1], cand[2][i2], cand[3][i3]);
+      AGB_NOTE(2, ((unsigned long long)cand[0][i0] << 48) | ((unsigned long long)cand[1][i1] << 32) | ((unsigned long long)cand[2][i2] << 16) | cand[3][i3]);
     }
     const unsigned m = agb_ballot(valid);
     if (m) {
@@ -745,6 +765,7 @@ AGB_NOINLINE void board_fix_missing(Frame& F, BoardState& B) {
       float mx = fdiv(fadd(F.sx[ia], F.sx[ib]), 2.0f);
       float my = fdiv(fadd(F.sy[ia], F.sy[ib]), 2.0f);
       sidx[j] = nearest1(F, mx, my);
+      AGB_COUNT(7, F.n);
     }
     if (B.n_quads < F.max_quads && is_valid_quad(F, sidx[0], sidx[1], sidx[2], sidx[3])) {
       AGB_SYNC();
@@ -775,7 +796,9 @@ AGB_FN void unrank_pair(int c, int n, int* i, int* j) {
 // what the reference's strict `board.score > best_score` keeps.
 AGB_NOINLINE int process_seed(Frame& F, int s0) {
   F.seedbest.n_quads = F.seedbest.n_touched = F.seedbest.score = 0;
+  AGB_COUNT(0, 1);
   const int n_nn = nearest_k(F, F.sx[s0], F.sy[s0], 50);
+  AGB_COUNT(1, (long long)n_nn * F.n);
   int n_same = 0, n_diff = 0;
   for (int j = 1; j < n_nn; ++j) {  // nearest[1..]: the first hit is the seed itself
     const int si = F.nn_idx[j];
@@ -805,6 +828,7 @@ AGB_NOINLINE int process_seed(Frame& F, int s0) {
   for (int a = 0; a < n_same; ++a) {
     const int s1 = F.same[a];
     if (!((diag_ok[a >> 5] >> (a & 31)) & 1u)) continue;  // every quad with this (s0, s1) fails :31
+    AGB_COUNT(2, n_pairs);
     for (int base = 0; base < n_pairs; base += AGB_LANES) {
       const int c = base + F.lane;
       bool valid = false;
@@ -826,6 +850,7 @@ AGB_NOINLINE int process_seed(Frame& F, int s0) {
         quad[0] = s0; quad[2] = s1;
         if (c0 > 0.0f) { quad[1] = d0; quad[3] = d1; }
         else { quad[1] = d1; quad[3] = d0; }
+        AGB_COUNT(3, 1);
         board_build(F, F.bs, quad);  // Board::new(refined, active_mask, &q, 0.3, tree)
         if (F.bs.score > F.seedbest.score) board_save(F, F.bs, F.seedbest);
       }
@@ -888,6 +913,8 @@ AGB_NOINLINE int find_best_board(Frame& F) {
       n_seeds += (int)m;
 #endif
     }
+    AGB_COUNT(9, n_seeds);
+    AGB_COUNT(10, F.n);
     if (F.lane == 0) {
       F.ctl[0] = n_seeds;
       F.ctl[5] = F.g_on;
@@ -1062,6 +1089,9 @@ AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
 // Every warp of the frame's block calls it; warp 0 decodes and compacts.
 AGB_FN void detect_boards(Frame& F, int max_boards) {
   for (int round = 0; round < max_boards; ++round) {
+#if defined(AGB_WORK_COUNTERS) && !defined(__CUDA_ARCH__)
+    agb_work_counters[31] = round;
+#endif
     if (find_best_board(F) < 0) continue;  // block-uniform
     if (F.warp == 0) {
       BoardState& B = F.bs;
@@ -1085,6 +1115,7 @@ AGB_FN void detect_boards(Frame& F, int max_boards) {
             ++n_tap;
           }
           TagRec t;
+          AGB_COUNT(8, 1);
           if (decode_quad(F, q, &t)) {
             if (F.lane == 0) {
               F.tag_by_id[t.id] = t;  // HashMap::insert: a repeated id overwrites

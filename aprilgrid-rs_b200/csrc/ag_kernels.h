@@ -22,7 +22,7 @@ struct BoardWsLayout {
   size_t sm_pos, sm_gstart, sm_gitem, sm_hist, sm_ctl, sm_warp0;
   size_t smw_cell, smw_active, smw_small, smem_per_warp, smem_per_block;
 };
-BoardWsLayout make_board_layout(int max_saddles, int lattice);
+BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps);
 
 // ag_dense.cu
 int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames, float* blur,

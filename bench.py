@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default 1024; dense 256)")
     ap.add_argument("--chunk", type=int, default=0, help="override pipeline chunk_frames")
     ap.add_argument("--lattice", type=int, default=0, help="override board_lattice (16/32/64)")
+    ap.add_argument("--board-warps", type=int, default=-1, help="override board_warps (0 auto, 1/2/4/8)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -172,6 +173,8 @@ def main():
         det.set_option("chunk_frames", args.chunk)
     if args.lattice:
         det.set_option("board_lattice", args.lattice)
+    if args.board_warps >= 0:
+        det.set_option("board_warps", args.board_warps)
     B = args.batch or (1024 if args.workload == "detect" else 256)
     cap = 64
     stream = torch.cuda.Stream()  # a real (non-default) stream: the kernels and the events share it

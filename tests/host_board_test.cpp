@@ -8,6 +8,17 @@
 #include <vector>
 
 #include "ag_board_core.h"
+#if defined(AGB_WORK_COUNTERS)
+#include <set>
+extern "C" { long long agb_work_counters[32] = {0}; }
+static std::set<unsigned long long> g_keys[2][3];
+extern "C" void agb_note_key(int kind, unsigned long long key) {
+  int r = (int)agb_work_counters[31];
+  agb_work_counters[24 + kind] += 1;  // total (both rounds)
+  if (g_keys[r][kind].insert(key).second) agb_work_counters[27 + kind] += 1;  // distinct
+}
+extern "C" void agb_reset_keys() { for (auto& a : g_keys) for (auto& b : a) b.clear(); }
+#endif
 
 extern "C" {
 
