@@ -92,6 +92,7 @@ def lib():
         L.ag_detect.argtypes = [vp, vp, ci, ci, sz, ci, vp, ci, vp]
         L.ag_detect_batch.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp, ci, vp, vp]
         L.ag_detect_batch_device.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp, ci, vp, vp, vp]
+        L.ag_detect_batch_device_wait.argtypes = [vp, vp]
         L.ag_dense_batch_device.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp]
         L.ag_refined_saddle_points.argtypes = [vp, vp, ci, ci, sz, ci, vp, ci, vp]
         L.ag_gaussian_blur_f32.argtypes = [vp, vp, ci, ci, C.c_float, vp]
@@ -109,6 +110,7 @@ def lib():
         L.ag_stage_times.argtypes = [vp, vp, vp, ci]
         L.ag_render_boards_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, C.c_uint64, vp]
         L.ag_test_unorm_tables.argtypes = [vp, vp, vp, vp, vp]
+        L.ag_test_board_times.argtypes = [vp, ci, vp, ci]
         _lib = L
     return _lib
 
@@ -246,6 +248,11 @@ class TagDetector:
             C.c_void_p(d_out_ptr), cap_per_frame, C.c_void_p(d_counts_ptr),
             C.c_void_p(d_status_ptr) if d_status_ptr else None, C.c_void_p(stream) if stream else None))
 
+    def detect_batch_device_wait(self, stream=None):
+        """With option device_async = 1: order every detect_batch_device call issued so far on `stream`
+        (None = block the host thread)."""
+        return self._check(lib().ag_detect_batch_device_wait(self._h, C.c_void_p(stream) if stream else None))
+
     def dense_batch_device(self, d_frames_ptr, n_frames, width, height, fmt, stream=None):
         return self._check(lib().ag_dense_batch_device(
             self._h, C.c_void_p(d_frames_ptr), 0, n_frames, width, height, 0, fmt,
@@ -317,6 +324,12 @@ class TagDetector:
         self._check(L.ag_stage_tags(self._h, _p(tags), 1024, C.byref(n)))
         return dict(blur=blur, resp=resp, min=float(mt[0]), thr=float(mt[1]), mask=mask, labels=labels,
                     centers=centers, raw=raw, refined=ref, quads=quads, tags=_tags_to_dict(tags[:n.value]))
+
+    def _board_times(self, slot, n_frames):
+        """Profiling hook: n_frames x 16 u32 timing taps of the last board-kernel launch of a slot."""
+        out = np.zeros((n_frames, 16), np.uint32)
+        self._check(lib().ag_test_board_times(self._h, slot, _p(out), n_frames))
+        return out
 
     def _unorm_tables(self):
         o8, o16 = np.zeros(256, np.float32), np.zeros(65536, np.float32)

@@ -35,9 +35,15 @@ bool family_info(int family, FamilyInfo* f) {  // src/detector.rs:369-405
 
 std::string g_create_error;
 
+// Pipeline slots.  The device-batch path keeps up to kSlots chunks in flight: the dense + sparse
+// front end of chunk i+1 runs on the caller's stream while the latency-bound board searches of
+// chunks i, i-1, ... run on their slots' own streams, side by side.
+constexpr int kSlots = 4;
+
 // Device buffers of one pipeline slot (one chunk in flight).
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaStream_t bstream = nullptr;  // board search of this slot's chunk (device-batch pipeline)
   cudaEvent_t done = nullptr;
   cudaEvent_t ev_front = nullptr, ev_boards = nullptr;  // device-batch pipeline hand-offs
   bool boards_pending = false;
@@ -57,6 +63,7 @@ struct Slot {
   int* h_ntags = nullptr;
   uint32_t* h_status = nullptr;
   // taps
+  uint32_t* d_board_tm = nullptr;  // optional per-frame timing of the board kernel ([frames][16])
   int32_t* d_tap_quads = nullptr;
   int* d_tap_nquads = nullptr;
   BoardWsLayout layout{};       // sized for the largest warps-per-frame (allocation)
@@ -72,13 +79,15 @@ struct ag_detector {
   ag_params params{};
   std::mutex mu;
   std::string err;
-  Slot slot[2];
+  Slot slot[kSlots];
+  int slot_rr = 0;            // next slot of the device-batch pipeline (rotates across calls)
+  bool device_async = false;  // ag_detect_batch_device returns without ordering the results on the
+                              // caller's stream; ag_detect_batch_device_wait does that
   uint64_t launches = 0;
   long chunk_frames = 512;
   long max_clusters = 16384;
   long max_saddles = 2048;
   uint64_t* d_codes = nullptr;  // family table in global memory (renderer)
-  cudaStream_t board_stream = nullptr;  // boards+decode of chunk i overlap the dense stages of i+1
   // stage-tap state
   FrameGeom tap_geom{};
   bool tap_valid = false;
@@ -89,6 +98,8 @@ struct ag_detector {
   // fill the GPU with one-warp blocks, 4 otherwise), or 1 / 2 / 4 / 8
   long board_warps = 0;
   long board_batch_frames = 296;  // automatic mode: launches with at least this many frames use 1 warp
+  bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
+  bool board_fast = true;  // four-lane group scoring of candidate boards (0 = general path only)
   bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -161,6 +172,7 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
   int rc;
   if (!S.stream) {
     AG_CUDA(det, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    AG_CUDA(det, cudaStreamCreateWithFlags(&S.bstream, cudaStreamNonBlocking));
     AG_CUDA(det, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
     AG_CUDA(det, cudaEventCreateWithFlags(&S.ev_front, cudaEventDisableTiming));
     AG_CUDA(det, cudaEventCreateWithFlags(&S.ev_boards, cudaEventDisableTiming));
@@ -205,6 +217,7 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     if ((rc = regrow(det, &S.d_board_ws, (size_t)F * S.layout.bytes_per_frame))) return rc;
     if ((rc = regrow(det, &S.d_tap_quads, (size_t)F * S.layout.max_quads * 4))) return rc;
     if ((rc = regrow(det, &S.d_tap_nquads, (size_t)F))) return rc;
+    if ((rc = regrow(det, &S.d_board_tm, (size_t)F * 16))) return rc;
     if (S.h_ntags) cudaFreeHost(S.h_ntags);
     if (S.h_status) cudaFreeHost(S.h_status);
     AG_CUDA(det, cudaMallocHost((void**)&S.h_ntags, sizeof(int) * F));
@@ -237,7 +250,7 @@ void free_slot(Slot& S) {
   cudaFree(S.d_status); cudaFree(S.d_parent); cudaFree(S.d_acc); cudaFree(S.d_ncl);
   cudaFree(S.d_nref); cudaFree(S.d_ntags); cudaFree(S.d_centers); cudaFree(S.d_raw);
   cudaFree(S.d_refined); cudaFree(S.d_raw_valid); cudaFree(S.d_board_ws); cudaFree(S.d_tags);
-  cudaFree(S.d_tap_quads); cudaFree(S.d_tap_nquads);
+  cudaFree(S.d_tap_quads); cudaFree(S.d_tap_nquads); cudaFree(S.d_board_tm);
   if (S.h_tags) cudaFreeHost(S.h_tags);
   if (S.h_ntags) cudaFreeHost(S.h_ntags);
   if (S.h_status) cudaFreeHost(S.h_status);
@@ -245,6 +258,7 @@ void free_slot(Slot& S) {
   if (S.ev_front) cudaEventDestroy(S.ev_front);
   if (S.ev_boards) cudaEventDestroy(S.ev_boards);
   if (S.stream) cudaStreamDestroy(S.stream);
+  if (S.bstream) cudaStreamDestroy(S.bstream);
   S = Slot();
 }
 
@@ -303,7 +317,7 @@ int run_boards(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGe
       d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->fam.n_codes, det->fam.edge,
       det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
       d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout.max_quads,
-      det->board_grid ? 1 : 0, s);
+      det->board_grid ? 1 : 0, det->board_fast ? 1 : 0, det->board_timing ? S.d_board_tm : nullptr, s);
   prof_mark(det, 4, s);
   AG_CUDA(det, cudaGetLastError());
   return AG_OK;
@@ -464,9 +478,7 @@ void ag_destroy(ag_detector* det) {
   if (!det) return;
   cudaSetDevice(det->device);
   cudaDeviceSynchronize();
-  free_slot(det->slot[0]);
-  free_slot(det->slot[1]);
-  if (det->board_stream) cudaStreamDestroy(det->board_stream);
+  for (auto& S : det->slot) free_slot(S);
   for (auto e : det->ev_pool) cudaEventDestroy(e);
   cudaFree(det->d_codes);
   cudaFree(det->d_f32_a); cudaFree(det->d_f32_b); cudaFree(det->d_f32_c); cudaFree(det->d_taps);
@@ -490,15 +502,21 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "board_lattice")) {
     if (value != 16 && value != 32 && value != 64) return fail(det, AG_ERR_INVALID, "board_lattice must be 16, 32 or 64");
     det->board_lattice = value;
-    det->slot[0].cap_saddles = det->slot[1].cap_saddles = -1;  // force the board workspace to be rebuilt
+    for (auto& S : det->slot) S.cap_saddles = -1;  // force the board workspace to be rebuilt
   } else if (!strcmp(key, "board_warps")) {
     if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
       return fail(det, AG_ERR_INVALID, "board_warps must be 0 (auto), 1, 2, 4 or 8");
     det->board_warps = value;
-    det->slot[0].cap_saddles = det->slot[1].cap_saddles = -1;
+    for (auto& S : det->slot) S.cap_saddles = -1;
+  } else if (!strcmp(key, "device_async")) {
+    det->device_async = value != 0;
   } else if (!strcmp(key, "board_batch_frames")) {
     if (value < 1) return fail(det, AG_ERR_INVALID, "board_batch_frames must be positive");
     det->board_batch_frames = value;
+  } else if (!strcmp(key, "board_timing")) {
+    det->board_timing = value != 0;
+  } else if (!strcmp(key, "board_fast")) {
+    det->board_fast = value != 0;
   } else if (!strcmp(key, "board_grid")) {
     det->board_grid = value != 0;
   } else if (!strcmp(key, "profile")) {
@@ -550,23 +568,19 @@ int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
   const int chunk = (int)std::min<long>(det->chunk_frames, std::max(n_frames, 1));
-  const int n_slots = n_frames > chunk ? 2 : 1;
-  for (int i = 0; i < n_slots; ++i)
-    if ((rc = ensure_slot(det, det->slot[i], g, chunk, 1, false, true))) return rc;
-  if (n_slots == 1 && det->slot[1].boards_pending) {
-    AG_CUDA(det, cudaEventSynchronize(det->slot[1].ev_boards));
-    det->slot[1].boards_pending = false;
-  }
-  if (!det->board_stream)
-    AG_CUDA(det, cudaStreamCreateWithFlags(&det->board_stream, cudaStreamNonBlocking));
   cudaStream_t s = stream ? (cudaStream_t)stream : det->slot[0].stream;
-  cudaStream_t sb = det->board_stream;
-  // Two-deep software pipeline: the dense + sparse front end of chunk i+1 (stream s) overlaps
-  // the latency-bound board search of chunk i (stream sb).  Slots alternate; a slot is reused
-  // only after its board kernel has finished.
-  int which = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk, which ^= 1) {
-    Slot& S = det->slot[which];
+  if (!stream && !det->slot[0].stream) {
+    if ((rc = ensure_slot(det, det->slot[0], g, chunk, 1, false, true))) return rc;
+    s = det->slot[0].stream;
+  }
+  // Software pipeline over kSlots slots: the dense + sparse front end of a chunk runs on stream s,
+  // its board search on the slot's own stream, so the searches of up to kSlots chunks (of this
+  // call and of earlier calls) overlap each other and the front end of the following chunks.
+  // A slot is reused only after its board kernel has finished.
+  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    Slot& S = det->slot[det->slot_rr];
+    det->slot_rr = (det->slot_rr + 1) % kSlots;
+    if ((rc = ensure_slot(det, S, g, chunk, 1, false, true))) return rc;
     const int n = std::min(chunk, n_frames - f0);
     const uint8_t* in = (const uint8_t*)d_frames + (size_t)f0 * g.frame_stride;
     uint32_t* st = d_frame_status ? d_frame_status + f0 : S.d_status;
@@ -574,16 +588,30 @@ int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_
     if ((rc = run_dense(det, S, in, g, n, true, s))) return rc;
     if ((rc = run_sparse(det, S, g, n, st, s))) return rc;
     AG_CUDA(det, cudaEventRecord(S.ev_front, s));
-    AG_CUDA(det, cudaStreamWaitEvent(sb, S.ev_front, 0));
+    AG_CUDA(det, cudaStreamWaitEvent(S.bstream, S.ev_front, 0));
     if ((rc = run_boards(det, S, in, g, n, d_out + (size_t)f0 * cap_per_frame, cap_per_frame,
-                         d_n_per_frame + f0, st, false, sb)))
+                         d_n_per_frame + f0, st, false, S.bstream)))
       return rc;
-    AG_CUDA(det, cudaEventRecord(S.ev_boards, sb));
+    AG_CUDA(det, cudaEventRecord(S.ev_boards, S.bstream));
     S.boards_pending = true;
   }
-  // results become visible in the caller's stream order
-  for (int i = 0; i < n_slots; ++i)
-    if (det->slot[i].boards_pending) AG_CUDA(det, cudaStreamWaitEvent(s, det->slot[i].ev_boards, 0));
+  // results become visible in the caller's stream order (unless the caller asked to do that
+  // itself with ag_detect_batch_device_wait, which lets consecutive calls overlap)
+  if (!det->device_async)
+    for (auto& S : det->slot)
+      if (S.boards_pending) AG_CUDA(det, cudaStreamWaitEvent(s, S.ev_boards, 0));
+  return AG_OK;
+}
+
+int ag_detect_batch_device_wait(ag_detector* det, void* stream) {
+  if (!det) return AG_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  for (auto& S : det->slot) {
+    if (!S.boards_pending) continue;
+    if (stream) AG_CUDA(det, cudaStreamWaitEvent((cudaStream_t)stream, S.ev_boards, 0));
+    else AG_CUDA(det, cudaEventSynchronize(S.ev_boards));
+  }
   return AG_OK;
 }
 
@@ -916,6 +944,19 @@ int ag_render_boards_device(ag_detector* det, void* d_frames, int n_frames, int 
                                           (cudaStream_t)stream);
   }
   AG_CUDA(det, cudaGetLastError());
+  return AG_OK;
+}
+
+// Profiling hook (not in the public header): per-frame timing taps of the last board-kernel launch
+// on pipeline slot `slot` (needs ag_set_option("board_timing", 1)); out = n_frames x 16 u32.
+AG_API int ag_test_board_times(ag_detector* det, int slot, uint32_t* out, int n_frames) {
+  if (!det || slot < 0 || slot > 1 || !out) return AG_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  Slot& S = det->slot[slot];
+  if (!S.d_board_tm || n_frames > S.cap_frames) return fail(det, AG_ERR_INVALID, "no timing data");
+  AG_CUDA(det, cudaDeviceSynchronize());
+  AG_CUDA(det, cudaMemcpy(out, S.d_board_tm, sizeof(uint32_t) * 16 * (size_t)n_frames, cudaMemcpyDeviceToHost));
   return AG_OK;
 }
 

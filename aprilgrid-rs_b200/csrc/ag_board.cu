@@ -1,8 +1,11 @@
 // K6/K7: board assembly + tag decoding, one warp per frame (see ag_board_core.h).
 // reference: src/detector.rs:505-639, src/board.rs, src/saddle.rs.
 #include "ag_board_core.h"
+#include "ag_board_fast.cuh"
 #include "ag_common.cuh"
 #include "ag_kernels.h"
+
+#include <algorithm>
 
 namespace ag {
 
@@ -68,10 +71,17 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps) {
     return r;
   };
   L.sm_pos = stake(sizeof(float) * 3 * L.smem_saddles);
-  L.sm_gstart = stake(sizeof(uint16_t) * (L.grid_cap_cells + 1));
+  L.sm_gstart = stake(sizeof(uint16_t) * (L.grid_cap_cells + 2));
   L.sm_gitem = stake(sizeof(uint16_t) * L.smem_saddles);
   L.sm_hist = stake(sizeof(int) * agb::kHistBins);
   L.sm_ctl = stake(sizeof(int) * 16);
+  // throughput path (ag_board_fast.cuh)
+  L.sm_qlist = stake(sizeof(int16_t) * 4 * agb::kQListCap);
+  L.sm_qscore = stake(sizeof(uint16_t) * agb::kQListCap);
+  L.sm_fvec = stake(sizeof(float) * 64 * 4);
+  L.sm_elig = stake(64);
+  L.sm_squeue = stake(sizeof(uint32_t) * 64);
+  L.sm_wave = stake(32 * (sizeof(uint16_t) + 4 * sizeof(int16_t) + 2));
   L.sm_warp0 = sm;
   size_t sw = 0;
   auto swtake = [&](size_t bytes) {
@@ -79,7 +89,8 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps) {
     sw = align_up(sw + bytes, 16);
     return r;
   };
-  L.smw_cell = swtake(sizeof(int16_t) * cells);
+  // the lattice region doubles as the eight 1 KB group states of the throughput path
+  L.smw_cell = swtake(std::max(sizeof(int16_t) * cells, (size_t)agb::kGroupsPerWarp * agb::kGroupBytes));
   L.smw_active = swtake(sizeof(uint32_t) * ((N + 31) / 32));
   L.smw_small = swtake(sizeof(int16_t) * 64 * 4);  // nn_idx, same, diff, samp
   L.smem_per_warp = sw;
@@ -94,7 +105,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
                 int hamming, int max_boards, ag_tag* __restrict__ out, int cap,
                 int* __restrict__ n_out, uint32_t* __restrict__ frame_status,
                 int32_t* __restrict__ tap_quads, int* __restrict__ tap_n_quads, int tap_cap,
-                int use_grid) {
+                int use_grid, int fast, uint32_t* __restrict__ timing) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -138,7 +149,8 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   {
     int bucket = 32;
     while (((g.w + bucket - 1) / bucket) * ((g.h + bucket - 1) / bucket) > L.grid_cap_cells) bucket *= 2;
-    F.g_start = use_grid ? (uint16_t*)(smem + L.sm_gstart) : nullptr;
+    F.g_base = use_grid ? (uint16_t*)(smem + L.sm_gstart) : nullptr;
+    F.g_start = F.g_base;
     F.g_item = (uint16_t*)(smem + L.sm_gitem);
     F.g_nx = (g.w + bucket - 1) / bucket;
     F.g_ny = (g.h + bucket - 1) / bucket;
@@ -172,6 +184,28 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.tap_n_quads = tap_n_quads ? tap_n_quads + f : nullptr;
   F.tap_cap = tap_cap;
   F.status = 0;
+  F.active_words = (L.max_saddles + 31) / 32;
+  F.tm = timing ? timing + (size_t)f * 16 : nullptr;
+  unsigned long long t_start = 0;
+  if (F.tm) {
+    if (threadIdx.x < 16) F.tm[threadIdx.x] = 0u;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+  }
+  F.fx_qlist = (int16_t*)(smem + L.sm_qlist);
+  F.fx_qscore = (uint16_t*)(smem + L.sm_qscore);
+  F.fx_dvx = (float*)(smem + L.sm_fvec);
+  F.fx_dvy = F.fx_dvx + 64;
+  F.fx_dth = F.fx_dvy + 64;
+  F.fx_dc = F.fx_dth + 64;
+  F.fx_elig = smem + L.sm_elig;
+  F.fx_squeue = (uint32_t*)(smem + L.sm_squeue);
+  F.fx_gstate = SW + L.smw_cell;
+  F.fx_wscore = (uint16_t*)(smem + L.sm_wave);
+  F.fx_wquad = (int16_t*)(F.fx_wscore + 32);
+  F.fx_wlo = (uint8_t*)(F.fx_wquad + 128);
+  F.fx_whi = F.fx_wlo + 32;
+  // block-uniform: the whole frame takes the throughput path or the general one
+  F.fast_on = (fast && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles) ? 1 : 0;
 
   // init: every warp clears its lattice and activates every saddle; warp 0 clears the tag map
   {
@@ -218,6 +252,13 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
     n += __popc(m);
   }
   if (lane == 0) {
+    if (F.tm) {
+      unsigned long long t_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      F.tm[0] = (uint32_t)(t_end - t_start);
+      F.tm[11] = (uint32_t)n_refined[f];
+      F.tm[12] = (uint32_t)F.fast_on;
+    }
     n_out[f] = n;
     uint32_t st = F.status;
     if (n > cap) st |= (uint32_t)AG_FRAME_TAG_OVERFLOW;
@@ -229,8 +270,8 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
                          const ag_saddle* refined, const int* n_refined, uint8_t* ws,
                          const BoardWsLayout& L, int n_codes, int edge, int border, int hamming,
                          int max_boards, ag_tag* out, int cap, int* n_out, uint32_t* frame_status,
-                         int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid,
-                         cudaStream_t s) {
+                         int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid, int fast,
+                         uint32_t* timing, cudaStream_t s) {
   const int blocks = n_frames;
   if (blocks == 0) return 0;
   const size_t smem = L.smem_per_block;
@@ -242,7 +283,7 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
     return 0;
   k_boards_decode<<<blocks, L.warps * 32, smem, s>>>(
       frames, g, n_frames, refined, n_refined, ws, L, n_codes, edge, border, hamming, max_boards,
-      out, cap, n_out, frame_status, tap_quads, tap_n_quads, tap_cap, use_grid);
+      out, cap, n_out, frame_status, tap_quads, tap_n_quads, tap_cap, use_grid, fast, timing);
   return 1;
 }
 

@@ -116,6 +116,20 @@ struct Frame {
   int tap_cap;
   uint32_t status;
   int lane;  // 0 on host
+  // throughput path (device only, ag_board_fast.cuh); unused when fast_on == 0
+  int fast_on;
+  uint16_t* g_base;      // unshifted bucket-grid array ([cells + 2])
+  int active_words;      // words of bs.active
+  int16_t* fx_qlist;     // [kQListCap][4] candidate quads of the current seed
+  uint16_t* fx_qscore;   // [kQListCap]
+  float *fx_dvx, *fx_dvy, *fx_dth, *fx_dc;  // [64] per `diff` entry
+  uint8_t* fx_elig;      // [64]
+  uint32_t* fx_squeue;   // [64] ring of pairs that passed the cheap gates
+  uint8_t* fx_gstate;    // this warp's group states (aliases bs.cell)
+  uint16_t* fx_wscore;   // [32] per wave slot: best score of the seed so far
+  int16_t* fx_wquad;     // [32][4] ... and its quad
+  uint8_t *fx_wlo, *fx_whi;  // [32] the slot's range in the current list batch
+  uint32_t* tm;          // optional per-frame timing / work counters ([16], may be null)
 };
 
 // ---- warp plumbing ---------------------------------------------------------------------
@@ -859,6 +873,61 @@ AGB_NOINLINE int process_seed(Frame& F, int s0) {
   return F.seedbest.score;
 }
 
+// Most populated round(theta) bin -> seed list (detector.rs:601-616); one warp.  Leaves the
+// number of seeds in F.ctl[0] and the grid flag in F.ctl[5].
+AGB_NOINLINE void select_seeds(Frame& F) {
+  // histogram of round(theta)
+  for (int b = F.lane; b < kHistBins; b += AGB_LANES) F.hist[b] = 0;
+  AGB_SYNC();
+  for (int i = F.lane; i < F.n; i += AGB_LANES) {
+    int key = sat_i32(roundf(F.st[i])) + 90;
+    key = key < 0 ? 0 : (key >= kHistBins ? kHistBins - 1 : key);
+#if AGB_DEVICE
+    atomicAdd(&F.hist[key], 1);
+#else
+    F.hist[key] += 1;
+#endif
+  }
+  AGB_SYNC();
+  int best_cnt = -1, best_key = -1;
+  for (int b = F.lane; b < kHistBins; b += AGB_LANES) {
+    int c = F.hist[b];
+    if (c > best_cnt || (c == best_cnt && b > best_key)) { best_cnt = c; best_key = b; }
+  }
+#if AGB_DEVICE
+  for (int o = 16; o > 0; o >>= 1) {
+    int oc = __shfl_xor_sync(0xffffffffu, best_cnt, o);
+    int ok = __shfl_xor_sync(0xffffffffu, best_key, o);
+    if (oc > best_cnt || (oc == best_cnt && ok > best_key)) { best_cnt = oc; best_key = ok; }
+  }
+#endif
+  // seeds: members of that bin in ascending index order
+  int n_seeds = 0;
+  for (int base = 0; base < F.n; base += AGB_LANES) {
+    int i = base + F.lane;
+    bool in = false;
+    if (i < F.n) {
+      int key = sat_i32(roundf(F.st[i])) + 90;
+      key = key < 0 ? 0 : (key >= kHistBins ? kHistBins - 1 : key);
+      in = key == best_key;
+    }
+    unsigned m = agb_ballot(in);
+#if AGB_DEVICE
+    if (in) F.seeds[n_seeds + __popc(m & ((1u << F.lane) - 1u))] = (int16_t)i;
+    n_seeds += __popc(m);
+#else
+    if (in) F.seeds[n_seeds] = (int16_t)i;
+    n_seeds += (int)m;
+#endif
+  }
+  AGB_COUNT(9, n_seeds);
+  AGB_COUNT(10, F.n);
+  if (F.lane == 0) {
+    F.ctl[0] = n_seeds;
+    F.ctl[5] = F.g_on;
+  }
+}
+
 // try_find_best_board (detector.rs:588-639).  Seeds are handed to the warps of the block in
 // waves; after each wave the per-seed results are merged in the reference's seed order, with
 // its `score > best_score` replacement, its `best_score >= 36` early exit and its limit of 30
@@ -869,56 +938,7 @@ AGB_NOINLINE int find_best_board(Frame& F) {
   if (F.n == 0) return -1;
   if (F.warp == 0) {
     grid_build(F);
-    // histogram of round(theta)
-    for (int b = F.lane; b < kHistBins; b += AGB_LANES) F.hist[b] = 0;
-    AGB_SYNC();
-    for (int i = F.lane; i < F.n; i += AGB_LANES) {
-      int key = sat_i32(roundf(F.st[i])) + 90;
-      key = key < 0 ? 0 : (key >= kHistBins ? kHistBins - 1 : key);
-#if AGB_DEVICE
-      atomicAdd(&F.hist[key], 1);
-#else
-      F.hist[key] += 1;
-#endif
-    }
-    AGB_SYNC();
-    int best_cnt = -1, best_key = -1;
-    for (int b = F.lane; b < kHistBins; b += AGB_LANES) {
-      int c = F.hist[b];
-      if (c > best_cnt || (c == best_cnt && b > best_key)) { best_cnt = c; best_key = b; }
-    }
-#if AGB_DEVICE
-    for (int o = 16; o > 0; o >>= 1) {
-      int oc = __shfl_xor_sync(0xffffffffu, best_cnt, o);
-      int ok = __shfl_xor_sync(0xffffffffu, best_key, o);
-      if (oc > best_cnt || (oc == best_cnt && ok > best_key)) { best_cnt = oc; best_key = ok; }
-    }
-#endif
-    // seeds: members of that bin in ascending index order
-    int n_seeds = 0;
-    for (int base = 0; base < F.n; base += AGB_LANES) {
-      int i = base + F.lane;
-      bool in = false;
-      if (i < F.n) {
-        int key = sat_i32(roundf(F.st[i])) + 90;
-        key = key < 0 ? 0 : (key >= kHistBins ? kHistBins - 1 : key);
-        in = key == best_key;
-      }
-      unsigned m = agb_ballot(in);
-#if AGB_DEVICE
-      if (in) F.seeds[n_seeds + __popc(m & ((1u << F.lane) - 1u))] = (int16_t)i;
-      n_seeds += __popc(m);
-#else
-      if (in) F.seeds[n_seeds] = (int16_t)i;
-      n_seeds += (int)m;
-#endif
-    }
-    AGB_COUNT(9, n_seeds);
-    AGB_COUNT(10, F.n);
-    if (F.lane == 0) {
-      F.ctl[0] = n_seeds;
-      F.ctl[5] = F.g_on;
-    }
+    select_seeds(F);
   }
   AGB_BLOCK_SYNC();
   int seeds_left = F.ctl[0];
@@ -1087,12 +1107,20 @@ AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
 // TagDetector::detect from the refined saddle list on (detector.rs:510-538).
 // Workspace must be initialised by the caller: cells 0, active bits 1, tag_valid 0, counters 0.
 // Every warp of the frame's block calls it; warp 0 decodes and compacts.
+#if AGB_DEVICE
+__device__ int find_best_board_fast(Frame& F);  // ag_board_fast.cuh
+#endif
 AGB_FN void detect_boards(Frame& F, int max_boards) {
   for (int round = 0; round < max_boards; ++round) {
 #if defined(AGB_WORK_COUNTERS) && !defined(__CUDA_ARCH__)
     agb_work_counters[31] = round;
 #endif
-    if (find_best_board(F) < 0) continue;  // block-uniform
+#if AGB_DEVICE
+    const int found = F.fast_on ? find_best_board_fast(F) : find_best_board(F);
+#else
+    const int found = find_best_board(F);
+#endif
+    if (found < 0) continue;  // block-uniform
     if (F.warp == 0) {
       BoardState& B = F.bs;
       for (int i = F.lane; i < F.n; i += AGB_LANES) F.remove[i] = 0;
@@ -1161,7 +1189,7 @@ AGB_FN void detect_boards(Frame& F, int max_boards) {
       if (F.lane == 0) F.ctl[1] = n_new;
     }
     // saddle indices changed: every warp forgets its board
-    board_reset(F, F.bs);
+    if (!F.fast_on) board_reset(F, F.bs);
     AGB_BLOCK_SYNC();
     F.n = F.ctl[1];
     AGB_BLOCK_SYNC();

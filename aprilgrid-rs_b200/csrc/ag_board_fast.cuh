@@ -1,0 +1,650 @@
+// Throughput path of the board search (device only).  Same results as ag_board_core.h's
+// find_best_board, different mapping onto the warp:
+//
+//   * try_find_best_board (detector.rs:588-639) visits seeds one after the other; the seed's
+//     candidate quads (init_quads, detector.rs:543-586) are ENUMERATED first, in the
+//     reference's order, into a list;
+//   * every quad of the list is then SCORED by growing its board (Board::new + try_expand,
+//     board.rs:27-48, :114-176).  Board growth is a chain of dependent steps with four small
+//     neighbour searches each, so a whole warp per board wastes 28 lanes: here a GROUP OF FOUR
+//     LANES grows one board (lane j runs neighbour search j of try_expand_one), eight boards
+//     per warp side by side, each with a 1 KB state in shared memory (16 x 16 tag window,
+//     64 quads).  Only the score (= number of quads) is kept;
+//   * a board that leaves the small window or has more than 64 quads is re-scored by the
+//     general warp-wide board_build of ag_board_core.h (same result, any size);
+//   * the winning (seed, quad) -- first maximum in the reference's visiting order, with its
+//     strict `score > best_score`, `>= 36` early exit and 30-seed limit -- is rebuilt once
+//     with the general board_build, so everything downstream (try_fix_missing, decoding)
+//     runs on the same state as before.
+//
+// The enumeration of init_quads is reorganised so that the cheap gates of is_valid_quad
+// (saddle.rs:18-66) run first and only their survivors reach the transcendental gates; every
+// gate only ever rejects, so the set and the order of valid quads are those of the reference.
+#pragma once
+#include "ag_board_core.h"
+
+namespace agb {
+
+constexpr int kFastMaxSaddles = 512;  // saddle list and bucket grid live in shared memory
+constexpr int kGroupLanes = 4;
+constexpr int kGroupsPerWarp = 8;
+constexpr int kGroupBytes = 1024;
+constexpr int kGWin = 16;           // tag window per group: x, y in [-8, 7]
+constexpr int kGQuads = 64;         // quads per group board
+constexpr int kQListCap = 128;      // candidate quads buffered between enumeration and scoring
+constexpr int kScoreRedo = 0xffff;  // group board overflowed: score it with the general path
+// group state layout (bytes)
+constexpr int kGOffCell = 0;        // u8 [256]: 0 unvisited, 0xff None, q + 1 Some(q)
+constexpr int kGOffQuads = 256;     // i16 [64][4]
+constexpr int kGOffStack = 768;     // u16 [64]: cell | next direction << 8
+constexpr int kGOffActive = 896;    // u32 [16]: 512 saddles
+
+}  // namespace agb
+
+#if AGB_DEVICE
+namespace agb {
+
+// ---- bucket grid, built by the whole warp ------------------------------------------------------
+// Layout: G[0] = 0, G[b + 1] = first entry of bucket b, G[nc + 1] = n; F.g_start = G + 1.
+// Order inside a bucket is arbitrary: every query selects by the total order (d2, index).
+__device__ __noinline__ void grid_build_warp(Frame& F) {
+  F.g_on = 0;
+  if (!F.g_base) return;
+  const int nc = F.g_nx * F.g_ny;
+  if (F.n > F.g_cap_items || nc > F.g_cap_cells || F.n > 65535) return;
+  F.g_on = 1;
+  uint16_t* G = F.g_base;
+  for (int c = F.lane; c <= nc + 1; c += 32) G[c] = 0;
+  __syncwarp();
+  // counts into G[b + 1]
+  for (int base = 0; base < F.n; base += 32) {
+    const int i = base + F.lane;
+    const int b = i < F.n ? grid_bucket(F, F.sx[i], F.sy[i]) : (0x10000 + F.lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) G[b + 1] = (uint16_t)(G[b + 1] + __popc(peers));
+    __syncwarp();
+  }
+  // inclusive scan of G[1 .. nc]: afterwards G[b + 1] = end of bucket b
+  {
+    const int per = (nc + 31) / 32;
+    const int c0 = 1 + F.lane * per, c1 = min(c0 + per, nc + 1);
+    unsigned sum = 0;
+    for (int c = c0; c < c1; ++c) sum += G[c];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (F.lane >= o) incl += v;
+    }
+    unsigned run = incl - sum;
+    for (int c = c0; c < c1; ++c) {
+      run += G[c];
+      G[c] = (uint16_t)run;
+    }
+  }
+  __syncwarp();
+  // fill from the back of every bucket: G[b + 1] walks down from end(b) to start(b)
+  for (int base = 0; base < F.n; base += 32) {
+    const int i = base + F.lane;
+    const int b = i < F.n ? grid_bucket(F, F.sx[i], F.sy[i]) : (0x10000 + F.lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (i < F.n) {
+      const int rank = __popc(peers & ((1u << F.lane) - 1u));
+      const int e = G[b + 1];
+      F.g_item[e - 1 - rank] = (uint16_t)i;
+    }
+    __syncwarp();
+    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) G[b + 1] = (uint16_t)(G[b + 1] - __popc(peers));
+    __syncwarp();
+  }
+  if (F.lane == 0) G[nc + 1] = (uint16_t)F.n;
+  F.g_start = G + 1;
+  __syncwarp();
+}
+
+// ---- one neighbour search of try_expand_one on ONE lane ----------------------------------------
+// find_closest_potential_saddle_idxs (board.rs:177-234) for the edge a -> b seen from `self`:
+// the up to three nearest saddles within the radius, ascending by (d2, index), then filtered by
+// the board's active mask and the theta gate.  Returns the survivors packed as
+// count | c0 << 2 | c1 << 12 | c2 << 22 (indices < 1024).
+__device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* active, int a, int b,
+                                                int self) {
+  const float ratio0 = fadd(1.0f, 0.3f);  // 1.0 + spacing_ratio; detector.rs:621 passes 0.3
+  const float ax = F.sx[a], ay = F.sy[a], bx = F.sx[b], by = F.sy[b];
+  const float dx = fsub(ax, bx), dy = fsub(ay, by);
+  const float r2 = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
+  const float v10x = fsub(bx, ax), v10y = fsub(by, ay);
+  const float sfx = self == a ? ax : bx, sfy = self == a ? ay : by;
+  const float qx = fadd(sfx, fmul(v10x, ratio0)), qy = fadd(sfy, fmul(v10y, ratio0));
+  const unsigned long long kInf = ~0ull;
+  unsigned long long k0 = kInf, k1 = kInf, k2 = kInf;
+  auto consider = [&](int i) {
+    const float d = dist2(F, qx, qy, i);
+    if (d <= r2) {
+      const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
+      if (k < k2) {
+        k2 = k;
+        if (k2 < k1) { const unsigned long long t = k1; k1 = k2; k2 = t; }
+        if (k1 < k0) { const unsigned long long t = k0; k0 = k1; k1 = t; }
+      }
+    }
+  };
+  if (F.g_on && r2 >= 0.0f && r2 < 1.0e12f) {
+    const float r = sqrtf(r2) * 1.0001f + 0.01f;
+    int x0 = (int)floorf((qx - r) * F.g_inv), x1 = (int)floorf((qx + r) * F.g_inv);
+    int y0 = (int)floorf((qy - r) * F.g_inv), y1 = (int)floorf((qy + r) * F.g_inv);
+    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
+    x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+    const int bw = x1 - x0 + 1;
+    if (bw > 0)
+      for (int yy = y0; yy <= y1; ++yy) {
+        const int b0 = yy * F.g_nx + x0;
+        const int e1 = F.g_start[b0 + bw];
+        for (int e = F.g_start[b0]; e < e1; ++e) consider(F.g_item[e]);
+      }
+  } else {
+    for (int i = 0; i < F.n; ++i) consider(i);
+  }
+  const float ts = F.st[self];
+  unsigned packed = 0, cnt = 0;
+  auto keep = [&](unsigned long long k) {
+    if (k == kInf) return;
+    const int i = (int)(unsigned)k;
+    if (((active[i >> 5] >> (i & 31)) & 1u) && theta_distance_degree(ts, F.st[i]) < 5.0f) {
+      packed |= (unsigned)i << (2 + 10 * cnt);
+      ++cnt;
+    }
+  };
+  keep(k0);
+  keep(k1);
+  keep(k2);
+  return packed | cnt;
+}
+__device__ __forceinline__ int packed_count(unsigned p) { return (int)(p & 3u); }
+__device__ __forceinline__ int packed_cand(unsigned p, int k) { return (int)((p >> (2 + 10 * k)) & 0x3ffu); }
+
+// ---- Board::new + try_expand (board.rs:27-48, :114-176), eight boards per warp --------------------
+// Scores the quads F.fx_qlist[0 .. nq): score = number of quads of the grown board, or kScoreRedo
+// when the board leaves the group window / quad capacity.  A group of four lanes grows one board;
+// the eight groups of the warp advance in LOCKSTEP, one expansion attempt per iteration (cheap
+// bookkeeping steps -- returning to a parent cell, neighbours that already hold a tag -- are
+// skipped inside the iteration), so the warp issues each instruction of the expensive part once
+// for all eight boards.  A group that finishes its board takes the next quad of the list
+// (cursor F.ctl[kCtlNext], shared by the warps of the block), so long and short boards overlap.
+constexpr int kCtlNext = 6, kCtlListN = 7, kCtlDone = 2;  // slots of F.ctl
+__device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
+  const unsigned full = 0xffffffffu;
+  const int grp = F.lane >> 2, jl = F.lane & 3, gshift = grp * 4;
+  const unsigned gmask = 0xfu << gshift;
+  uint8_t* gs = F.fx_gstate + grp * kGroupBytes;
+  uint8_t* cell = gs + kGOffCell;
+  int16_t* quads = (int16_t*)(gs + kGOffQuads);
+  uint16_t* stack = (uint16_t*)(gs + kGOffStack);
+  uint32_t* active = (uint32_t*)(gs + kGOffActive);
+  const int c_origin = 8 * kGWin + 8;
+  bool alive = false, list_empty = false;
+  int k = 0, n_quads = 0, depth = 0, cur_ci = 0, cur_i = 0;
+  for (;;) {
+    // (0) idle groups take the next quads of the list
+    const unsigned idle = __ballot_sync(full, !alive) & 0x11111111u;
+    if (idle != 0u && !list_empty) {
+      const int cnt = __popc(idle);
+      int base = 0;
+      if (F.lane == 0) base = atomicAdd(&F.ctl[kCtlNext], cnt);
+      base = __shfl_sync(full, base, 0);
+      if (base + cnt >= nq) list_empty = true;
+      const int kk = base + __popc(idle & ((1u << gshift) - 1u));
+      if (!alive && kk < nq) {
+        k = kk;
+        alive = true;
+        uint32_t* c32 = (uint32_t*)cell;  // window empty, every saddle active
+#pragma unroll
+        for (int t = 0; t < 16; ++t) c32[jl + 4 * t] = 0u;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) active[jl + 4 * t] = 0xffffffffu;
+        __syncwarp(gmask);
+        if (jl == 0) {
+          const int16_t* quad = F.fx_qlist + 4 * k;
+          for (int j = 1; j < 4; ++j) {  // quad[0] stays active (board.rs:35-37)
+            const int sdl = quad[j];
+            active[sdl >> 5] &= ~(1u << (sdl & 31));
+          }
+          for (int j = 0; j < 4; ++j) quads[j] = quad[j];
+          cell[c_origin] = 1;
+        }
+        n_quads = 1;
+        depth = 1;
+        cur_ci = c_origin;
+        cur_i = 0;
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(full, alive)) break;
+    // (1) every running board advances to its next expansion attempt (or finishes)
+    bool need = false;
+    int dir = 0, nci = 0, result = -1;
+    if (alive) {
+      for (;;) {
+        if (cur_i == 4) {  // all four directions of this cell done: return to the parent
+          if (--depth == 0) { result = n_quads; break; }
+          const unsigned e = stack[depth - 1];
+          cur_ci = (int)(e & 0xffu);
+          cur_i = (int)(e >> 8);
+          continue;
+        }
+        dir = cur_i++;
+        const int bx = (cur_ci >> 4) - 8, by = (cur_ci & 15) - 8;
+        int nx = bx, ny = by;
+        if (dir == 0) nx = bx + 1;
+        else if (dir == 1) ny = by - 1;
+        else if (dir == 2) nx = bx - 1;
+        else ny = by + 1;
+        if (nx < -8 || nx > 7 || ny < -8 || ny > 7) { result = kScoreRedo; break; }
+        nci = (nx + 8) * kGWin + (ny + 8);
+        const int cur = cell[nci];
+        if (cur != 0 && cur != 0xff) continue;  // already Some (board.rs:131-135)
+        if (n_quads >= F.max_quads) {           // no room: the attempt fails, the cell becomes None
+          if (jl == 0) cell[nci] = 0xff;
+          __syncwarp(gmask);
+          continue;
+        }
+        if (n_quads >= kGQuads) { result = kScoreRedo; break; }
+        need = true;
+        break;
+      }
+      if (result >= 0) {
+        if (jl == 0) F.fx_qscore[k] = (uint16_t)result;
+        alive = false;
+      }
+    }
+    __syncwarp();
+    {
+      const unsigned nb = __ballot_sync(full, need);
+      if (nb == 0u) continue;
+      if (F.tm && F.warp == 0 && F.lane == 0) {
+        F.tm[13] += 1;
+        F.tm[14] += __popc(nb) >> 2;
+      }
+    }
+    // (2) the four neighbour searches of try_expand_one, one per lane
+    unsigned mine = 0;
+    if (need) {
+      const int qi = cell[cur_ci] - 1;
+      const int2 qv = *(const int2*)(quads + 4 * qi);  // 4 x i16
+      const int qq0 = (int)(int16_t)(qv.x & 0xffff), qq1 = qv.x >> 16;
+      const int qq2 = (int)(int16_t)(qv.y & 0xffff), qq3 = qv.y >> 16;
+      // rotate_left(dir): qs[j] = quad[(j + dir) & 3]; lanes 0, 1 use the edge qs[0] -> qs[1],
+      // lanes 2, 3 the edge qs[3] -> qs[2]
+      const int ia = (jl < 2 ? dir : dir + 3) & 3, ib = (jl < 2 ? dir + 1 : dir + 2) & 3;
+      const int a = ia == 0 ? qq0 : (ia == 1 ? qq1 : (ia == 2 ? qq2 : qq3));
+      const int b = ib == 0 ? qq0 : (ib == 1 ? qq1 : (ib == 2 ? qq2 : qq3));
+      const int self = (jl == 1 || jl == 2) ? b : a;
+      mine = group_query(F, active, a, b, self);
+    }
+    __syncwarp();
+    const unsigned p0 = __shfl_sync(full, mine, 0, 4), p1 = __shfl_sync(full, mine, 1, 4);
+    const unsigned p2 = __shfl_sync(full, mine, 2, 4), p3 = __shfl_sync(full, mine, 3, 4);
+    const int n0 = packed_count(p0), n1 = packed_count(p1), n2 = packed_count(p2), n3 = packed_count(p3);
+    const int total = need ? n0 * n1 * n2 * n3 : 0;
+    // (3) candidate 4-tuples in the reference's nested-loop order (i0 outermost), four at a time
+    bool ok = false;
+    int nq0 = 0, nq1 = 0, nq2 = 0, nq3 = 0;
+    for (int base = 0; __any_sync(full, !ok && base < total); base += 4) {
+      if (F.tm && F.warp == 0 && F.lane == 0) F.tm[15] += 1;
+      const int t = base + jl;
+      bool valid = false;
+      if (!ok && t < total) {
+        int r = t;
+        const int i3 = r % n3; r /= n3;
+        const int i2 = r % n2; r /= n2;
+        const int i1 = r % n1; r /= n1;
+        valid = is_valid_quad(F, packed_cand(p0, r), packed_cand(p1, i1), packed_cand(p2, i2),
+                              packed_cand(p3, i3));
+      }
+      const unsigned m = (__ballot_sync(full, valid) >> gshift) & 0xfu;
+      if (!ok && m) {
+        int r = base + __ffs((int)m) - 1;
+        const int i3 = r % n3; r /= n3;
+        const int i2 = r % n2; r /= n2;
+        const int i1 = r % n1; r /= n1;
+        nq0 = packed_cand(p0, r); nq1 = packed_cand(p1, i1);
+        nq2 = packed_cand(p2, i2); nq3 = packed_cand(p3, i3);
+        ok = true;
+      }
+    }
+    // (4) update the board
+    if (need) {
+      if (ok) {
+        if (jl == 0) {
+          // rotate_right(dir): v[(j + dir) & 3] = nq[j]
+          int v[4];
+          v[dir & 3] = nq0; v[(dir + 1) & 3] = nq1; v[(dir + 2) & 3] = nq2; v[(dir + 3) & 3] = nq3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            active[v[j] >> 5] &= ~(1u << (v[j] & 31));
+            quads[n_quads * 4 + j] = (int16_t)v[j];
+          }
+          cell[nci] = (uint8_t)(n_quads + 1);
+          stack[depth - 1] = (uint16_t)(cur_ci | (cur_i << 8));
+        }
+        ++n_quads;
+        ++depth;
+        cur_ci = nci;
+        cur_i = 0;
+      } else if (jl == 0) {
+        cell[nci] = 0xff;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- init_quads, enumerated by one warp ----------------------------------------------------------
+struct SeedEnum {
+  int s0, n_same, n_diff;
+  unsigned diag_ok[2];  // bit a: quad_diag_ok(s0, same[a])
+  int a;                // `same` entry being expanded (-1 before the first)
+  int m, n_pairs, pbase;
+  int q_head, q_n;      // ring of cheap-gate survivors
+  bool exhausted;
+};
+
+// (p, q), p < q, of the c-th pair of m items in lexicographic order
+__device__ __forceinline__ void unrank_pair_fast(int c, int m, int* p, int* q) {
+  const float tm = (float)(2 * m - 1);
+  int a = (int)((tm - sqrtf(tm * tm - 8.0f * (float)c)) * 0.5f);
+  a = a < 0 ? 0 : (a > m - 2 ? m - 2 : a);
+  while (a > 0 && a * (2 * m - a - 1) / 2 > c) --a;
+  while ((a + 1) * (2 * m - a - 2) / 2 <= c) ++a;
+  *p = a;
+  *q = a + 1 + (c - a * (2 * m - a - 1) / 2);
+}
+
+// 50-NN of the seed, same / diff classification (detector.rs:550-563), per-diff vectors.
+__device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
+  E.s0 = s0;
+  const int n_nn = nearest_k(F, F.sx[s0], F.sy[s0], 50);
+  const float t0 = F.st[s0], x0 = F.sx[s0], y0 = F.sy[s0];
+  int n_same = 0, n_diff = 0;
+  for (int base = 1; base < n_nn; base += 32) {  // nearest[1..]: the first hit is the seed itself
+    const int j = base + F.lane;
+    int si = 0;
+    bool is_same = false, is_diff = false;
+    if (j < n_nn) {
+      si = F.nn_idx[j];
+      const float td = theta_distance_degree(t0, F.st[si]);
+      is_same = td < 5.0f;
+      is_diff = !is_same && td > 80.0f;
+    }
+    const unsigned ms = __ballot_sync(0xffffffffu, is_same), md = __ballot_sync(0xffffffffu, is_diff);
+    const unsigned lt = (1u << F.lane) - 1u;
+    if (is_same) F.same[n_same + __popc(ms & lt)] = (int16_t)si;
+    if (is_diff) {
+      const int d = n_diff + __popc(md & lt);
+      F.diff[d] = (int16_t)si;
+      F.fx_dvx[d] = fsub(F.sx[si], x0);
+      F.fx_dvy[d] = fsub(F.sy[si], y0);
+      F.fx_dth[d] = F.st[si];
+    }
+    n_same += __popc(ms);
+    n_diff += __popc(md);
+  }
+  __syncwarp();
+  E.n_same = n_same;
+  E.n_diff = n_diff;
+  E.diag_ok[0] = E.diag_ok[1] = 0u;
+  for (int blk = 0; blk * 32 < n_same; ++blk) {  // n_same <= 49
+    const int a = blk * 32 + F.lane;
+    const bool ok = a < n_same && quad_diag_ok(F, s0, F.same[a]);
+    E.diag_ok[blk & 1] = __ballot_sync(0xffffffffu, ok);
+  }
+  E.a = -1;
+  E.m = E.n_pairs = E.pbase = 0;
+  E.q_head = E.q_n = 0;
+  E.exhausted = n_diff < 2;
+}
+
+// Appends valid quads to F.fx_qlist (from *list_n on) until the seed is exhausted (returns true)
+// or the list may not hold another batch (returns false; call again after draining the list).
+__device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) {
+  const unsigned lt = (1u << F.lane) - 1u;
+  const float x0 = F.sx[E.s0], y0 = F.sy[E.s0];
+  for (;;) {
+    if (E.q_n >= 32 || (E.exhausted && E.q_n > 0)) {
+      // expensive gates for up to 32 survivors, in order
+      if (*list_n + 32 > kQListCap) return false;
+      const int take = E.q_n < 32 ? E.q_n : 32;
+      bool valid = false;
+      int s1 = 0, d0 = 0, d1 = 0;
+      if (F.lane < take) {
+        const unsigned e = F.fx_squeue[(E.q_head + F.lane) & 63];
+        s1 = F.same[e & 0xffu];
+        d0 = F.diff[(e >> 8) & 0xffu];
+        d1 = F.diff[(e >> 16) & 0xffu];
+        valid = quad_rest_ok(F, E.s0, d0, s1, d1);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        // winding (detector.rs:571-583)
+        const float c0 = cross2(fsub(F.sx[d0], x0), fsub(F.sy[d0], y0), fsub(F.sx[s1], x0), fsub(F.sy[s1], y0));
+        int16_t* q = F.fx_qlist + 4 * (*list_n + __popc(m & lt));
+        q[0] = (int16_t)E.s0;
+        q[2] = (int16_t)s1;
+        if (c0 > 0.0f) { q[1] = (int16_t)d0; q[3] = (int16_t)d1; }
+        else { q[1] = (int16_t)d1; q[3] = (int16_t)d0; }
+      }
+      *list_n += __popc(m);
+      E.q_head = (E.q_head + take) & 63;
+      E.q_n -= take;
+      __syncwarp();
+      continue;
+    }
+    if (E.exhausted) return true;
+    if (E.pbase >= E.n_pairs) {
+      // next `same` entry that passes the (s0, s1)-only gate
+      int a = E.a + 1;
+      while (a < E.n_same && !((E.diag_ok[a >> 5] >> (a & 31)) & 1u)) ++a;
+      E.a = a;
+      if (a >= E.n_same) {
+        E.exhausted = true;
+        continue;
+      }
+      const int s1 = F.same[a];
+      const float v02x = fsub(F.sx[s1], x0), v02y = fsub(F.sy[s1], y0);
+      // per diff entry: side of the diagonal (cross) and the dot gate (saddle.rs:40-45, :55-59)
+      int m = 0;
+      __syncwarp();
+      for (int base = 0; base < E.n_diff; base += 32) {
+        const int d = base + F.lane;
+        bool el = false;
+        if (d < E.n_diff) {
+          const float vx = F.fx_dvx[d], vy = F.fx_dvy[d];
+          F.fx_dc[d] = cross2(vx, vy, v02x, v02y);
+          el = !(dot2(vx, vy, v02x, v02y) < 0.0f);
+        }
+        const unsigned me = __ballot_sync(0xffffffffu, el);
+        if (el) F.fx_elig[m + __popc(me & lt)] = (uint8_t)d;
+        m += __popc(me);
+      }
+      __syncwarp();
+      E.m = m;
+      E.n_pairs = m * (m - 1) / 2;
+      E.pbase = 0;
+      continue;
+    }
+    // cheap gates on the next 32 pairs (lexicographic over the eligible diff entries)
+    {
+      const int c = E.pbase + F.lane;
+      bool pass = false;
+      unsigned entry = 0;
+      if (c < E.n_pairs) {
+        int p, q;
+        unrank_pair_fast(c, E.m, &p, &q);
+        const int i = F.fx_elig[p], j = F.fx_elig[q];
+        // saddle.rs:21-24 (theta of d0 vs d1) and :40-45: c0 * c1 < 0 with c0 = cross(v01, v02) =
+        // dc[i] and c1 = cross(v02, v03) = -dc[j] exactly (the products commute, x - y = -(y - x))
+        pass = !(theta_distance_degree(F.fx_dth[i], F.fx_dth[j]) > 5.0f) &&
+               !(fmul(F.fx_dc[i], -F.fx_dc[j]) < 0.0f);
+        entry = (unsigned)E.a | ((unsigned)i << 8) | ((unsigned)j << 16);
+      }
+      const unsigned mp = __ballot_sync(0xffffffffu, pass);
+      if (pass) F.fx_squeue[(E.q_head + E.q_n + __popc(mp & lt)) & 63] = entry;
+      E.q_n += __popc(mp);
+      E.pbase += 32;
+      __syncwarp();
+    }
+  }
+}
+
+// Clear this warp's general board state (its lattice region doubles as the group states).
+__device__ __forceinline__ void general_state_init(Frame& F) {
+  uint32_t* c = (uint32_t*)F.bs.cell;
+  const int words = F.lat * F.lat / 2;
+  for (int i = F.lane; i < words; i += 32) c[i] = 0u;
+  for (int i = F.lane; i < (F.active_words); i += 32) F.bs.active[i] = 0xffffffffu;
+  F.bs.n_quads = F.bs.n_touched = F.bs.score = 0;
+  __syncwarp();
+}
+
+// try_find_best_board (detector.rs:588-639).  Every warp of the block calls it.  Returns 1 with
+// the best board (after try_fix_missing) live in warp 0's F.bs, or -1 for None.
+// timing taps (warp 0, lane 0 of the frame's block; F.tm may be null)
+#define AGB_TM_ADD(slot, v) do { if (F.tm && F.warp == 0 && F.lane == 0) F.tm[slot] += (uint32_t)(v); } while (0)
+
+constexpr int kWaveMax = 16;  // seeds whose quads may be scored side by side
+
+// try_find_best_board (detector.rs:588-639).  Every warp of the block calls it.  Returns 1 with
+// the best board (after try_fix_missing) live in warp 0's F.bs, or -1 for None.
+//
+// Seeds are taken in the reference's pop order, in WAVES (1, 4, 8, 16, 16 ... seeds): warp 0
+// enumerates the quads of the wave's seeds into the list, all warps score list batches, warp 0
+// keeps each seed's first-maximum quad.  After the wave its seeds are merged in order with the
+// reference's `score > best_score`, `>= 36` early exit and 30-seed limit; seeds of the wave
+// that lie past the early exit were scored in vain and are ignored, so the outcome equals the
+// sequential loop.
+__device__ __noinline__ int find_best_board_fast(Frame& F) {
+  if (F.n == 0) return -1;
+  long long t0 = clock64();
+  if (F.warp == 0) {
+    grid_build_warp(F);
+    select_seeds(F);
+  }
+  __syncthreads();
+  AGB_TM_ADD(1, clock64() - t0);
+  int seeds_left = F.ctl[0];
+  F.g_on = F.ctl[5];
+  if (F.g_on) F.g_start = F.g_base + 1;
+  int best_score = 0, count = 0, wave = 1;
+  int best_quad[4] = {0, 0, 0, 0};  // meaningful in warp 0
+  SeedEnum E;
+  while (seeds_left > 0 && count < 30 && best_score < 36) {
+    int nw = wave < seeds_left ? wave : seeds_left;
+    nw = nw < 30 - count ? nw : 30 - count;
+    // ---- enumerate + score the wave's seeds; slot t holds seed F.seeds[seeds_left - 1 - t]
+    if (F.warp == 0 && F.lane < nw) F.fx_wscore[F.lane] = 0;
+    int t_cur = 0;        // warp 0: slot being enumerated
+    bool begun = false;   // warp 0: seed_enum_begin done for t_cur
+    bool wave_done = false;
+    while (!wave_done) {
+      t0 = clock64();
+      if (F.warp == 0) {
+        int list_n = 0;
+        if (F.lane < nw) F.fx_wlo[F.lane] = F.fx_whi[F.lane] = 0;
+        __syncwarp();
+        for (;;) {
+          if (!begun) {
+            if (t_cur == nw) break;
+            const long long tb = clock64();
+            seed_enum_begin(F, E, F.seeds[seeds_left - 1 - t_cur]);
+            AGB_TM_ADD(2, clock64() - tb);
+            AGB_TM_ADD(8, 1);
+            begun = true;
+            if (F.lane == 0) F.fx_wlo[t_cur] = F.fx_whi[t_cur] = (uint8_t)list_n;
+          }
+          const bool seed_done = seed_enum_fill(F, E, &list_n);
+          if (F.lane == 0) F.fx_whi[t_cur] = (uint8_t)list_n;
+          if (!seed_done) break;  // list full: score it, then continue with this seed
+          ++t_cur;
+          begun = false;
+        }
+        if (F.lane == 0) {
+          F.ctl[kCtlListN] = list_n;
+          F.ctl[kCtlDone] = (t_cur == nw) ? 1 : 0;
+          F.ctl[kCtlNext] = 0;
+        }
+      }
+      __syncthreads();
+      const int nq = F.ctl[kCtlListN];
+      wave_done = F.ctl[kCtlDone] != 0;
+      AGB_TM_ADD(3, clock64() - t0);
+      AGB_TM_ADD(9, nq);
+      t0 = clock64();
+      // score the listed quads: eight boards per warp, four lanes each
+      warp_score_quads(F, nq);
+      __syncthreads();
+      AGB_TM_ADD(4, clock64() - t0);
+      t0 = clock64();
+      bool redo = false;
+      for (int k = F.warp + F.n_warps * F.lane; k < nq; k += F.n_warps * 32)
+        redo |= F.fx_qscore[k] == kScoreRedo;
+      if (__any_sync(0xffffffffu, redo)) {
+        // boards too large for a group: the general warp-wide build gives the same score
+        general_state_init(F);
+        for (int k = F.warp; k < nq; k += F.n_warps) {
+          if (F.fx_qscore[k] != kScoreRedo) continue;  // warp-uniform
+          int quad[4];
+          for (int j = 0; j < 4; ++j) quad[j] = F.fx_qlist[4 * k + j];
+          board_build(F, F.bs, quad);
+          const int sc = F.bs.score < kScoreRedo ? F.bs.score : kScoreRedo - 1;
+          __syncwarp();
+          if (F.lane == 0) F.fx_qscore[k] = (uint16_t)sc;
+          __syncwarp();
+        }
+        board_reset(F, F.bs);
+        AGB_TM_ADD(10, 1);
+      }
+      __syncthreads();
+      AGB_TM_ADD(5, clock64() - t0);
+      // per seed: first maximum of its quads in this batch (list order); `>` keeps the earliest
+      // across batches.  Lane t looks after slot t.
+      if (F.warp == 0 && F.lane < nw) {
+        const int lo = F.fx_wlo[F.lane], hi = F.fx_whi[F.lane];
+        int bs = F.fx_wscore[F.lane], bk = -1;
+        for (int k = lo; k < hi; ++k) {
+          const int sc = F.fx_qscore[k];
+          if (sc > bs) { bs = sc; bk = k; }
+        }
+        if (bk >= 0) {
+          F.fx_wscore[F.lane] = (uint16_t)bs;
+          for (int j = 0; j < 4; ++j) F.fx_wquad[4 * F.lane + j] = F.fx_qlist[4 * bk + j];
+        }
+      }
+      __syncthreads();  // the list is rewritten by the next batch
+    }
+    // ---- merge the wave in seed order
+    for (int t = 0; t < nw; ++t) {
+      const int sc = F.fx_wscore[t];
+      if (sc > best_score) {  // best_board_option = Some(board)
+        best_score = sc;
+        for (int j = 0; j < 4; ++j) best_quad[j] = F.fx_wquad[4 * t + j];
+      }
+      if (best_score >= 36) break;
+      ++count;
+    }
+    seeds_left -= nw;
+    wave = wave == 1 ? 4 : (wave < kWaveMax ? wave * 2 : kWaveMax);
+    __syncthreads();  // fx_wscore / fx_wquad are reused by the next wave
+  }
+  if (best_score == 0) return -1;
+  t0 = clock64();
+  if (F.warp == 0) {
+    general_state_init(F);
+    board_build(F, F.bs, best_quad);
+    board_fix_missing(F, F.bs);
+  }
+  AGB_TM_ADD(6, clock64() - t0);
+  return 1;
+}
+
+}  // namespace agb
+#endif  // AGB_DEVICE

@@ -20,6 +20,7 @@ struct BoardWsLayout {
   // shared memory per block (= per frame in flight): frame-wide part, then per-warp parts
   int smem_saddles, grid_cap_cells;
   size_t sm_pos, sm_gstart, sm_gitem, sm_hist, sm_ctl, sm_warp0;
+  size_t sm_qlist, sm_qscore, sm_fvec, sm_elig, sm_squeue, sm_wave;
   size_t smw_cell, smw_active, smw_small, smem_per_warp, smem_per_block;
 };
 BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps);
@@ -53,8 +54,8 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
                          const ag_saddle* refined, const int* n_refined, uint8_t* ws,
                          const BoardWsLayout& L, int n_codes, int edge, int border, int hamming,
                          int max_boards, ag_tag* out, int cap, int* n_out, uint32_t* frame_status,
-                         int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid,
-                         cudaStream_t s);
+                         int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid, int fast,
+                         uint32_t* timing, cudaStream_t s);
 
 // ag_render.cu
 int launch_render_boards(uint8_t* frames, int n_frames, int w, int h, int cols, int rows,

@@ -139,6 +139,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="override pipeline chunk_frames")
     ap.add_argument("--lattice", type=int, default=0, help="override board_lattice (16/32/64)")
     ap.add_argument("--board-warps", type=int, default=-1, help="override board_warps (0 auto, 1/2/4/8)")
+    ap.add_argument("--sync-calls", action="store_true",
+                    help="order every step's results on the stream before the next step starts "
+                         "(default: steps stream through the pipeline, one wait at the end)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -184,16 +187,28 @@ def main():
 
     frames = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
     det.render_boards_device(frames.data_ptr(), B, W, H, 6, 6, 1000 + 7919 * rank, stream=sp)
-    d_tags = torch.zeros((B, cap * 9), dtype=torch.int32, device="cuda")
-    d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
-    d_status = torch.zeros(B, dtype=torch.int32, device="cuda")
+    # two sets of result buffers: with streaming calls, step k+1 starts while step k's board
+    # search is still running, so consecutive steps must not share output buffers
+    d_tags = [torch.zeros((B, cap * 9), dtype=torch.int32, device="cuda") for _ in range(2)]
+    d_cnt = [torch.zeros(B, dtype=torch.int32, device="cuda") for _ in range(2)]
+    d_status = [torch.zeros(B, dtype=torch.int32, device="cuda") for _ in range(2)]
+    streaming = args.workload == "detect" and not args.sync_calls
+    if streaming:
+        det.set_option("device_async", 1)
+    step_no = [0]
 
     def step_device():
         if args.workload == "detect":
-            det.detect_batch_device(frames.data_ptr(), B, W, H, pkg.FMT_L8, d_tags.data_ptr(), cap,
-                                    d_cnt.data_ptr(), d_status.data_ptr(), stream=sp)
+            k = step_no[0] & 1
+            step_no[0] += 1
+            det.detect_batch_device(frames.data_ptr(), B, W, H, pkg.FMT_L8, d_tags[k].data_ptr(), cap,
+                                    d_cnt[k].data_ptr(), d_status[k].data_ptr(), stream=sp)
         else:
             det.dense_batch_device(frames.data_ptr(), B, W, H, pkg.FMT_L8, stream=sp)
+
+    def drain():
+        if streaming:
+            det.detect_batch_device_wait(stream=sp)
 
     def barrier():
         torch.cuda.synchronize()
@@ -204,6 +219,7 @@ def main():
     # ---- device-resident throughput ("value") ---------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step_device()
+    drain()
     barrier()
     det.stage_times(reset=True)
     det.set_option("profile", 1)
@@ -217,6 +233,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
+    drain()  # every step's results are complete before the closing event
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -227,7 +244,11 @@ def main():
     from aprilgrid_rs_b200 import shard
     ms_max = shard.max_over_ranks(ms, device="cuda")
     value = world * B * args.steps / (ms_max * 1e-3)
-    cnt_host = d_cnt.cpu().numpy() if args.workload == "detect" else None
+    cnt_host = d_cnt[0].cpu().numpy() if args.workload == "detect" else None
+    if cnt_host is not None:
+        assert np.array_equal(cnt_host, d_cnt[1].cpu().numpy()), "steps disagree on the same frames"
+    if streaming:
+        det.set_option("device_async", 0)
 
     # ---- end to end through the host-buffer C-ABI call ("e2e") -------------------------------
     e2e = None
@@ -298,7 +319,9 @@ def main():
                        else ("dense_blur_hessian_threshold_1280x1024_batch%d" % B),
                        "frames_per_gpu_per_step": B, "image": [W, H], "format": "L8",
                        "parallelism": "frames sharded image-wise, %d rank(s), no collective on the data path" % world,
-                       "l2": "inputs (%.2f GB per step) larger than L2" % (B * W * H / 1e9)},
+                       "l2": "inputs (%.2f GB per step) larger than L2" % (B * W * H / 1e9),
+                       "calls": "streaming (ag_detect_batch_device with device_async, one wait after the "
+                                "last step)" if streaming else "one synchronising call per step"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu,
             "stage_share": {k: v[0] / total_stage for k, v in stage.items()},

@@ -106,8 +106,10 @@ AG_API void ag_destroy(ag_detector* det);
 AG_API const char* ag_last_error(const ag_detector* det);
 
 /* Tunables.  key: "chunk_frames" (frames per pipeline chunk), "max_clusters",
- * "max_saddles" (per-frame capacities), "profile" (0/1, see ag_stage_times).  Must be set before the first detect call that
- * needs them larger. */
+ * "max_saddles" (per-frame capacities), "profile" (0/1, see ag_stage_times), "device_async"
+ * (see ag_detect_batch_device_wait), "board_warps" (warps per frame in the board search:
+ * 0 = automatic, 1/2/4/8), "board_fast" (0 = general board path only), "board_lattice".
+ * Capacities must be set before the first detect call that needs them larger. */
 AG_API int ag_set_option(ag_detector* det, const char* key, long value);
 
 /* TagDetector::detect on one host image.  `out` receives up to `cap` tags in ascending id
@@ -130,6 +132,14 @@ AG_API int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t
                                   int n_frames, int width, int height, size_t row_stride,
                                   int format, ag_tag* d_out, int cap_per_frame,
                                   int* d_n_per_frame, uint32_t* d_frame_status, void* stream);
+
+/* Streaming use of ag_detect_batch_device.  By default every call orders its results on
+ * `stream` before returning control to the stream, so back-to-back calls drain the internal
+ * pipeline at each call boundary.  After ag_set_option(det, "device_async", 1) a call only
+ * enqueues its work; ag_detect_batch_device_wait(det, stream) then makes `stream` (NULL = the
+ * host thread) wait for every call issued so far.  Output buffers of calls that are still in
+ * flight must not be reused.  (detect_batch over an unbounded frame sequence.)            */
+AG_API int ag_detect_batch_device_wait(ag_detector* det, void* stream);
 
 /* TagDetector::refined_saddle_points: refined saddles of one host image, reference order. */
 AG_API int ag_refined_saddle_points(ag_detector* det, const void* pixels, int width, int height,

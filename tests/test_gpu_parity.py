@@ -218,3 +218,48 @@ def test_other_families(pkg, oracle):
         want = oracle.detect(img, family=name)
         assert_tags_match(got, want)
         assert len(want) >= 15, (name, len(want))
+
+
+# ---- board search variants: the four-lane group scoring path vs the general warp-wide path ----
+BOARD_VARIANTS = [dict(board_fast=1, board_warps=1), dict(board_fast=1, board_warps=4),
+                  dict(board_fast=1, board_warps=8), dict(board_fast=0, board_warps=1),
+                  dict(board_fast=0, board_warps=4)]
+
+
+@pytest.mark.parametrize("variant", BOARD_VARIANTS, ids=lambda v: "fast%d_w%d" % (v["board_fast"], v["board_warps"]))
+def test_board_search_variants_agree_with_oracle(pkg, oracle, images, variant):
+    """Every mapping of the board search onto warps gives the oracle's quads, ids and corners."""
+    det = pkg.TagDetector(pkg.TagFamily.T36H11)
+    try:
+        for k, v in variant.items():
+            det.set_option(k, v)
+        for name in ("EuRoC", "TUM_VI", "r45", "two_boards"):
+            img = images[name]
+            g = det.stages(img)
+            o = oracle.front_end(img, want_labels=False)
+            oq = oracle.try_find_best_board(o["refined"])
+            assert oq is not None and np.array_equal(g["quads"], oq), name
+            assert_tags_match(g["tags"], oracle.detect(img))
+        frames = synth.fixture_like_frames(6, 640, 480, seed=40, tag_px=41.0)
+        frames[2] = 0
+        for gt, wt in zip(det.detect_batch(frames), oracle.detect_batch(frames)):
+            assert_tags_match(gt, wt)
+    finally:
+        det.close()
+
+
+def test_group_board_overflow_falls_back_to_general_build(pkg, oracle):
+    """A board wider than the 16 x 16 group window is re-scored by the general path: a 14 x 2
+    strip (28 tags, ~216 saddles, so the frame does take the throughput path)."""
+    img = synth.render_board_numpy(1280, 1024, cols=14, rows=2, seed=4, tag_px=60.0)
+    fe = oracle.front_end(img, want_labels=False)
+    want = oracle.detect(img)
+    assert len(want) == 28 and len(fe["refined"]) <= 512
+    for fast, warps in ((1, 1), (1, 4), (0, 4)):
+        det = pkg.TagDetector(pkg.TagFamily.T36H11)
+        try:
+            det.set_option("board_fast", fast)
+            det.set_option("board_warps", warps)
+            assert_tags_match(det.detect(img), want)
+        finally:
+            det.close()

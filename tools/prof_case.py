@@ -19,6 +19,9 @@ det = pkg.TagDetector(pkg.TagFamily.T36H11)
 det.set_option("chunk_frames", chunk)
 if os.environ.get("AG_BOARD_GRID") is not None:
     det.set_option("board_grid", int(os.environ["AG_BOARD_GRID"]))
+for key in ("board_warps", "board_fast", "board_lattice"):
+    if os.environ.get("AG_" + key.upper()) is not None:
+        det.set_option(key, int(os.environ["AG_" + key.upper()]))
 s = torch.cuda.Stream()
 torch.cuda.set_stream(s)
 frames = torch.empty((n, H, W), dtype=torch.uint8, device="cuda")
