@@ -75,13 +75,8 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps) {
   L.sm_gitem = stake(sizeof(uint16_t) * L.smem_saddles);
   L.sm_hist = stake(sizeof(int) * agb::kHistBins);
   L.sm_ctl = stake(sizeof(int) * 16);
-  // throughput path (ag_board_fast.cuh)
-  L.sm_qlist = stake(sizeof(int16_t) * 4 * agb::kQListCap);
-  L.sm_qscore = stake(sizeof(uint16_t) * agb::kQListCap);
-  L.sm_fvec = stake(sizeof(float) * 64 * 4);
-  L.sm_elig = stake(64);
-  L.sm_squeue = stake(sizeof(uint32_t) * 64);
-  L.sm_wave = stake(32 * (sizeof(uint16_t) + 4 * sizeof(int16_t) + 2));
+  // throughput path (ag_board_fast.cuh): per wave slot best score + quad
+  L.sm_wave = stake(32 * (sizeof(uint16_t) + 4 * sizeof(int16_t)));
   L.sm_warp0 = sm;
   size_t sw = 0;
   auto swtake = [&](size_t bytes) {
@@ -93,6 +88,12 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps) {
   L.smw_cell = swtake(std::max(sizeof(int16_t) * cells, (size_t)agb::kGroupsPerWarp * agb::kGroupBytes));
   L.smw_active = swtake(sizeof(uint32_t) * ((N + 31) / 32));
   L.smw_small = swtake(sizeof(int16_t) * 64 * 4);  // nn_idx, same, diff, samp
+  // throughput path: the warp's quad list and enumeration scratch
+  L.smw_qlist = swtake(sizeof(int16_t) * 4 * agb::kQListCap);
+  L.smw_qscore = swtake(sizeof(uint16_t) * agb::kQListCap);
+  L.smw_fvec = swtake(sizeof(float) * 64 * 4);
+  L.smw_elig = swtake(64);
+  L.smw_squeue = swtake(sizeof(uint32_t) * 64);
   L.smem_per_warp = sw;
   L.smem_per_block = L.sm_warp0 + sw * kBoardWarps;
   return L;
@@ -191,19 +192,17 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
     if (threadIdx.x < 16) F.tm[threadIdx.x] = 0u;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   }
-  F.fx_qlist = (int16_t*)(smem + L.sm_qlist);
-  F.fx_qscore = (uint16_t*)(smem + L.sm_qscore);
-  F.fx_dvx = (float*)(smem + L.sm_fvec);
+  F.fx_qlist = (int16_t*)(SW + L.smw_qlist);
+  F.fx_qscore = (uint16_t*)(SW + L.smw_qscore);
+  F.fx_dvx = (float*)(SW + L.smw_fvec);
   F.fx_dvy = F.fx_dvx + 64;
   F.fx_dth = F.fx_dvy + 64;
   F.fx_dc = F.fx_dth + 64;
-  F.fx_elig = smem + L.sm_elig;
-  F.fx_squeue = (uint32_t*)(smem + L.sm_squeue);
+  F.fx_elig = SW + L.smw_elig;
+  F.fx_squeue = (uint32_t*)(SW + L.smw_squeue);
   F.fx_gstate = SW + L.smw_cell;
   F.fx_wscore = (uint16_t*)(smem + L.sm_wave);
   F.fx_wquad = (int16_t*)(F.fx_wscore + 32);
-  F.fx_wlo = (uint8_t*)(F.fx_wquad + 128);
-  F.fx_whi = F.fx_wlo + 32;
   // block-uniform: the whole frame takes the throughput path or the general one
   F.fast_on = (fast && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles) ? 1 : 0;
 

@@ -128,7 +128,6 @@ struct Frame {
   uint8_t* fx_gstate;    // this warp's group states (aliases bs.cell)
   uint16_t* fx_wscore;   // [32] per wave slot: best score of the seed so far
   int16_t* fx_wquad;     // [32][4] ... and its quad
-  uint8_t *fx_wlo, *fx_whi;  // [32] the slot's range in the current list batch
   uint32_t* tm;          // optional per-frame timing / work counters ([16], may be null)
 };
 

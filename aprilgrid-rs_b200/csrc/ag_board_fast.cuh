@@ -31,7 +31,7 @@ constexpr int kGroupsPerWarp = 8;
 constexpr int kGroupBytes = 1024;
 constexpr int kGWin = 16;           // tag window per group: x, y in [-8, 7]
 constexpr int kGQuads = 64;         // quads per group board
-constexpr int kQListCap = 128;      // candidate quads buffered between enumeration and scoring
+constexpr int kQListCap = 64;       // candidate quads a warp buffers between enumeration and scoring
 constexpr int kScoreRedo = 0xffff;  // group board overflowed: score it with the general path
 // group state layout (bytes)
 constexpr int kGOffCell = 0;        // u8 [256]: 0 unvisited, 0xff None, q + 1 Some(q)
@@ -170,8 +170,8 @@ __device__ __forceinline__ int packed_cand(unsigned p, int k) { return (int)((p 
 // bookkeeping steps -- returning to a parent cell, neighbours that already hold a tag -- are
 // skipped inside the iteration), so the warp issues each instruction of the expensive part once
 // for all eight boards.  A group that finishes its board takes the next quad of the list
-// (cursor F.ctl[kCtlNext], shared by the warps of the block), so long and short boards overlap.
-constexpr int kCtlNext = 6, kCtlListN = 7, kCtlDone = 2;  // slots of F.ctl
+// of the warp's list, so long and short boards overlap.
+constexpr int kCtlNext = 6;  // slot of F.ctl: next wave slot (seed) to hand to a warp
 __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
   const unsigned full = 0xffffffffu;
   const int grp = F.lane >> 2, jl = F.lane & 3, gshift = grp * 4;
@@ -184,14 +184,14 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
   const int c_origin = 8 * kGWin + 8;
   bool alive = false, list_empty = false;
   int k = 0, n_quads = 0, depth = 0, cur_ci = 0, cur_i = 0;
+  int next = 0;  // list cursor (warp-uniform)
   for (;;) {
     // (0) idle groups take the next quads of the list
     const unsigned idle = __ballot_sync(full, !alive) & 0x11111111u;
     if (idle != 0u && !list_empty) {
       const int cnt = __popc(idle);
-      int base = 0;
-      if (F.lane == 0) base = atomicAdd(&F.ctl[kCtlNext], cnt);
-      base = __shfl_sync(full, base, 0);
+      const int base = next;
+      next += cnt;
       if (base + cnt >= nq) list_empty = true;
       const int kk = base + __popc(idle & ((1u << gshift) - 1u));
       if (!alive && kk < nq) {
@@ -512,16 +512,18 @@ __device__ __forceinline__ void general_state_init(Frame& F) {
 #define AGB_TM_ADD(slot, v) do { if (F.tm && F.warp == 0 && F.lane == 0) F.tm[slot] += (uint32_t)(v); } while (0)
 
 constexpr int kWaveMax = 16;  // seeds whose quads may be scored side by side
+constexpr int kMaxRanges = 8;  // seeds whose quads may share one list batch of a warp
 
 // try_find_best_board (detector.rs:588-639).  Every warp of the block calls it.  Returns 1 with
 // the best board (after try_fix_missing) live in warp 0's F.bs, or -1 for None.
 //
-// Seeds are taken in the reference's pop order, in WAVES (1, 4, 8, 16, 16 ... seeds): warp 0
-// enumerates the quads of the wave's seeds into the list, all warps score list batches, warp 0
-// keeps each seed's first-maximum quad.  After the wave its seeds are merged in order with the
-// reference's `score > best_score`, `>= 36` early exit and 30-seed limit; seeds of the wave
-// that lie past the early exit were scored in vain and are ignored, so the outcome equals the
-// sequential loop.
+// Seeds are taken in the reference's pop order, in WAVES (2, 4, 8, 16, 16 ... seeds; 1 first
+// for a single warp).  Inside a wave the warps work independently: a warp claims the next
+// seed (slot) of the wave, enumerates its quads into its own list, scores list batches with
+// its eight lane groups and keeps the seed's first-maximum quad in the slot.  After the wave
+// the slots are merged in seed order with the reference's `score > best_score`, `>= 36` early
+// exit and 30-seed limit; seeds of the wave that lie past the early exit were scored in vain
+// and are ignored, so the outcome equals the sequential loop.
 __device__ __noinline__ int find_best_board_fast(Frame& F) {
   if (F.n == 0) return -1;
   long long t0 = clock64();
@@ -534,93 +536,104 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
   int seeds_left = F.ctl[0];
   F.g_on = F.ctl[5];
   if (F.g_on) F.g_start = F.g_base + 1;
-  int best_score = 0, count = 0, wave = 1;
-  int best_quad[4] = {0, 0, 0, 0};  // meaningful in warp 0
+  int best_score = 0, count = 0, wave = F.n_warps > 1 ? 2 : 1;
+  int best_quad[4] = {0, 0, 0, 0};
   SeedEnum E;
   while (seeds_left > 0 && count < 30 && best_score < 36) {
     int nw = wave < seeds_left ? wave : seeds_left;
     nw = nw < 30 - count ? nw : 30 - count;
-    // ---- enumerate + score the wave's seeds; slot t holds seed F.seeds[seeds_left - 1 - t]
-    if (F.warp == 0 && F.lane < nw) F.fx_wscore[F.lane] = 0;
-    int t_cur = 0;        // warp 0: slot being enumerated
-    bool begun = false;   // warp 0: seed_enum_begin done for t_cur
-    bool wave_done = false;
-    while (!wave_done) {
-      t0 = clock64();
-      if (F.warp == 0) {
-        int list_n = 0;
-        if (F.lane < nw) F.fx_wlo[F.lane] = F.fx_whi[F.lane] = 0;
-        __syncwarp();
+    // slot t of the wave holds seed F.seeds[seeds_left - 1 - t]
+    if (F.warp == 0) {
+      if (F.lane < nw) F.fx_wscore[F.lane] = 0;
+      if (F.lane == 0) F.ctl[kCtlNext] = 0;
+    }
+    __syncthreads();
+    t0 = clock64();
+    {
+      int list_n = 0, n_rng = 0;
+      int rng_slot[kMaxRanges], rng_lo[kMaxRanges], rng_hi[kMaxRanges];
+      int t_cur = -1;
+      bool begun = false, no_more = false;
+      for (;;) {
+        // ---- fill the list with the quads of one or more seeds
         for (;;) {
           if (!begun) {
-            if (t_cur == nw) break;
-            const long long tb = clock64();
-            seed_enum_begin(F, E, F.seeds[seeds_left - 1 - t_cur]);
-            AGB_TM_ADD(2, clock64() - tb);
+            if (no_more || n_rng == kMaxRanges) break;
+            int t = 0;
+            if (F.lane == 0) t = atomicAdd(&F.ctl[kCtlNext], 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= nw) { no_more = true; break; }
+            t_cur = t;
+            seed_enum_begin(F, E, F.seeds[seeds_left - 1 - t]);
             AGB_TM_ADD(8, 1);
             begun = true;
-            if (F.lane == 0) F.fx_wlo[t_cur] = F.fx_whi[t_cur] = (uint8_t)list_n;
+            rng_slot[n_rng] = t;
+            rng_lo[n_rng] = rng_hi[n_rng] = list_n;
+            ++n_rng;
           }
           const bool seed_done = seed_enum_fill(F, E, &list_n);
-          if (F.lane == 0) F.fx_whi[t_cur] = (uint8_t)list_n;
+          rng_hi[n_rng - 1] = list_n;
           if (!seed_done) break;  // list full: score it, then continue with this seed
-          ++t_cur;
           begun = false;
         }
-        if (F.lane == 0) {
-          F.ctl[kCtlListN] = list_n;
-          F.ctl[kCtlDone] = (t_cur == nw) ? 1 : 0;
-          F.ctl[kCtlNext] = 0;
+        if (list_n == 0 && !begun) break;  // nothing left for this warp in this wave
+        AGB_TM_ADD(9, list_n);
+        // ---- score the listed quads: eight boards side by side, four lanes each
+        const long long ts = clock64();
+        warp_score_quads(F, list_n);
+        __syncwarp();
+        bool redo = false;
+        for (int k = F.lane; k < list_n; k += 32) redo |= F.fx_qscore[k] == kScoreRedo;
+        if (__any_sync(0xffffffffu, redo)) {
+          // boards too large for a group: the general warp-wide build gives the same score
+          general_state_init(F);
+          for (int k = 0; k < list_n; ++k) {
+            if (F.fx_qscore[k] != kScoreRedo) continue;  // warp-uniform
+            int quad[4];
+            for (int j = 0; j < 4; ++j) quad[j] = F.fx_qlist[4 * k + j];
+            board_build(F, F.bs, quad);
+            const int sc = F.bs.score < kScoreRedo ? F.bs.score : kScoreRedo - 1;
+            __syncwarp();
+            if (F.lane == 0) F.fx_qscore[k] = (uint16_t)sc;
+            __syncwarp();
+          }
+          board_reset(F, F.bs);
+          AGB_TM_ADD(10, 1);
         }
-      }
-      __syncthreads();
-      const int nq = F.ctl[kCtlListN];
-      wave_done = F.ctl[kCtlDone] != 0;
-      AGB_TM_ADD(3, clock64() - t0);
-      AGB_TM_ADD(9, nq);
-      t0 = clock64();
-      // score the listed quads: eight boards per warp, four lanes each
-      warp_score_quads(F, nq);
-      __syncthreads();
-      AGB_TM_ADD(4, clock64() - t0);
-      t0 = clock64();
-      bool redo = false;
-      for (int k = F.warp + F.n_warps * F.lane; k < nq; k += F.n_warps * 32)
-        redo |= F.fx_qscore[k] == kScoreRedo;
-      if (__any_sync(0xffffffffu, redo)) {
-        // boards too large for a group: the general warp-wide build gives the same score
-        general_state_init(F);
-        for (int k = F.warp; k < nq; k += F.n_warps) {
-          if (F.fx_qscore[k] != kScoreRedo) continue;  // warp-uniform
-          int quad[4];
-          for (int j = 0; j < 4; ++j) quad[j] = F.fx_qlist[4 * k + j];
-          board_build(F, F.bs, quad);
-          const int sc = F.bs.score < kScoreRedo ? F.bs.score : kScoreRedo - 1;
+        AGB_TM_ADD(4, clock64() - ts);
+        // ---- per seed: first maximum of its quads in this batch (list order); `>` keeps the
+        //      earliest across batches.  The slot belongs to this warp alone during the wave.
+        for (int r = 0; r < n_rng; ++r) {
+          int bs = -1, bk = kNone;
+          for (int k = rng_lo[r] + F.lane; k < rng_hi[r]; k += 32) {
+            const int sc = F.fx_qscore[k];
+            if (sc > bs) { bs = sc; bk = k; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o), ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (os > bs || (os == bs && ok < bk)) { bs = os; bk = ok; }
+          }
+          const int t = rng_slot[r];
+          if (bs > (int)F.fx_wscore[t]) {
+            __syncwarp();
+            if (F.lane == 0) F.fx_wscore[t] = (uint16_t)bs;
+            if (F.lane < 4) F.fx_wquad[4 * t + F.lane] = F.fx_qlist[4 * bk + F.lane];
+          }
           __syncwarp();
-          if (F.lane == 0) F.fx_qscore[k] = (uint16_t)sc;
-          __syncwarp();
         }
-        board_reset(F, F.bs);
-        AGB_TM_ADD(10, 1);
-      }
-      __syncthreads();
-      AGB_TM_ADD(5, clock64() - t0);
-      // per seed: first maximum of its quads in this batch (list order); `>` keeps the earliest
-      // across batches.  Lane t looks after slot t.
-      if (F.warp == 0 && F.lane < nw) {
-        const int lo = F.fx_wlo[F.lane], hi = F.fx_whi[F.lane];
-        int bs = F.fx_wscore[F.lane], bk = -1;
-        for (int k = lo; k < hi; ++k) {
-          const int sc = F.fx_qscore[k];
-          if (sc > bs) { bs = sc; bk = k; }
-        }
-        if (bk >= 0) {
-          F.fx_wscore[F.lane] = (uint16_t)bs;
-          for (int j = 0; j < 4; ++j) F.fx_wquad[4 * F.lane + j] = F.fx_qlist[4 * bk + j];
+        // ---- next batch; a seed that is not finished continues at the head of the list
+        list_n = 0;
+        n_rng = 0;
+        if (begun) {
+          rng_slot[0] = t_cur;
+          rng_lo[0] = rng_hi[0] = 0;
+          n_rng = 1;
         }
       }
-      __syncthreads();  // the list is rewritten by the next batch
     }
+    __syncthreads();
+    AGB_TM_ADD(3, clock64() - t0);
     // ---- merge the wave in seed order
     for (int t = 0; t < nw; ++t) {
       const int sc = F.fx_wscore[t];
@@ -632,7 +645,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
       ++count;
     }
     seeds_left -= nw;
-    wave = wave == 1 ? 4 : (wave < kWaveMax ? wave * 2 : kWaveMax);
+    wave = wave < 4 ? 4 : (wave < kWaveMax ? wave * 2 : kWaveMax);
     __syncthreads();  // fx_wscore / fx_wquad are reused by the next wave
   }
   if (best_score == 0) return -1;
