@@ -292,9 +292,45 @@ __global__ void k_fill_u32(uint32_t* p, int n, uint32_t v) {
 }
 
 // -----------------------------------------------------------------------------------------
-// K2: threshold.  One warp handles runs of 32 consecutive pixels of a row with one ballot
-// per word; each thread keeps several independent 4-byte loads in flight.
+// K2: threshold.  mask bit = resp < 0.05 * min (detector.rs:418, :176-177).
+//
+// Vector version (width % 32 == 0): a thread loads 4 consecutive responses with one 16-byte
+// streaming load, eight lanes cover one 32-pixel mask word, and the 4-bit nibbles are ORed
+// together with three shuffles, so a warp produces four mask words per load instruction.
+// Generic version: one pixel per lane, one ballot per word.
 // -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_threshold_mask_v4(const float* __restrict__ resp, FrameGeom g, const uint32_t* __restrict__ frame_min,
+                    uint32_t* __restrict__ mask) {
+  const int f = blockIdx.y;
+  const float thr = __fmul_rn(ordered_to_float(frame_min[f]), 0.05f);  // detector.rs:418
+  const float4* R = reinterpret_cast<const float4*>(resp + (size_t)f * g.n_px);
+  uint32_t* M = mask + (size_t)f * g.n_words;
+  const int lane = threadIdx.x & 31;
+  const int n_vec = g.n_px >> 2;  // rows are whole words, so the frame is a flat run of words
+  const int stride = gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (int v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < n_vec; v0 += stride * U) {
+    float4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * stride;
+      q[u] = v < n_vec ? __ldcs(R + v) : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * stride;
+      uint32_t b = (q[u].x < thr ? 1u : 0u) | (q[u].y < thr ? 2u : 0u) | (q[u].z < thr ? 4u : 0u) |
+                   (q[u].w < thr ? 8u : 0u);
+      b <<= 4 * (lane & 7);
+      b |= __shfl_xor_sync(0xffffffffu, b, 1);
+      b |= __shfl_xor_sync(0xffffffffu, b, 2);
+      b |= __shfl_xor_sync(0xffffffffu, b, 4);
+      if ((lane & 7) == 0 && v < n_vec) M[v >> 3] = b;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_threshold_mask(const float* __restrict__ resp, FrameGeom g, const uint32_t* __restrict__ frame_min,
                  uint32_t* __restrict__ mask) {
@@ -427,6 +463,15 @@ int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames,
 
 int launch_threshold(const float* resp, const FrameGeom& g, int n_frames, const uint32_t* frame_min,
                      uint32_t* mask, cudaStream_t s) {
+  if ((g.w & 31) == 0 && (((uintptr_t)resp) & 15) == 0) {
+    // whole-word rows: flat float4 version; 296 blocks per frame-row of the grid keep all SMs busy
+    const int n_vec = g.n_px >> 2;
+    int bx = (n_vec + 256 * 4 - 1) / (256 * 4);
+    if (bx > 64) bx = 64;
+    dim3 grid(bx, n_frames);
+    k_threshold_mask_v4<<<grid, 256, 0, s>>>(resp, g, frame_min, mask);
+    return 1;
+  }
   int blocks_x = (g.n_words + 8 * 4 - 1) / (8 * 4);  // 8 warps x 4 words per block iteration
   if (blocks_x > 4096) blocks_x = 4096;
   if (blocks_x < 1) blocks_x = 1;

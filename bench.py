@@ -53,6 +53,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.t_begin = self.t_end = None  # host clock window of the timed region
 
     def run(self):
         try:
@@ -63,7 +64,7 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
@@ -75,7 +76,9 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        inside = [r for t, r in self.rows
+                  if self.t_begin is None or (self.t_begin <= t <= (self.t_end or t) + 0.2)]
+        for r in (inside or [r for _, r in self.rows[-3:]]):
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -131,8 +134,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="detect", choices=["detect", "dense"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default 1024; dense 256)")
@@ -226,16 +229,20 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.5)  # nvidia-smi start-up; its samples are filtered to the timed window below
     launches0 = det.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.t_begin = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     drain()  # every step's results are complete before the closing event
     e1.record(stream)
     barrier()
+    if sampler:
+        sampler.t_end = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = det.launch_count - launches0
     clocks = sampler.finish() if sampler else None
