@@ -97,7 +97,8 @@ struct ag_detector {
   // warps per frame in the board kernel: 0 = automatic (1 when a launch has enough frames to
   // fill the GPU with one-warp blocks, 4 otherwise), or 1 / 2 / 4 / 8
   long board_warps = 0;
-  long board_batch_frames = 296;  // automatic mode: launches with at least this many frames use 1 warp
+  long board_batch_frames = 1 << 30;  // automatic mode: launches with at least this many frames use 1 warp
+                                      // (measured on B200: 4 warps per frame is at least as fast at every batch size)
   bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
   bool board_fast = true;  // four-lane group scoring of candidate boards (0 = general path only)
   bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
@@ -313,6 +314,7 @@ int run_boards(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGe
   prof_mark(det, -1, s);
   // throughput mode: one warp per frame once the launch alone can occupy every SM several times
   const BoardWsLayout& BL = (det->board_warps == 0 && n >= det->board_batch_frames) ? S.layout_batch : S.layout;
+  (void)S.layout_batch;
   det->launches += launch_boards_decode(
       d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->fam.n_codes, det->fam.edge,
       det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,

@@ -73,6 +73,7 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps) {
   L.sm_pos = stake(sizeof(float) * 3 * L.smem_saddles);
   L.sm_gstart = stake(sizeof(uint16_t) * (L.grid_cap_cells + 2));
   L.sm_gitem = stake(sizeof(uint16_t) * L.smem_saddles);
+  L.sm_gpos = stake(sizeof(float2) * L.smem_saddles);
   L.sm_hist = stake(sizeof(int) * agb::kHistBins);
   L.sm_ctl = stake(sizeof(int) * 16);
   // throughput path (ag_board_fast.cuh): per wave slot best score + quad
@@ -153,6 +154,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
     F.g_base = use_grid ? (uint16_t*)(smem + L.sm_gstart) : nullptr;
     F.g_start = F.g_base;
     F.g_item = (uint16_t*)(smem + L.sm_gitem);
+    F.g_pos = (float2*)(smem + L.sm_gpos);
     F.g_nx = (g.w + bucket - 1) / bucket;
     F.g_ny = (g.h + bucket - 1) / bucket;
     F.g_cap_cells = L.grid_cap_cells;

@@ -119,6 +119,7 @@ struct Frame {
   // throughput path (device only, ag_board_fast.cuh); unused when fast_on == 0
   int fast_on;
   uint16_t* g_base;      // unshifted bucket-grid array ([cells + 2])
+  float2* g_pos;         // [n] saddle positions in g_item order (one load per scanned candidate)
   int active_words;      // words of bs.active
   int16_t* fx_qlist;     // [kQListCap][4] candidate quads of the current seed
   uint16_t* fx_qscore;   // [kQListCap]

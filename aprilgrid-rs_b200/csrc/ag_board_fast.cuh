@@ -92,6 +92,7 @@ __device__ __noinline__ void grid_build_warp(Frame& F) {
       const int rank = __popc(peers & ((1u << F.lane) - 1u));
       const int e = G[b + 1];
       F.g_item[e - 1 - rank] = (uint16_t)i;
+      F.g_pos[e - 1 - rank] = make_float2(F.sx[i], F.sy[i]);
     }
     __syncwarp();
     if (i < F.n && (__ffs((int)peers) - 1) == F.lane) G[b + 1] = (uint16_t)(G[b + 1] - __popc(peers));
@@ -118,15 +119,12 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
   const float qx = fadd(sfx, fmul(v10x, ratio0)), qy = fadd(sfy, fmul(v10y, ratio0));
   const unsigned long long kInf = ~0ull;
   unsigned long long k0 = kInf, k1 = kInf, k2 = kInf;
-  auto consider = [&](int i) {
-    const float d = dist2(F, qx, qy, i);
-    if (d <= r2) {
-      const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
-      if (k < k2) {
-        k2 = k;
-        if (k2 < k1) { const unsigned long long t = k1; k1 = k2; k2 = t; }
-        if (k1 < k0) { const unsigned long long t = k0; k0 = k1; k1 = t; }
-      }
+  auto insert = [&](float d, int i) {
+    const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
+    if (k < k2) {
+      k2 = k;
+      if (k2 < k1) { const unsigned long long t = k1; k1 = k2; k2 = t; }
+      if (k1 < k0) { const unsigned long long t = k0; k0 = k1; k1 = t; }
     }
   };
   if (F.g_on && r2 >= 0.0f && r2 < 1.0e12f) {
@@ -136,14 +134,32 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
     x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
     x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
     const int bw = x1 - x0 + 1;
-    if (bw > 0)
-      for (int yy = y0; yy <= y1; ++yy) {
-        const int b0 = yy * F.g_nx + x0;
-        const int e1 = F.g_start[b0 + bw];
-        for (int e = F.g_start[b0]; e < e1; ++e) consider(F.g_item[e]);
+    if (bw > 0 && y0 <= y1) {
+      // One flat loop over the window's bucket rows (a row of buckets is one contiguous range of
+      // the grid-ordered arrays): lanes with different windows stay in the same loop, so the warp
+      // pays max(total candidates) rather than the sum of per-row maxima.
+      int yy = y0, b0 = y0 * F.g_nx + x0;
+      int e = F.g_start[b0], e1 = F.g_start[b0 + bw];
+      for (;;) {
+        if (e >= e1) {
+          if (++yy > y1) break;
+          b0 += F.g_nx;
+          e = F.g_start[b0];
+          e1 = F.g_start[b0 + bw];
+          continue;
+        }
+        const float2 p = F.g_pos[e];
+        const float ddx = fsub(qx, p.x), ddy = fsub(qy, p.y);  // dist2(): (0 + dx*dx) + dy*dy
+        const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
+        if (d <= r2) insert(d, F.g_item[e]);
+        ++e;
       }
+    }
   } else {
-    for (int i = 0; i < F.n; ++i) consider(i);
+    for (int i = 0; i < F.n; ++i) {
+      const float d = dist2(F, qx, qy, i);
+      if (d <= r2) insert(d, i);
+    }
   }
   const float ts = F.st[self];
   unsigned packed = 0, cnt = 0;
@@ -360,10 +376,82 @@ __device__ __forceinline__ void unrank_pair_fast(int c, int m, int* p, int* q) {
   *q = a + 1 + (c - a * (2 * m - a - 1) / 2);
 }
 
+// The k (<= 64) nearest saddles of a point for n <= 512 saddles, ascending by (d2, index), into
+// F.nn_idx -- same result as nearest_k (kdtree `nearest`, ties -> lower index).  Every lane keeps
+// the squared distances of its <= 16 saddles in registers; the k-th smallest distance is found
+// by bisection on its bit pattern (d2 >= 0: the IEEE bits are monotone) with one warp reduction
+// per bit, the saddles at or below it are gathered and sorted by a 64-wide bitonic network.
+__device__ __noinline__ int nearest_k_fast(Frame& F, float qx, float qy, int k, unsigned long long* scratch64) {
+  const int n = F.n;
+  const int kk = k < n ? k : n;
+  if (kk <= 0) return 0;
+  unsigned db[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int i = F.lane + 32 * j;
+    db[j] = i < n ? __float_as_uint(dist2(F, qx, qy, i)) : 0xffffffffu;
+  }
+  // smallest T with |{d <= T}| >= kk  (NaN / negative patterns cannot occur: d2 = x*x + y*y)
+  unsigned T = 0;
+#pragma unroll 1
+  for (int bit = 30; bit >= 0; --bit) {
+    const unsigned trial = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) c += db[j] < trial ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c < kk) T = trial;  // fewer than kk strictly below trial: the answer is >= trial
+  }
+  // gather {d <= T} (>= kk of them; more only on exact ties at T)
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool in = db[j] <= T && (F.lane + 32 * j) < n;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const int dst = cnt + __popc(m & ((1u << F.lane) - 1u));
+      if (dst < 64) scratch64[dst] = ((unsigned long long)db[j] << 32) | (unsigned)(F.lane + 32 * j);
+    }
+    cnt += __popc(m);
+  }
+  if (cnt > 64) return -1;  // > 14 exact ties at the k-th distance: let the caller use nearest_k
+  __syncwarp();
+  unsigned long long v0 = F.lane < cnt ? scratch64[F.lane] : ~0ull;
+  unsigned long long v1 = F.lane + 32 < cnt ? scratch64[F.lane + 32] : ~0ull;
+  // bitonic sort of 64 keys, element e = lane (v0) or lane + 32 (v1)
+#pragma unroll
+  for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride == 32) {
+        // partner of element e is e ^ 32: the lane's own other register; ascending for size 64
+        const unsigned long long lo = v0 < v1 ? v0 : v1, hi = v0 < v1 ? v1 : v0;
+        v0 = lo;
+        v1 = hi;
+      } else {
+        const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, v0, stride);
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, v1, stride);
+        const bool lower = (F.lane & stride) == 0;
+        const bool up0 = (F.lane & size) == 0 || size == 64;          // direction of element `lane`
+        const bool up1 = ((F.lane + 32) & size) == 0 || size == 64;   // ... of element `lane + 32`
+        const bool keep_min0 = lower == up0, keep_min1 = lower == up1;
+        v0 = keep_min0 ? (v0 < o0 ? v0 : o0) : (v0 < o0 ? o0 : v0);
+        v1 = keep_min1 ? (v1 < o1 ? v1 : o1) : (v1 < o1 ? o1 : v1);
+      }
+    }
+  }
+  if (F.lane < kk) F.nn_idx[F.lane] = (int16_t)(unsigned)v0;
+  if (F.lane + 32 < kk) F.nn_idx[F.lane + 32] = (int16_t)(unsigned)v1;
+  __syncwarp();
+  return kk;
+}
+
 // 50-NN of the seed, same / diff classification (detector.rs:550-563), per-diff vectors.
 __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
   E.s0 = s0;
-  const int n_nn = nearest_k(F, F.sx[s0], F.sy[s0], 50);
+  // fx_dvx .. fx_dc (1 KB, contiguous) are free until the classification below fills them
+  int n_nn = nearest_k_fast(F, F.sx[s0], F.sy[s0], 50, (unsigned long long*)F.fx_dvx);
+  if (n_nn < 0) n_nn = nearest_k(F, F.sx[s0], F.sy[s0], 50);
   const float t0 = F.st[s0], x0 = F.sx[s0], y0 = F.sy[s0];
   int n_same = 0, n_diff = 0;
   for (int base = 1; base < n_nn; base += 32) {  // nearest[1..]: the first hit is the seed itself

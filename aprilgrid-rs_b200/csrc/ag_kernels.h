@@ -20,7 +20,7 @@ struct BoardWsLayout {
   // shared memory per block (= per frame in flight): frame-wide part, then per-warp parts
   int smem_saddles, grid_cap_cells;
   size_t sm_pos, sm_gstart, sm_gitem, sm_hist, sm_ctl, sm_warp0;
-  size_t sm_wave;
+  size_t sm_wave, sm_gpos;
   size_t smw_cell, smw_active, smw_small, smw_qlist, smw_qscore, smw_fvec, smw_elig, smw_squeue;
   size_t smem_per_warp, smem_per_block;
 };
