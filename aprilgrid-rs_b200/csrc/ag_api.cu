@@ -85,6 +85,7 @@ struct ag_detector {
                               // caller's stream; ag_detect_batch_device_wait does that
   uint64_t launches = 0;
   long chunk_frames = 512;
+  long host_chunk_frames = 128;  // chunk of the host-buffer path (ag_detect_batch)
   long max_clusters = 16384;
   long max_saddles = 2048;
   uint64_t* d_codes = nullptr;  // family table in global memory (renderer)
@@ -97,8 +98,7 @@ struct ag_detector {
   // warps per frame in the board kernel: 0 = automatic (1 when a launch has enough frames to
   // fill the GPU with one-warp blocks, 4 otherwise), or 1 / 2 / 4 / 8
   long board_warps = 0;
-  long board_batch_frames = 1 << 30;  // automatic mode: launches with at least this many frames use 1 warp
-                                      // (measured on B200: 4 warps per frame is at least as fast at every batch size)
+  long board_batch_frames = 148;  // automatic mode: launches with at least this many frames use 2 warps per frame
   bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
   bool board_fast = true;  // four-lane group scoring of candidate boards (0 = general path only)
   bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
@@ -213,8 +213,8 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     if ((rc = regrow(det, &S.d_raw, (size_t)F * ncl))) return rc;
     if ((rc = regrow(det, &S.d_raw_valid, (size_t)F * ncl))) return rc;
     if ((rc = regrow(det, &S.d_refined, (size_t)F * nsd))) return rc;
-    S.layout = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 4);
-    S.layout_batch = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 1);
+    S.layout = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 8);
+    S.layout_batch = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 2);
     if ((rc = regrow(det, &S.d_board_ws, (size_t)F * S.layout.bytes_per_frame))) return rc;
     if ((rc = regrow(det, &S.d_tap_quads, (size_t)F * S.layout.max_quads * 4))) return rc;
     if ((rc = regrow(det, &S.d_tap_nquads, (size_t)F))) return rc;
@@ -313,8 +313,9 @@ int run_boards(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGe
                cudaStream_t s) {
   prof_mark(det, -1, s);
   // throughput mode: one warp per frame once the launch alone can occupy every SM several times
+  // automatic warps per frame: throughput (2 warps: most frames resident per SM) once a launch can
+  // fill the GPU, latency (8 warps share one frame's seeds) for a handful of frames
   const BoardWsLayout& BL = (det->board_warps == 0 && n >= det->board_batch_frames) ? S.layout_batch : S.layout;
-  (void)S.layout_batch;
   det->launches += launch_boards_decode(
       d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->fam.n_codes, det->fam.edge,
       det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
@@ -493,6 +494,9 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   if (!strcmp(key, "chunk_frames")) {
     if (value < 1 || value > 65535) return fail(det, AG_ERR_INVALID, "chunk_frames out of range");
     det->chunk_frames = value;
+  } else if (!strcmp(key, "host_chunk_frames")) {
+    if (value < 1 || value > 65535) return fail(det, AG_ERR_INVALID, "host_chunk_frames out of range");
+    det->host_chunk_frames = value;
   } else if (!strcmp(key, "max_clusters")) {
     if (value < 16 || value > (1 << 22)) return fail(det, AG_ERR_INVALID, "max_clusters out of range");
     det->max_clusters = value;
@@ -650,15 +654,18 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
   if (n_frames == 0) return AG_OK;
-  const int chunk = (int)std::min<long>(det->chunk_frames, n_frames);
-  const int n_slots = n_frames > chunk ? 2 : 1;
+  // host frames: smaller chunks than the device path so that uploads, kernels and downloads of
+  // up to kSlots chunks overlap (each slot has its own stream)
+  const int chunk = (int)std::min<long>(std::min<long>(det->chunk_frames, det->host_chunk_frames), n_frames);
+  const int n_slots = std::min(kSlots, (n_frames + chunk - 1) / chunk);
   for (int i = 0; i < n_slots; ++i)
     if ((rc = ensure_slot(det, det->slot[i], g, chunk, cap_per_frame, true))) return rc;
   bool truncated = false;
-  // Software pipeline over two slots: while slot A computes chunk i, slot B uploads chunk i+1.
-  struct Pending { int f0, n; bool live; } pend[2] = {{0, 0, false}, {0, 0, false}};
+  // Software pipeline over the slots: while one slot computes chunk i, the next ones upload
+  // chunks i+1, i+2, ...; a slot's results are copied out just before the slot is reused.
+  struct Pending { int f0, n; bool live; } pend[kSlots] = {};
   int which = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk, which ^= 1) {
+  for (int f0 = 0; f0 < n_frames; f0 += chunk, which = (which + 1) % n_slots) {
     Slot& S = det->slot[which];
     if (pend[which].live) {
       AG_CUDA(det, cudaEventSynchronize(S.done));
@@ -682,7 +689,8 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
     AG_CUDA(det, cudaEventRecord(S.done, S.stream));
     pend[which] = {f0, n, true};
   }
-  for (int i = 0; i < 2; ++i) {
+  for (int k = 0; k < n_slots; ++k) {  // oldest first
+    const int i = (which + k) % n_slots;
     if (!pend[i].live) continue;
     Slot& S = det->slot[i];
     AG_CUDA(det, cudaEventSynchronize(S.done));

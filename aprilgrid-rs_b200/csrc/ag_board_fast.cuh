@@ -103,20 +103,26 @@ __device__ __noinline__ void grid_build_warp(Frame& F) {
   __syncwarp();
 }
 
-// ---- one neighbour search of try_expand_one on ONE lane ----------------------------------------
+// ---- one neighbour search of try_expand_one per lane, the whole warp in step -----------------------
 // find_closest_potential_saddle_idxs (board.rs:177-234) for the edge a -> b seen from `self`:
 // the up to three nearest saddles within the radius, ascending by (d2, index), then filtered by
 // the board's active mask and the theta gate.  Returns the survivors packed as
 // count | c0 << 2 | c1 << 12 | c2 << 22 (indices < 1024).
-__device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* active, int a, int b,
-                                                int self) {
-  const float ratio0 = fadd(1.0f, 0.3f);  // 1.0 + spacing_ratio; detector.rs:621 passes 0.3
-  const float ax = F.sx[a], ay = F.sy[a], bx = F.sx[b], by = F.sy[b];
-  const float dx = fsub(ax, bx), dy = fsub(ay, by);
-  const float r2 = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
-  const float v10x = fsub(bx, ax), v10y = fsub(by, ay);
-  const float sfx = self == a ? ax : bx, sfy = self == a ? ay : by;
-  const float qx = fadd(sfx, fmul(v10x, ratio0)), qy = fadd(sfy, fmul(v10y, ratio0));
+//
+// EVERY lane of the warp calls this (lanes with `on` == false search nothing): the candidate
+// loop is kept convergent with one vote per iteration, so the warp pays the longest search of
+// its 32 lanes once instead of running the lanes' loops one after the other.
+//
+// Best-first scan of the window's bucket rows: the row of the query first, then alternately
+// the rows above and below (a row of buckets is one contiguous range of the grid-ordered
+// arrays).  Once three saddles are known, a row whose vertical distance from the query exceeds
+// the third-best distance ends the search, and the column range of a row shrinks to that
+// distance -- a long edge a -> b gives a radius that covers most of the board although only
+// the three nearest saddles matter.  All bounds are conservative, so the result equals the
+// scan of the whole window.
+__device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* active, bool on, int a,
+                                                int b, int self) {
+  const unsigned full = 0xffffffffu;
   const unsigned long long kInf = ~0ull;
   unsigned long long k0 = kInf, k1 = kInf, k2 = kInf;
   auto insert = [&](float d, int i) {
@@ -127,53 +133,98 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
       if (k1 < k0) { const unsigned long long t = k0; k0 = k1; k1 = t; }
     }
   };
-  if (F.g_on && r2 >= 0.0f && r2 < 1.0e12f) {
-    const float r = sqrtf(r2) * 1.0001f + 0.01f;
-    int x0 = (int)floorf((qx - r) * F.g_inv), x1 = (int)floorf((qx + r) * F.g_inv);
-    int y0 = (int)floorf((qy - r) * F.g_inv), y1 = (int)floorf((qy + r) * F.g_inv);
-    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
-    x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
-    const int bw = x1 - x0 + 1;
-    if (bw > 0 && y0 <= y1) {
-      // One flat loop over the window's bucket rows (a row of buckets is one contiguous range of
-      // the grid-ordered arrays): lanes with different windows stay in the same loop, so the warp
-      // pays max(total candidates) rather than the sum of per-row maxima.
-      int yy = y0, b0 = y0 * F.g_nx + x0;
-      int e = F.g_start[b0], e1 = F.g_start[b0 + bw];
-      for (;;) {
-        if (e >= e1) {
-          if (++yy > y1) break;
-          b0 += F.g_nx;
-          e = F.g_start[b0];
-          e1 = F.g_start[b0 + bw];
-          continue;
+  float qx = 0.0f, qy = 0.0f, r2 = -1.0f, r = 0.0f;
+  if (on) {
+    const float ratio0 = fadd(1.0f, 0.3f);  // 1.0 + spacing_ratio; detector.rs:621 passes 0.3
+    const float ax = F.sx[a], ay = F.sy[a], bx = F.sx[b], by = F.sy[b];
+    const float dx = fsub(ax, bx), dy = fsub(ay, by);
+    r2 = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
+    const float v10x = fsub(bx, ax), v10y = fsub(by, ay);
+    const float sfx = self == a ? ax : bx, sfy = self == a ? ay : by;
+    qx = fadd(sfx, fmul(v10x, ratio0));
+    qy = fadd(sfy, fmul(v10y, ratio0));
+  }
+  if (F.g_on) {  // block-uniform
+    const bool windowed = on && r2 >= 0.0f && r2 < 1.0e12f;
+    int x0 = 0, x1 = -1, y0 = 0, y1 = -1, cy = 0, t = 0, t_end = 0;
+    if (windowed) {
+      r = sqrtf(r2) * 1.0001f + 0.01f;
+      x0 = (int)floorf((qx - r) * F.g_inv); x1 = (int)floorf((qx + r) * F.g_inv);
+      y0 = (int)floorf((qy - r) * F.g_inv); y1 = (int)floorf((qy + r) * F.g_inv);
+      x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
+      x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+      if (x0 <= x1 && y0 <= y1) {
+        cy = (int)floorf(qy * F.g_inv);
+        cy = cy < y0 ? y0 : (cy > y1 ? y1 : cy);
+        t_end = 2 * max(cy - y0, y1 - cy) + 1;  // rows are visited at offsets 0, -1, +1, -2, ...
+      }
+    }
+    const float bsz = 1.0f / F.g_inv;  // bucket side, a power of two: bucket indices are exact
+    int e = 0, e1 = 0;
+    for (;;) {
+      if (e >= e1 && t < t_end) {  // step to the next row of the window (one row per iteration)
+        const int j = (t + 1) >> 1, yy = (t & 1) ? cy - j : cy + j;
+        ++t;
+        if (yy >= y0 && yy <= y1) {
+          float R = r;
+          bool row_ok = true;
+          if (k2 != kInf) {
+            const float d3 = __uint_as_float((unsigned)(k2 >> 32));
+            const float lb = (float)(j > 0 ? j - 1 : 0) * bsz;  // every saddle of the row is farther than this
+            if (lb * lb * 0.9999f > d3) {                        // ... and so are the remaining rows
+              t = t_end;
+              row_ok = false;
+            }
+            R = fminf(r, sqrtf(d3) * 1.0001f + 0.01f);
+          }
+          if (row_ok) {
+            int bx0 = (int)floorf((qx - R) * F.g_inv), bx1 = (int)floorf((qx + R) * F.g_inv);
+            bx0 = bx0 < x0 ? x0 : bx0;
+            bx1 = bx1 > x1 ? x1 : bx1;
+            if (bx0 <= bx1) {
+              const int b0 = yy * F.g_nx;
+              e = F.g_start[b0 + bx0];
+              e1 = F.g_start[b0 + bx1 + 1];
+            }
+          }
         }
+      }
+      if (e < e1) {
         const float2 p = F.g_pos[e];
         const float ddx = fsub(qx, p.x), ddy = fsub(qy, p.y);  // dist2(): (0 + dx*dx) + dy*dy
         const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
         if (d <= r2) insert(d, F.g_item[e]);
         ++e;
       }
+      if (!__any_sync(full, e < e1 || t < t_end)) break;
     }
+    if (on && !windowed)  // degenerate radius (NaN / huge): exhaustive
+      for (int i = 0; i < F.n; ++i) {
+        const float d = dist2(F, qx, qy, i);
+        if (d <= r2) insert(d, i);
+      }
   } else {
-    for (int i = 0; i < F.n; ++i) {
-      const float d = dist2(F, qx, qy, i);
-      if (d <= r2) insert(d, i);
-    }
+    for (int i = 0; __any_sync(full, on && i < F.n); ++i)
+      if (on && i < F.n) {
+        const float d = dist2(F, qx, qy, i);
+        if (d <= r2) insert(d, i);
+      }
   }
-  const float ts = F.st[self];
   unsigned packed = 0, cnt = 0;
-  auto keep = [&](unsigned long long k) {
-    if (k == kInf) return;
-    const int i = (int)(unsigned)k;
-    if (((active[i >> 5] >> (i & 31)) & 1u) && theta_distance_degree(ts, F.st[i]) < 5.0f) {
-      packed |= (unsigned)i << (2 + 10 * cnt);
-      ++cnt;
-    }
-  };
-  keep(k0);
-  keep(k1);
-  keep(k2);
+  if (on) {
+    const float ts = F.st[self];
+    auto keep = [&](unsigned long long k) {
+      if (k == kInf) return;
+      const int i = (int)(unsigned)k;
+      if (((active[i >> 5] >> (i & 31)) & 1u) && theta_distance_degree(ts, F.st[i]) < 5.0f) {
+        packed |= (unsigned)i << (2 + 10 * cnt);
+        ++cnt;
+      }
+    };
+    keep(k0);
+    keep(k1);
+    keep(k2);
+  }
   return packed | cnt;
 }
 __device__ __forceinline__ int packed_count(unsigned p) { return (int)(p & 3u); }
@@ -201,7 +252,9 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
   bool alive = false, list_empty = false;
   int k = 0, n_quads = 0, depth = 0, cur_ci = 0, cur_i = 0;
   int next = 0;  // list cursor (warp-uniform)
+  const bool tmon = F.tm && F.warp == 0 && F.lane == 0;
   for (;;) {
+    long long tc0 = clock64();
     // (0) idle groups take the next quads of the list
     const unsigned idle = __ballot_sync(full, !alive) & 0x11111111u;
     if (idle != 0u && !list_empty) {
@@ -236,6 +289,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
       __syncwarp();
     }
     if (!__any_sync(full, alive)) break;
+    if (tmon) { const long long tc = clock64(); F.tm[2] += (uint32_t)(tc - tc0); tc0 = tc; }
     // (1) every running board advances to its next expansion attempt (or finishes)
     bool need = false;
     int dir = 0, nci = 0, result = -1;
@@ -283,7 +337,8 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
       }
     }
     // (2) the four neighbour searches of try_expand_one, one per lane
-    unsigned mine = 0;
+    if (tmon) { const long long tc = clock64(); F.tm[5] += (uint32_t)(tc - tc0); tc0 = tc; }
+    int qa = 0, qb = 0, qself = 0;
     if (need) {
       const int qi = cell[cur_ci] - 1;
       const int2 qv = *(const int2*)(quads + 4 * qi);  // 4 x i16
@@ -292,12 +347,13 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
       // rotate_left(dir): qs[j] = quad[(j + dir) & 3]; lanes 0, 1 use the edge qs[0] -> qs[1],
       // lanes 2, 3 the edge qs[3] -> qs[2]
       const int ia = (jl < 2 ? dir : dir + 3) & 3, ib = (jl < 2 ? dir + 1 : dir + 2) & 3;
-      const int a = ia == 0 ? qq0 : (ia == 1 ? qq1 : (ia == 2 ? qq2 : qq3));
-      const int b = ib == 0 ? qq0 : (ib == 1 ? qq1 : (ib == 2 ? qq2 : qq3));
-      const int self = (jl == 1 || jl == 2) ? b : a;
-      mine = group_query(F, active, a, b, self);
+      qa = ia == 0 ? qq0 : (ia == 1 ? qq1 : (ia == 2 ? qq2 : qq3));
+      qb = ib == 0 ? qq0 : (ib == 1 ? qq1 : (ib == 2 ? qq2 : qq3));
+      qself = (jl == 1 || jl == 2) ? qb : qa;
     }
     __syncwarp();
+    const unsigned mine = group_query(F, active, need, qa, qb, qself);  // whole warp, convergent
+    if (tmon) { const long long tc = clock64(); F.tm[7] += (uint32_t)(tc - tc0); tc0 = tc; }
     const unsigned p0 = __shfl_sync(full, mine, 0, 4), p1 = __shfl_sync(full, mine, 1, 4);
     const unsigned p2 = __shfl_sync(full, mine, 2, 4), p3 = __shfl_sync(full, mine, 3, 4);
     const int n0 = packed_count(p0), n1 = packed_count(p1), n2 = packed_count(p2), n3 = packed_count(p3);
@@ -328,6 +384,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
         ok = true;
       }
     }
+    if (tmon) { const long long tc = clock64(); F.tm[10] += (uint32_t)(tc - tc0); tc0 = tc; }
     // (4) update the board
     if (need) {
       if (ok) {

@@ -47,6 +47,8 @@ print("  seeds processed %.1f  quads scored %.1f  redo batches %.2f  saddles %.0
       % (t[:, 8].mean(), t[:, 9].mean(), t[:, 10].mean(), t[:, 11].mean(), t[:, 12].mean()))
 print("  lockstep iterations %.0f  expansion attempts %.0f (%.2f groups / iteration)  tuple passes %.0f"
       % (t[:, 13].mean(), t[:, 14].mean(), t[:, 14].sum() / max(t[:, 13].sum(), 1), t[:, 15].mean()))
+print("  lockstep cycles: take-work %.0f  advance %.0f  queries %.0f  tuples %.0f  (per frame, warp 0)"
+      % (t[:, 2].mean(), t[:, 5].mean(), t[:, 7].mean(), t[:, 10].mean()))
 worst = np.argsort(-ns)[:5]
 for f in worst[:3]:
     print("  slow frame %d: %.0f us, seeds %d quads %d redo %d saddles %d tags %d; cycles %s"
