@@ -63,6 +63,8 @@ struct Slot {
   int* h_ntags = nullptr;
   uint32_t* h_status = nullptr;
   // taps
+  uint32_t* d_pixlist = nullptr;   // K3: compact list of mask pixels, [frames][pix_cap]
+  int pix_cap = 0;
   uint32_t* d_board_tm = nullptr;  // optional per-frame timing of the board kernel ([frames][16])
   int32_t* d_tap_quads = nullptr;
   int* d_tap_nquads = nullptr;
@@ -99,6 +101,7 @@ struct ag_detector {
   // fill the GPU with one-warp blocks, 4 otherwise), or 1 / 2 / 4 / 8
   long board_warps = 0;
   long board_batch_frames = 148;  // automatic mode: launches with at least this many frames use 2 warps per frame
+  bool label_list = true;  // K3 over a compact pixel list (0 = word-oriented version only)
   bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
   bool board_fast = true;  // four-lane group scoring of candidate boards (0 = general path only)
   bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
@@ -197,6 +200,10 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     if ((rc = regrow(det, &S.d_resp, (size_t)F * px))) return rc;
     if ((rc = regrow(det, &S.d_parent, (size_t)F * px))) return rc;
     if ((rc = regrow(det, &S.d_mask, (size_t)F * words))) return rc;
+    // the saddle mask is 1-4 % full; a list of 1/8 of the pixels covers every real image, fuller
+    // masks (noise) take the word-oriented labelling path
+    S.pix_cap = (int)std::min<size_t>(std::max<size_t>(px / 8, 1024), (size_t)1 << 20);
+    if ((rc = regrow(det, &S.d_pixlist, (size_t)F * S.pix_cap))) return rc;
     S.cap_px = px;
     S.cap_words = words;
   }
@@ -251,7 +258,7 @@ void free_slot(Slot& S) {
   cudaFree(S.d_status); cudaFree(S.d_parent); cudaFree(S.d_acc); cudaFree(S.d_ncl);
   cudaFree(S.d_nref); cudaFree(S.d_ntags); cudaFree(S.d_centers); cudaFree(S.d_raw);
   cudaFree(S.d_refined); cudaFree(S.d_raw_valid); cudaFree(S.d_board_ws); cudaFree(S.d_tags);
-  cudaFree(S.d_tap_quads); cudaFree(S.d_tap_nquads); cudaFree(S.d_board_tm);
+  cudaFree(S.d_tap_quads); cudaFree(S.d_tap_nquads); cudaFree(S.d_board_tm); cudaFree(S.d_pixlist);
   if (S.h_tags) cudaFreeHost(S.h_tags);
   if (S.h_ntags) cudaFreeHost(S.h_ntags);
   if (S.h_status) cudaFreeHost(S.h_status);
@@ -297,7 +304,8 @@ int run_sparse(ag_detector* det, Slot& S, const FrameGeom& g, int n, uint32_t* d
   AG_CUDA(det, cudaMemsetAsync(d_status, 0, sizeof(uint32_t) * n, s));
   prof_mark(det, -1, s);
   det->launches += launch_label_clusters(S.d_mask, g, n, S.d_parent, S.cap_clusters, S.d_acc,
-                                         S.d_centers, S.d_ncl, d_status, s);
+                                         S.d_centers, S.d_ncl, d_status,
+                                         det->label_list ? S.d_pixlist : nullptr, S.pix_cap, s);
   prof_mark(det, 2, s);
   det->launches += launch_refine_filter(S.d_blur, g, n, S.d_centers, S.d_ncl, S.cap_clusters, S.d_raw,
                                         S.d_raw_valid, det->params.min_saddle_angle,
@@ -519,6 +527,8 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "board_batch_frames")) {
     if (value < 1) return fail(det, AG_ERR_INVALID, "board_batch_frames must be positive");
     det->board_batch_frames = value;
+  } else if (!strcmp(key, "label_list")) {
+    det->label_list = value != 0;
   } else if (!strcmp(key, "board_timing")) {
     det->board_timing = value != 0;
   } else if (!strcmp(key, "board_fast")) {

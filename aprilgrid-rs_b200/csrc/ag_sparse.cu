@@ -69,13 +69,12 @@ AG_D int block_exclusive_scan(int v, int* s_warp /*[32]*/, int* total) {
   return r;
 }
 
-__global__ void __launch_bounds__(kCclThreads)
-k_label_clusters(const uint32_t* __restrict__ mask, FrameGeom g, int* __restrict__ parent,
-                 int max_clusters, int* __restrict__ acc /*[F][max_clusters][3]*/,
-                 float2* __restrict__ centers, int* __restrict__ n_clusters,
-                 uint32_t* __restrict__ frame_status) {
-  __shared__ int s_warp[32];
-  __shared__ int s_total;
+// Word-oriented version: every thread walks the set bits of its own mask words.  Works for any
+// image and any fill of the mask; used when the compact pixel list below does not apply.
+AG_D void label_clusters_words(const uint32_t* __restrict__ mask, const FrameGeom& g, int* __restrict__ parent,
+                               int max_clusters, int* __restrict__ acc /*[F][max_clusters][3]*/,
+                               float2* __restrict__ centers, int* __restrict__ n_clusters,
+                               uint32_t* __restrict__ frame_status, int* s_warp, int& s_total) {
   const int f = blockIdx.x;
   const uint32_t* M = mask + (size_t)f * g.n_words;
   int* P = parent + (size_t)f * g.n_px;
@@ -188,6 +187,133 @@ k_label_clusters(const uint32_t* __restrict__ mask, FrameGeom g, int* __restrict
         atomicAdd(A + 3 * cid + 1, row);
         atomicAdd(A + 3 * cid + 2, 1);
       }
+    }
+  }
+  __syncthreads();
+  float2* Cn = centers + (size_t)f * max_clusters;
+  for (int c = tid; c < n_used; c += nt) {
+    float n = (float)__ldcg(A + 3 * c + 2);
+    float sx = (float)__ldcg(A + 3 * c + 0), sy = (float)__ldcg(A + 3 * c + 1);
+    Cn[c] = make_float2(__fdiv_rn(sx, n), __fdiv_rn(sy, n));  // detector.rs:427
+  }
+  if (tid == 0) {
+    n_clusters[f] = n_used;
+    if (total > max_clusters) atomicOr(frame_status + f, (uint32_t)AG_FRAME_CLUSTER_OVERFLOW);
+  }
+}
+
+// K3.  One CTA per frame.  The mask is 1-4 % full, so walking mask words leaves most lanes idle
+// (4 of 32 active in the word-oriented version).  Here the set pixels are first COMPACTED into a
+// list in raster order (count bits per thread, block scan, write (row << 16 | x) entries); every
+// later pass runs over the list with all lanes busy:
+//   P0 parent = left neighbour or self      P1 union with the pixel above (atomicMin hooking:
+//   the root is the component's minimum raster index)      P2 flatten      P3 number the roots
+//   in list (= raster) order with a block scan (= the reference's discovery order,
+//   detector.rs:174-185)      P4 integer centroid sums.
+// Falls back to the word-oriented version when the list does not fit or coordinates exceed 16 bits.
+__global__ void __launch_bounds__(kCclThreads)
+k_label_clusters(const uint32_t* __restrict__ mask, FrameGeom g, int* __restrict__ parent,
+                 int max_clusters, int* __restrict__ acc /*[F][max_clusters][3]*/,
+                 float2* __restrict__ centers, int* __restrict__ n_clusters,
+                 uint32_t* __restrict__ frame_status, uint32_t* __restrict__ pixlist, int list_cap) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int f = blockIdx.x;
+  const uint32_t* M = mask + (size_t)f * g.n_words;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int wpr = g.wpr, w = g.w;
+  // A: count the set pixels of this thread's contiguous word range
+  const int per = (g.n_words + nt - 1) / nt;
+  const int w_begin = min(tid * per, g.n_words), w_end = min(w_begin + per, g.n_words);
+  int my_px = 0;
+  for (int wi = w_begin; wi < w_end; ++wi) my_px += __popc(M[wi]);
+  int offset = block_exclusive_scan(my_px, s_warp, &s_total);
+  const int n_px = s_total;
+  __syncthreads();
+  if (!pixlist || n_px > list_cap || g.w > 65535 || g.h > 65535) {  // block-uniform
+    label_clusters_words(mask, g, parent, max_clusters, acc, centers, n_clusters, frame_status, s_warp,
+                         s_total);
+    return;
+  }
+  uint32_t* L = pixlist + (size_t)f * list_cap;
+  int* P = parent + (size_t)f * g.n_px;
+  int* A = acc + (size_t)f * max_clusters * 3;
+  if (my_px) {
+    int row = w_begin / wpr, wc = w_begin - row * wpr;
+    for (int wi = w_begin; wi < w_end; ++wi) {
+      uint32_t m = M[wi];
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        L[offset++] = ((uint32_t)row << 16) | (uint32_t)(wc * 32 + b);
+      }
+      if (++wc == wpr) { wc = 0; ++row; }
+    }
+  }
+  __syncthreads();
+  auto bit = [&](int row, int x) -> bool { return (M[row * wpr + (x >> 5)] >> (x & 31)) & 1u; };
+  // P0: every mask pixel points at its left neighbour if that is set, else at itself.
+  for (int i = tid; i < n_px; i += nt) {
+    const uint32_t e = L[i];
+    const int row = (int)(e >> 16), x = (int)(e & 0xffffu);
+    const int p = row * w + x;
+    P[p] = (x > 0 && bit(row, x - 1)) ? p - 1 : p;
+  }
+  __syncthreads();
+  // P1: union with the pixel above.  A pixel whose left and upper-left neighbours are both
+  // set is already connected to its upper neighbour through them, so it is skipped.
+  for (int i = tid; i < n_px; i += nt) {
+    const uint32_t e = L[i];
+    const int row = (int)(e >> 16), x = (int)(e & 0xffffu);
+    if (row == 0 || !bit(row - 1, x)) continue;
+    if (x > 0 && bit(row, x - 1) && bit(row - 1, x - 1)) continue;
+    const int p = row * w + x;
+    uf_union(P, p, p - w);
+  }
+  __syncthreads();
+  // P2: flatten so that every pixel stores its root (= min raster index of the component).
+  for (int i = tid; i < n_px; i += nt) {
+    const uint32_t e = L[i];
+    const int p = (int)(e >> 16) * w + (int)(e & 0xffffu);
+    const int r = uf_find(P, p);
+    if (r != p) P[p] = r;
+  }
+  __syncthreads();
+  // P3: number the roots in ascending raster order.  Thread t owns a contiguous part of the list.
+  const int lper = (n_px + nt - 1) / nt;
+  const int l_begin = min(tid * lper, n_px), l_end = min(l_begin + lper, n_px);
+  int my_roots = 0;
+  for (int i = l_begin; i < l_end; ++i) {
+    const uint32_t e = L[i];
+    const int p = (int)(e >> 16) * w + (int)(e & 0xffffu);
+    if (__ldcg(P + p) == p) ++my_roots;
+  }
+  int roff = block_exclusive_scan(my_roots, s_warp, &s_total);
+  const int total = s_total;
+  for (int i = l_begin; i < l_end; ++i) {
+    const uint32_t e = L[i];
+    const int p = (int)(e >> 16) * w + (int)(e & 0xffffu);
+    if (__ldcg(P + p) == p) {
+      P[p] = -(roff + 1);  // root now carries its cluster id, encoded negative
+      ++roff;
+    }
+  }
+  const int n_used = min(total, max_clusters);
+  for (int i = tid; i < n_used * 3; i += nt) A[i] = 0;
+  __syncthreads();
+  // P4: accumulate (sum x, sum y, count) per cluster with integer atomics.  The reference
+  // sums the coordinates in f32 (detector.rs:424-426); integer sums below 2^24 are exact
+  // in f32 whatever the order, so one int->float conversion reproduces them bit for bit.
+  for (int i = tid; i < n_px; i += nt) {
+    const uint32_t e = L[i];
+    const int row = (int)(e >> 16), x = (int)(e & 0xffffu);
+    const int p = row * w + x;
+    const int v = __ldcg(P + p);
+    const int cid = v < 0 ? -v - 1 : -__ldcg(P + v) - 1;
+    if (cid < max_clusters) {
+      atomicAdd(A + 3 * cid + 0, x);
+      atomicAdd(A + 3 * cid + 1, row);
+      atomicAdd(A + 3 * cid + 2, 1);
     }
   }
   __syncthreads();
@@ -396,9 +522,9 @@ k_refine_filter(const float* __restrict__ blur, FrameGeom g, const float2* __res
 
 int launch_label_clusters(const uint32_t* mask, const FrameGeom& g, int n_frames, int* parent,
                           int max_clusters, int* acc, float2* centers, int* n_clusters,
-                          uint32_t* frame_status, cudaStream_t s) {
+                          uint32_t* frame_status, uint32_t* pixlist, int list_cap, cudaStream_t s) {
   k_label_clusters<<<n_frames, kCclThreads, 0, s>>>(mask, g, parent, max_clusters, acc, centers,
-                                                    n_clusters, frame_status);
+                                                    n_clusters, frame_status, pixlist, list_cap);
   return 1;
 }
 
