@@ -39,24 +39,46 @@ std::string g_create_error;
 // front end of chunk i+1 runs on the caller's stream while the latency-bound board searches of
 // chunks i, i-1, ... run on their slots' own streams, side by side.
 constexpr int kSlots = 4;
+// Device-batch path: the dense buffers of ONE slot are reused chunk after chunk (K1-K4 of
+// consecutive chunks are serial on the caller's stream anyway); only the light board-search side
+// is multi-buffered, so the board searches of up to kBoardSlots chunks overlap each other and
+// the front end of later chunks, which hides the long tail of the slowest frames of a chunk.
+constexpr int kBoardSlots = 8;
+
+// Board-search side of a chunk: what K4 hands to K6, K6's workspace, its stream and events.
+// A few hundred KB per frame, so many of these can be in flight (see kBoardSlots).
+struct BoardSlot {
+  cudaStream_t bstream = nullptr;
+  cudaEvent_t ev_front = nullptr, ev_boards = nullptr;  // front end done / board search done
+  bool pending = false;                                 // a board kernel may still be running
+  int cap_frames = 0, cap_saddles = 0;
+  long cfg_warps = -1, cfg_lattice = -1;
+  ag_saddle* d_refined = nullptr;
+  int* d_nref = nullptr;
+  uint8_t* d_board_ws = nullptr;
+  uint32_t* d_status = nullptr;
+  uint32_t* d_board_tm = nullptr;  // optional per-frame timing of the board kernel ([frames][16])
+  int32_t* d_tap_quads = nullptr;
+  int* d_tap_nquads = nullptr;
+  BoardWsLayout layout{};        // sized for the largest warps-per-frame (allocation)
+  BoardWsLayout layout_batch{};  // layout used when many frames are in flight
+};
 
 // Device buffers of one pipeline slot (one chunk in flight).
 struct Slot {
   cudaStream_t stream = nullptr;
-  cudaStream_t bstream = nullptr;  // board search of this slot's chunk (device-batch pipeline)
   cudaEvent_t done = nullptr;
-  cudaEvent_t ev_front = nullptr, ev_boards = nullptr;  // device-batch pipeline hand-offs
-  bool boards_pending = false;
+  BoardSlot bb;  // the slot's own board-search side (host path, taps)
   int cap_frames = 0;
   size_t cap_px = 0, cap_words = 0, cap_in_bytes = 0;
   int cap_clusters = 0, cap_saddles = 0, cap_tags = 0;
   uint8_t* d_in = nullptr;
   float *d_blur = nullptr, *d_resp = nullptr;
   uint32_t *d_min = nullptr, *d_mask = nullptr, *d_status = nullptr;
-  int *d_parent = nullptr, *d_acc = nullptr, *d_ncl = nullptr, *d_nref = nullptr, *d_ntags = nullptr;
+  int *d_parent = nullptr, *d_acc = nullptr, *d_ncl = nullptr, *d_ntags = nullptr;
   float2* d_centers = nullptr;
-  ag_saddle *d_raw = nullptr, *d_refined = nullptr;
-  uint8_t *d_raw_valid = nullptr, *d_board_ws = nullptr;
+  ag_saddle* d_raw = nullptr;
+  uint8_t* d_raw_valid = nullptr;
   ag_tag* d_tags = nullptr;
   // pinned result staging
   ag_tag* h_tags = nullptr;
@@ -65,11 +87,6 @@ struct Slot {
   // taps
   uint32_t* d_pixlist = nullptr;   // K3: compact list of mask pixels, [frames][pix_cap]
   int pix_cap = 0;
-  uint32_t* d_board_tm = nullptr;  // optional per-frame timing of the board kernel ([frames][16])
-  int32_t* d_tap_quads = nullptr;
-  int* d_tap_nquads = nullptr;
-  BoardWsLayout layout{};       // sized for the largest warps-per-frame (allocation)
-  BoardWsLayout layout_batch{};  // layout used when many frames are in flight (1 warp per frame)
 };
 
 }  // namespace
@@ -82,7 +99,9 @@ struct ag_detector {
   std::mutex mu;
   std::string err;
   Slot slot[kSlots];
-  int slot_rr = 0;            // next slot of the device-batch pipeline (rotates across calls)
+  BoardSlot bslot[kBoardSlots];
+  int slot_rr = 0;            // next board slot of the device-batch pipeline (rotates across calls)
+  bool device_path_busy = false;  // device-batch work may still be in flight on slot 0 / the board slots
   bool device_async = false;  // ag_detect_batch_device returns without ordering the results on the
                               // caller's stream; ag_detect_batch_device_wait does that
   uint64_t launches = 0;
@@ -130,6 +149,10 @@ namespace {
     }                                                                                        \
   } while (0)
 
+// Host-buffer entry points and taps share slot 0 with the device-batch pipeline: wait until the
+// latter has drained before touching the buffers.
+int quiesce_device_path(ag_detector* det);
+
 int fail(ag_detector* det, int code, const char* msg) {
   if (det) det->err = msg;
   return code;
@@ -170,25 +193,59 @@ int regrow(ag_detector* det, T** p, size_t count) {
   return AG_OK;
 }
 
+// Make sure a board slot can hold `frames` frames.  Waits for a board kernel that may still be
+// using the slot only when its buffers have to be replaced (or when asked to: `drain`).
+int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
+  int rc;
+  if (!B.bstream) {
+    AG_CUDA(det, cudaStreamCreateWithFlags(&B.bstream, cudaStreamNonBlocking));
+    AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_front, cudaEventDisableTiming));
+    AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_boards, cudaEventDisableTiming));
+  }
+  const int nsd = (int)det->max_saddles;
+  const bool realloc = frames > B.cap_frames || nsd != B.cap_saddles || det->board_warps != B.cfg_warps ||
+                       det->board_lattice != B.cfg_lattice;
+  if (B.pending && (realloc || drain)) {
+    AG_CUDA(det, cudaEventSynchronize(B.ev_boards));
+    B.pending = false;
+  }
+  if (!realloc) return AG_OK;
+  const int F = std::max(frames, B.cap_frames);
+  if ((rc = regrow(det, &B.d_nref, (size_t)F))) return rc;
+  if ((rc = regrow(det, &B.d_status, (size_t)F))) return rc;
+  if ((rc = regrow(det, &B.d_refined, (size_t)F * nsd))) return rc;
+  B.layout = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 8);
+  B.layout_batch = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 2);
+  if ((rc = regrow(det, &B.d_board_ws, (size_t)F * B.layout.bytes_per_frame))) return rc;
+  if ((rc = regrow(det, &B.d_tap_quads, (size_t)F * B.layout.max_quads * 4))) return rc;
+  if ((rc = regrow(det, &B.d_tap_nquads, (size_t)F))) return rc;
+  if ((rc = regrow(det, &B.d_board_tm, (size_t)F * 16))) return rc;
+  B.cap_frames = F;
+  B.cap_saddles = nsd;
+  B.cfg_warps = det->board_warps;
+  B.cfg_lattice = det->board_lattice;
+  return AG_OK;
+}
+
+void free_board_slot(BoardSlot& B) {
+  cudaFree(B.d_nref); cudaFree(B.d_status); cudaFree(B.d_refined); cudaFree(B.d_board_ws);
+  cudaFree(B.d_tap_quads); cudaFree(B.d_tap_nquads); cudaFree(B.d_board_tm);
+  if (B.ev_front) cudaEventDestroy(B.ev_front);
+  if (B.ev_boards) cudaEventDestroy(B.ev_boards);
+  if (B.bstream) cudaStreamDestroy(B.bstream);
+  B = BoardSlot();
+}
+
 // Make sure a slot can hold `frames` frames of geometry g with `cap_tags` tags per frame.
+// `own_board` = the slot's own board-search side is needed too (host path, taps).
 int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int cap_tags,
-                bool need_input, bool keep_pending = false) {
+                bool need_input, bool own_board = true) {
   int rc;
   if (!S.stream) {
     AG_CUDA(det, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
-    AG_CUDA(det, cudaStreamCreateWithFlags(&S.bstream, cudaStreamNonBlocking));
     AG_CUDA(det, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
-    AG_CUDA(det, cudaEventCreateWithFlags(&S.ev_front, cudaEventDisableTiming));
-    AG_CUDA(det, cudaEventCreateWithFlags(&S.ev_boards, cudaEventDisableTiming));
   }
-  const bool will_realloc = frames > S.cap_frames || (size_t)g.n_px > S.cap_px ||
-                            (size_t)g.n_words > S.cap_words || (int)det->max_clusters != S.cap_clusters ||
-                            (int)det->max_saddles != S.cap_saddles || cap_tags > S.cap_tags;
-  if (S.boards_pending && (will_realloc || !keep_pending)) {
-    // a previous device-batch call may still be using these buffers on the board stream
-    AG_CUDA(det, cudaEventSynchronize(S.ev_boards));
-    S.boards_pending = false;
-  }
+  if (own_board && (rc = ensure_board_slot(det, S.bb, frames, true))) return rc;
   const bool grow_frames = frames > S.cap_frames;
   const int F = std::max(frames, S.cap_frames);
   const size_t px = std::max((size_t)g.n_px, S.cap_px);
@@ -213,19 +270,11 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     if ((rc = regrow(det, &S.d_min, (size_t)F))) return rc;
     if ((rc = regrow(det, &S.d_status, (size_t)F))) return rc;
     if ((rc = regrow(det, &S.d_ncl, (size_t)F))) return rc;
-    if ((rc = regrow(det, &S.d_nref, (size_t)F))) return rc;
     if ((rc = regrow(det, &S.d_ntags, (size_t)F))) return rc;
     if ((rc = regrow(det, &S.d_acc, (size_t)F * ncl * 3))) return rc;
     if ((rc = regrow(det, &S.d_centers, (size_t)F * ncl))) return rc;
     if ((rc = regrow(det, &S.d_raw, (size_t)F * ncl))) return rc;
     if ((rc = regrow(det, &S.d_raw_valid, (size_t)F * ncl))) return rc;
-    if ((rc = regrow(det, &S.d_refined, (size_t)F * nsd))) return rc;
-    S.layout = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 8);
-    S.layout_batch = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 2);
-    if ((rc = regrow(det, &S.d_board_ws, (size_t)F * S.layout.bytes_per_frame))) return rc;
-    if ((rc = regrow(det, &S.d_tap_quads, (size_t)F * S.layout.max_quads * 4))) return rc;
-    if ((rc = regrow(det, &S.d_tap_nquads, (size_t)F))) return rc;
-    if ((rc = regrow(det, &S.d_board_tm, (size_t)F * 16))) return rc;
     if (S.h_ntags) cudaFreeHost(S.h_ntags);
     if (S.h_status) cudaFreeHost(S.h_status);
     AG_CUDA(det, cudaMallocHost((void**)&S.h_ntags, sizeof(int) * F));
@@ -256,17 +305,14 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
 void free_slot(Slot& S) {
   cudaFree(S.d_in); cudaFree(S.d_blur); cudaFree(S.d_resp); cudaFree(S.d_min); cudaFree(S.d_mask);
   cudaFree(S.d_status); cudaFree(S.d_parent); cudaFree(S.d_acc); cudaFree(S.d_ncl);
-  cudaFree(S.d_nref); cudaFree(S.d_ntags); cudaFree(S.d_centers); cudaFree(S.d_raw);
-  cudaFree(S.d_refined); cudaFree(S.d_raw_valid); cudaFree(S.d_board_ws); cudaFree(S.d_tags);
-  cudaFree(S.d_tap_quads); cudaFree(S.d_tap_nquads); cudaFree(S.d_board_tm); cudaFree(S.d_pixlist);
+  cudaFree(S.d_ntags); cudaFree(S.d_centers); cudaFree(S.d_raw);
+  cudaFree(S.d_raw_valid); cudaFree(S.d_tags); cudaFree(S.d_pixlist);
+  free_board_slot(S.bb);
   if (S.h_tags) cudaFreeHost(S.h_tags);
   if (S.h_ntags) cudaFreeHost(S.h_ntags);
   if (S.h_status) cudaFreeHost(S.h_status);
   if (S.done) cudaEventDestroy(S.done);
-  if (S.ev_front) cudaEventDestroy(S.ev_front);
-  if (S.ev_boards) cudaEventDestroy(S.ev_boards);
   if (S.stream) cudaStreamDestroy(S.stream);
-  if (S.bstream) cudaStreamDestroy(S.bstream);
   S = Slot();
 }
 
@@ -299,7 +345,7 @@ int run_dense(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeo
 }
 
 // Sparse stages up to the refined saddle list.
-int run_sparse(ag_detector* det, Slot& S, const FrameGeom& g, int n, uint32_t* d_status,
+int run_sparse(ag_detector* det, Slot& S, BoardSlot& B, const FrameGeom& g, int n, uint32_t* d_status,
                cudaStream_t s) {
   AG_CUDA(det, cudaMemsetAsync(d_status, 0, sizeof(uint32_t) * n, s));
   prof_mark(det, -1, s);
@@ -309,18 +355,17 @@ int run_sparse(ag_detector* det, Slot& S, const FrameGeom& g, int n, uint32_t* d
   prof_mark(det, 2, s);
   det->launches += launch_refine_filter(S.d_blur, g, n, S.d_centers, S.d_ncl, S.cap_clusters, S.d_raw,
                                         S.d_raw_valid, det->params.min_saddle_angle,
-                                        det->params.max_saddle_angle, S.cap_saddles, S.d_refined,
-                                        S.d_nref, d_status, s);
+                                        det->params.max_saddle_angle, B.cap_saddles, B.d_refined,
+                                        B.d_nref, d_status, s);
   prof_mark(det, 3, s);
   AG_CUDA(det, cudaGetLastError());
   return AG_OK;
 }
 
-int run_boards(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
+int run_boards(ag_detector* det, BoardSlot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
                ag_tag* d_tags, int cap, int* d_ntags, uint32_t* d_status, bool taps,
                cudaStream_t s) {
   prof_mark(det, -1, s);
-  // throughput mode: one warp per frame once the launch alone can occupy every SM several times
   // automatic warps per frame: throughput (2 warps: most frames resident per SM) once a launch can
   // fill the GPU, latency (8 warps share one frame's seeds) for a handful of frames
   const BoardWsLayout& BL = (det->board_warps == 0 && n >= det->board_batch_frames) ? S.layout_batch : S.layout;
@@ -339,8 +384,21 @@ int run_chunk(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeo
               cudaStream_t s) {
   int rc;
   if ((rc = run_dense(det, S, d_frames, g, n, true, s))) return rc;
-  if ((rc = run_sparse(det, S, g, n, d_status, s))) return rc;
-  return run_boards(det, S, d_frames, g, n, d_tags, cap, d_ntags, d_status, taps, s);
+  if ((rc = run_sparse(det, S, S.bb, g, n, d_status, s))) return rc;
+  return run_boards(det, S.bb, d_frames, g, n, d_tags, cap, d_ntags, d_status, taps, s);
+}
+
+int quiesce_device_path(ag_detector* det) {
+  if (!det->device_path_busy) return AG_OK;
+  Slot& D = det->slot[0];
+  if (D.done) AG_CUDA(det, cudaEventSynchronize(D.done));
+  for (auto& B : det->bslot)
+    if (B.pending) {
+      AG_CUDA(det, cudaEventSynchronize(B.ev_boards));
+      B.pending = false;
+    }
+  det->device_path_busy = false;
+  return AG_OK;
 }
 
 void rochade_tables_host(float cone[25], float pinv[150]) {
@@ -490,6 +548,7 @@ void ag_destroy(ag_detector* det) {
   cudaSetDevice(det->device);
   cudaDeviceSynchronize();
   for (auto& S : det->slot) free_slot(S);
+  for (auto& B : det->bslot) free_board_slot(B);
   for (auto e : det->ev_pool) cudaEventDestroy(e);
   cudaFree(det->d_codes);
   cudaFree(det->d_f32_a); cudaFree(det->d_f32_b); cudaFree(det->d_f32_c); cudaFree(det->d_taps);
@@ -516,12 +575,11 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "board_lattice")) {
     if (value != 16 && value != 32 && value != 64) return fail(det, AG_ERR_INVALID, "board_lattice must be 16, 32 or 64");
     det->board_lattice = value;
-    for (auto& S : det->slot) S.cap_saddles = -1;  // force the board workspace to be rebuilt
+
   } else if (!strcmp(key, "board_warps")) {
     if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
       return fail(det, AG_ERR_INVALID, "board_warps must be 0 (auto), 1, 2, 4 or 8");
     det->board_warps = value;
-    for (auto& S : det->slot) S.cap_saddles = -1;
   } else if (!strcmp(key, "device_async")) {
     det->device_async = value != 0;
   } else if (!strcmp(key, "board_batch_frames")) {
@@ -584,38 +642,42 @@ int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
   const int chunk = (int)std::min<long>(det->chunk_frames, std::max(n_frames, 1));
-  cudaStream_t s = stream ? (cudaStream_t)stream : det->slot[0].stream;
-  if (!stream && !det->slot[0].stream) {
-    if ((rc = ensure_slot(det, det->slot[0], g, chunk, 1, false, true))) return rc;
-    s = det->slot[0].stream;
-  }
-  // Software pipeline over kSlots slots: the dense + sparse front end of a chunk runs on stream s,
-  // its board search on the slot's own stream, so the searches of up to kSlots chunks (of this
-  // call and of earlier calls) overlap each other and the front end of the following chunks.
-  // A slot is reused only after its board kernel has finished.
+  // One set of dense buffers (slot 0: K1-K4 of consecutive chunks are serial on stream s anyway),
+  // kBoardSlots board-search sides: chunk i's K6 runs on its board slot's own stream, so the
+  // searches of up to kBoardSlots chunks (of this call and of earlier calls) overlap each other
+  // and the front end of the following chunks.  A board slot is reused only after its kernel has
+  // finished (K4 of the new chunk writes the slot's saddle list).
+  Slot& D = det->slot[0];
+  if ((rc = ensure_slot(det, D, g, chunk, 1, false, false))) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : D.stream;
+  // the dense buffers are shared by every device-batch call: order this call after the front end
+  // of the previous one even if the caller switched streams
+  if (det->device_path_busy) AG_CUDA(det, cudaStreamWaitEvent(s, D.done, 0));
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
-    Slot& S = det->slot[det->slot_rr];
-    det->slot_rr = (det->slot_rr + 1) % kSlots;
-    if ((rc = ensure_slot(det, S, g, chunk, 1, false, true))) return rc;
+    BoardSlot& B = det->bslot[det->slot_rr];
+    det->slot_rr = (det->slot_rr + 1) % kBoardSlots;
+    if ((rc = ensure_board_slot(det, B, chunk, false))) return rc;
     const int n = std::min(chunk, n_frames - f0);
     const uint8_t* in = (const uint8_t*)d_frames + (size_t)f0 * g.frame_stride;
-    uint32_t* st = d_frame_status ? d_frame_status + f0 : S.d_status;
-    if (S.boards_pending) AG_CUDA(det, cudaStreamWaitEvent(s, S.ev_boards, 0));
-    if ((rc = run_dense(det, S, in, g, n, true, s))) return rc;
-    if ((rc = run_sparse(det, S, g, n, st, s))) return rc;
-    AG_CUDA(det, cudaEventRecord(S.ev_front, s));
-    AG_CUDA(det, cudaStreamWaitEvent(S.bstream, S.ev_front, 0));
-    if ((rc = run_boards(det, S, in, g, n, d_out + (size_t)f0 * cap_per_frame, cap_per_frame,
-                         d_n_per_frame + f0, st, false, S.bstream)))
+    uint32_t* st = d_frame_status ? d_frame_status + f0 : B.d_status;
+    if (B.pending) AG_CUDA(det, cudaStreamWaitEvent(s, B.ev_boards, 0));
+    if ((rc = run_dense(det, D, in, g, n, true, s))) return rc;
+    if ((rc = run_sparse(det, D, B, g, n, st, s))) return rc;
+    AG_CUDA(det, cudaEventRecord(B.ev_front, s));
+    AG_CUDA(det, cudaStreamWaitEvent(B.bstream, B.ev_front, 0));
+    if ((rc = run_boards(det, B, in, g, n, d_out + (size_t)f0 * cap_per_frame, cap_per_frame,
+                         d_n_per_frame + f0, st, false, B.bstream)))
       return rc;
-    AG_CUDA(det, cudaEventRecord(S.ev_boards, S.bstream));
-    S.boards_pending = true;
+    AG_CUDA(det, cudaEventRecord(B.ev_boards, B.bstream));
+    B.pending = true;
   }
+  AG_CUDA(det, cudaEventRecord(D.done, s));
+  det->device_path_busy = true;
   // results become visible in the caller's stream order (unless the caller asked to do that
   // itself with ag_detect_batch_device_wait, which lets consecutive calls overlap)
   if (!det->device_async)
-    for (auto& S : det->slot)
-      if (S.boards_pending) AG_CUDA(det, cudaStreamWaitEvent(s, S.ev_boards, 0));
+    for (auto& B : det->bslot)
+      if (B.pending) AG_CUDA(det, cudaStreamWaitEvent(s, B.ev_boards, 0));
   return AG_OK;
 }
 
@@ -623,10 +685,10 @@ int ag_detect_batch_device_wait(ag_detector* det, void* stream) {
   if (!det) return AG_ERR_INVALID;
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
-  for (auto& S : det->slot) {
-    if (!S.boards_pending) continue;
-    if (stream) AG_CUDA(det, cudaStreamWaitEvent((cudaStream_t)stream, S.ev_boards, 0));
-    else AG_CUDA(det, cudaEventSynchronize(S.ev_boards));
+  for (auto& B : det->bslot) {
+    if (!B.pending) continue;
+    if (stream) AG_CUDA(det, cudaStreamWaitEvent((cudaStream_t)stream, B.ev_boards, 0));
+    else AG_CUDA(det, cudaEventSynchronize(B.ev_boards));
   }
   return AG_OK;
 }
@@ -637,12 +699,13 @@ int ag_dense_batch_device(ag_detector* det, const void* d_frames, size_t frame_s
   if (!d_frames || n_frames < 0) return fail(det, AG_ERR_INVALID, "null pointer or bad count");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
+  { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
   Slot& S = det->slot[0];
   const int chunk = (int)std::min<long>(det->chunk_frames, std::max(n_frames, 1));
-  if ((rc = ensure_slot(det, S, g, chunk, 1, false))) return rc;
+  if ((rc = ensure_slot(det, S, g, chunk, 1, false, false))) return rc;
   cudaStream_t s = stream ? (cudaStream_t)stream : S.stream;
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
     const int n = std::min(chunk, n_frames - f0);
@@ -660,6 +723,7 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
     return fail(det, AG_ERR_INVALID, "null pointer or bad count");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
+  { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
@@ -727,6 +791,7 @@ int ag_stage_run(ag_detector* det, const void* pixels, int width, int height, si
   if (!pixels) return fail(det, AG_ERR_INVALID, "pixels is null");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
+  { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
   det->tap_valid = false;
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, 0, format, &g);
@@ -806,10 +871,10 @@ int ag_stage_saddles(ag_detector* det, int which, ag_saddle* out, int cap, int* 
   AG_TAP_PROLOGUE();
   if (which == 1) {
     int cnt = 0;
-    AG_CUDA(det, cudaMemcpy(&cnt, S.d_nref, sizeof(int), cudaMemcpyDeviceToHost));
+    AG_CUDA(det, cudaMemcpy(&cnt, S.bb.d_nref, sizeof(int), cudaMemcpyDeviceToHost));
     *n = cnt;
     int m = std::min(cnt, cap);
-    if (m > 0) AG_CUDA(det, cudaMemcpy(out, S.d_refined, sizeof(ag_saddle) * m, cudaMemcpyDeviceToHost));
+    if (m > 0) AG_CUDA(det, cudaMemcpy(out, S.bb.d_refined, sizeof(ag_saddle) * m, cudaMemcpyDeviceToHost));
     return AG_OK;
   }
   int ncl = 0;
@@ -832,10 +897,10 @@ int ag_stage_saddles(ag_detector* det, int which, ag_saddle* out, int cap, int* 
 int ag_stage_board_quads(ag_detector* det, int32_t* quads_out, int cap, int* n) {
   AG_TAP_PROLOGUE();
   int cnt = 0;
-  AG_CUDA(det, cudaMemcpy(&cnt, S.d_tap_nquads, sizeof(int), cudaMemcpyDeviceToHost));
+  AG_CUDA(det, cudaMemcpy(&cnt, S.bb.d_tap_nquads, sizeof(int), cudaMemcpyDeviceToHost));
   *n = cnt;
-  int m = std::min(std::min(cnt, cap), S.layout.max_quads);
-  if (m > 0) AG_CUDA(det, cudaMemcpy(quads_out, S.d_tap_quads, sizeof(int32_t) * 4 * m, cudaMemcpyDeviceToHost));
+  int m = std::min(std::min(cnt, cap), S.bb.layout.max_quads);
+  if (m > 0) AG_CUDA(det, cudaMemcpy(quads_out, S.bb.d_tap_quads, sizeof(int32_t) * 4 * m, cudaMemcpyDeviceToHost));
   return AG_OK;
 }
 int ag_stage_tags(ag_detector* det, ag_tag* out, int cap, int* n) {
@@ -854,6 +919,7 @@ int ag_refined_saddle_points(ag_detector* det, const void* pixels, int width, in
   if (!pixels || !out || !n) return fail(det, AG_ERR_INVALID, "null pointer");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
+  { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
   det->tap_valid = false;
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, 0, format, &g);
@@ -863,13 +929,13 @@ int ag_refined_saddle_points(ag_detector* det, const void* pixels, int width, in
   const size_t bytes = g.row_stride * (size_t)(g.h - 1) + (size_t)g.w * bytes_per_px(g.format);
   AG_CUDA(det, cudaMemcpyAsync(S.d_in, pixels, bytes, cudaMemcpyHostToDevice, S.stream));
   if ((rc = run_dense(det, S, S.d_in, g, 1, true, S.stream))) return rc;
-  if ((rc = run_sparse(det, S, g, 1, S.d_status, S.stream))) return rc;
+  if ((rc = run_sparse(det, S, S.bb, g, 1, S.d_status, S.stream))) return rc;
   int cnt = 0;
-  AG_CUDA(det, cudaMemcpyAsync(&cnt, S.d_nref, sizeof(int), cudaMemcpyDeviceToHost, S.stream));
+  AG_CUDA(det, cudaMemcpyAsync(&cnt, S.bb.d_nref, sizeof(int), cudaMemcpyDeviceToHost, S.stream));
   AG_CUDA(det, cudaStreamSynchronize(S.stream));
   *n = cnt;
   int m = std::min(cnt, cap);
-  if (m > 0) AG_CUDA(det, cudaMemcpy(out, S.d_refined, sizeof(ag_saddle) * m, cudaMemcpyDeviceToHost));
+  if (m > 0) AG_CUDA(det, cudaMemcpy(out, S.bb.d_refined, sizeof(ag_saddle) * m, cudaMemcpyDeviceToHost));
   return cnt > cap ? fail(det, AG_ERR_CAPACITY, "saddle capacity too small") : AG_OK;
 }
 
@@ -907,6 +973,7 @@ int ag_gaussian_blur_f32(ag_detector* det, const float* img, int width, int heig
   }
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
+  { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
   const size_t n = (size_t)width * height;
   int rc = ensure_f32(det, n);
   if (rc) return rc;
@@ -931,6 +998,7 @@ int ag_hessian_response(ag_detector* det, const float* img, int width, int heigh
   if (!img || !out || width <= 0 || height <= 0) return fail(det, AG_ERR_INVALID, "bad argument");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
+  { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
   const size_t n = (size_t)width * height;
   int rc = ensure_f32(det, n);
   if (rc) return rc;
@@ -970,10 +1038,10 @@ int ag_render_boards_device(ag_detector* det, void* d_frames, int n_frames, int 
 // Profiling hook (not in the public header): per-frame timing taps of the last board-kernel launch
 // on pipeline slot `slot` (needs ag_set_option("board_timing", 1)); out = n_frames x 16 u32.
 AG_API int ag_test_board_times(ag_detector* det, int slot, uint32_t* out, int n_frames) {
-  if (!det || slot < 0 || slot > 1 || !out) return AG_ERR_INVALID;
+  if (!det || slot < 0 || slot >= kBoardSlots || !out) return AG_ERR_INVALID;
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
-  Slot& S = det->slot[slot];
+  BoardSlot& S = det->bslot[slot];
   if (!S.d_board_tm || n_frames > S.cap_frames) return fail(det, AG_ERR_INVALID, "no timing data");
   AG_CUDA(det, cudaDeviceSynchronize());
   AG_CUDA(det, cudaMemcpy(out, S.d_board_tm, sizeof(uint32_t) * 16 * (size_t)n_frames, cudaMemcpyDeviceToHost));
