@@ -27,6 +27,10 @@
 #define AGB_DEVICE 0
 #endif
 
+#if !defined(__CUDACC__)
+struct float2 { float x, y; };  // host test build: the CUDA vector type is not available
+#endif
+
 #if defined(__CUDACC__)
 #define AGB_FN __host__ __device__ inline
 #define AGB_NOINLINE __host__ __device__ __noinline__
@@ -213,9 +217,33 @@ AGB_FN float angle_degree_fast(float ax, float ay, float bx, float by) {
   float x = fadd(fmul(ax, bx), fmul(ay, by));
   return atan2f(y, x) * 57.2957795f;
 }
-// |angle(a) - angle(b)| > limit ?  with a = angle(p, q), b = angle(r, s)
+// Margin, in the units of a quantity m = A - B (both ~ a product of two vector lengths), that
+// covers kGuardDeg of angle plus f32 rounding of the products: |dm / d angle| <= 1.02 * scale
+// per radian for the tests below, kGuardDeg = 7e-5 rad.
+constexpr float kGuardRel = 1.2e-4f;
+// |angle(a) - angle(b)| > limit ?  with a = angle(p, q), b = angle(r, s);  limit = 10 degrees.
 AGB_NOINLINE bool angle_gap_exceeds(float px, float py, float qx, float qy, float rx, float ry,
                                     float sx, float sy, float limit) {
+  {
+    // Trigonometry-free decision.  a = atan2(y1, x1), b = atan2(y2, x2).  When y1 and y2 have the
+    // same strict sign both angles lie in the same open half turn, so a - b = atan2(Y, X) with
+    // Y = y1 x2 - x1 y2, X = x1 x2 + y1 y2, and |a - b| <= limit  <=>  |Y| <= tan(limit) X.
+    // Away from the threshold (margin: guard band + rounding) the verdict is certain.
+    const float y1 = py * qx - px * qy, x1 = px * qx + py * qy;  // atan2 arguments of angle_degree(p, q)
+    const float y2 = ry * sx - rx * sy, x2 = rx * sx + ry * sy;
+    if ((y1 > 0.0f && y2 > 0.0f) || (y1 < 0.0f && y2 < 0.0f)) {
+      const float a1 = y1 * x2, a2 = x1 * y2, b1 = x1 * x2, b2 = y1 * y2;
+      const float Y = a1 - a2, X = b1 + b2;
+      const float kTan10 = 0.17632698f;
+      const float m = fabsf(Y) - kTan10 * X;
+      const float scale = fabsf(a1) + fabsf(a2) + fabsf(b1) + fabsf(b2);
+      const float margin = (kGuardRel + 4.0e-7f) * scale;
+      if (limit == 10.0f && scale < 1.0e30f && scale > 1.0e-30f) {
+        if (m > margin) return true;
+        if (m < -margin) return false;
+      }
+    }
+  }
   const float fa = angle_degree_fast(px, py, qx, qy), fb = angle_degree_fast(rx, ry, sx, sy);
   const float g = fabsf(fa - fb);
   if (g > limit + kGuardDeg) return true;
@@ -227,6 +255,24 @@ AGB_NOINLINE bool angle_gap_exceeds(float px, float py, float qx, float qy, floa
 AGB_NOINLINE bool quad_diag_ok(const Frame& F, int s0, int s1) {  // "filter white block", :26-38
   float v02x = fsub(F.sx[s1], F.sx[s0]), v02y = fsub(F.sy[s1], F.sy[s0]);
   float th = fmul(fdiv(F.st[s0], 180.0f), kPi);
+  {
+    // |angle(v02, u)| in [60, 120] degrees  <=>  sqrt(3) |dot| <= |cross|  (u = unit vector of
+    // theta); decided without atan2 away from the two thresholds.
+#if AGB_DEVICE
+    const float ux = __cosf(th), uy = __sinf(th);  // |th| <= pi: absolute error ~ 1e-6
+#else
+    const float ux = cosf(th), uy = sinf(th);
+#endif
+    const float a1 = uy * v02x, a2 = ux * v02y, b1 = v02x * ux, b2 = v02y * uy;
+    const float cr = a1 - a2, dt = b1 + b2;
+    const float m = 1.7320508f * fabsf(dt) - fabsf(cr);
+    const float scale = fabsf(a1) + fabsf(a2) + fabsf(b1) + fabsf(b2);
+    const float margin = (2.0f * kGuardRel + 4.0e-6f) * scale;
+    if (scale < 1.0e30f && scale > 1.0e-30f && fabsf(th) <= 3.2f) {
+      if (m < -margin) return true;
+      if (m > margin) return false;
+    }
+  }
   {
     const float fa = fabsf(angle_degree_fast(v02x, v02y, cosf(th), sinf(th)));
     if (fa > 60.0f + kGuardDeg && fa < 120.0f - kGuardDeg) return true;
