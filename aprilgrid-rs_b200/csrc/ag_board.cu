@@ -197,10 +197,8 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.fx_qlist = (int16_t*)(SW + L.smw_qlist);
   F.fx_qscore = (uint16_t*)(SW + L.smw_qscore);
   F.fx_dvx = (float*)(SW + L.smw_fvec);
-  F.fx_dvy = F.fx_dvx + 64;
-  F.fx_dth = F.fx_dvy + 64;
-  F.fx_dc = F.fx_dth + 64;
-  F.fx_elig = SW + L.smw_elig;
+  F.fx_dvy = F.fx_dvx + agb::kDiffCap;
+  F.fx_tmask = (unsigned long long*)(F.fx_dvy + agb::kDiffCap);  // 416 bytes in: 8-byte aligned
   F.fx_squeue = (uint32_t*)(SW + L.smw_squeue);
   F.fx_gstate = SW + L.smw_cell;
   F.fx_wscore = (uint16_t*)(smem + L.sm_wave);

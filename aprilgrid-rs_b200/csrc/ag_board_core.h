@@ -127,8 +127,8 @@ struct Frame {
   int active_words;      // words of bs.active
   int16_t* fx_qlist;     // [kQListCap][4] candidate quads of the current seed
   uint16_t* fx_qscore;   // [kQListCap]
-  float *fx_dvx, *fx_dvy, *fx_dth, *fx_dc;  // [64] per `diff` entry
-  uint8_t* fx_elig;      // [64]
+  float *fx_dvx, *fx_dvy;  // [52] per `diff` entry: vector from the seed
+  unsigned long long* fx_tmask;  // [52] per `diff` entry i: partners j > i passing the theta gate
   uint32_t* fx_squeue;   // [64] ring of pairs that passed the cheap gates
   uint8_t* fx_gstate;    // this warp's group states (aliases bs.cell)
   uint16_t* fx_wscore;   // [32] per wave slot: best score of the seed so far

@@ -38,6 +38,7 @@ constexpr int kGOffCell = 0;        // u8 [256]: 0 unvisited, 0xff None, q + 1 S
 constexpr int kGOffQuads = 256;     // i16 [64][4]
 constexpr int kGOffStack = 768;     // u16 [64]: cell | next direction << 8
 constexpr int kGOffActive = 896;    // u32 [16]: 512 saddles
+constexpr int kDiffCap = 52;        // `diff` / `same` entries of a seed: at most 49 (50-NN minus the seed)
 
 }  // namespace agb
 
@@ -417,21 +418,13 @@ struct SeedEnum {
   int s0, n_same, n_diff;
   unsigned diag_ok[2];  // bit a: quad_diag_ok(s0, same[a])
   int a;                // `same` entry being expanded (-1 before the first)
-  int m, n_pairs, pbase;
+  bool a_open;          // cand[] holds pairs of entry a that are not queued yet
+  // PER LANE: for diff entry i = lane (cand[0]) / lane + 32 (cand[1]), the partners j > i that
+  // passed the cheap gates and still have to be queued
+  unsigned long long cand[2];
   int q_head, q_n;      // ring of cheap-gate survivors
   bool exhausted;
 };
-
-// (p, q), p < q, of the c-th pair of m items in lexicographic order
-__device__ __forceinline__ void unrank_pair_fast(int c, int m, int* p, int* q) {
-  const float tm = (float)(2 * m - 1);
-  int a = (int)((tm - sqrtf(tm * tm - 8.0f * (float)c)) * 0.5f);
-  a = a < 0 ? 0 : (a > m - 2 ? m - 2 : a);
-  while (a > 0 && a * (2 * m - a - 1) / 2 > c) --a;
-  while ((a + 1) * (2 * m - a - 2) / 2 <= c) ++a;
-  *p = a;
-  *q = a + 1 + (c - a * (2 * m - a - 1) / 2);
-}
 
 // The k (<= 64) nearest saddles of a point for n <= 512 saddles, ascending by (d2, index), into
 // F.nn_idx -- same result as nearest_k (kdtree `nearest`, ties -> lower index).  Every lane keeps
@@ -506,7 +499,7 @@ __device__ __noinline__ int nearest_k_fast(Frame& F, float qx, float qy, int k, 
 // 50-NN of the seed, same / diff classification (detector.rs:550-563), per-diff vectors.
 __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
   E.s0 = s0;
-  // fx_dvx .. fx_dc (1 KB, contiguous) are free until the classification below fills them
+  // the 1 KB at fx_dvx (dvx, dvy, tmask) is free until the classification below fills it
   int n_nn = nearest_k_fast(F, F.sx[s0], F.sy[s0], 50, (unsigned long long*)F.fx_dvx);
   if (n_nn < 0) n_nn = nearest_k(F, F.sx[s0], F.sy[s0], 50);
   const float t0 = F.st[s0], x0 = F.sx[s0], y0 = F.sy[s0];
@@ -529,7 +522,6 @@ __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
       F.diff[d] = (int16_t)si;
       F.fx_dvx[d] = fsub(F.sx[si], x0);
       F.fx_dvy[d] = fsub(F.sy[si], y0);
-      F.fx_dth[d] = F.st[si];
     }
     n_same += __popc(ms);
     n_diff += __popc(md);
@@ -543,8 +535,22 @@ __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
     const bool ok = a < n_same && quad_diag_ok(F, s0, F.same[a]);
     E.diag_ok[blk & 1] = __ballot_sync(0xffffffffu, ok);
   }
+  // theta gate of is_valid_quad (saddle.rs:21-24) for every pair (i < j) of diff entries: it does
+  // not depend on s1, so it is evaluated once per seed.  tmask[i] bit j = pair (i, j) passes.
+  for (int base = 0; base < n_diff; base += 32) {
+    const int i = base + F.lane;
+    if (i < n_diff) {
+      const float ti = F.st[F.diff[i]];
+      unsigned long long m = 0ull;
+      for (int j = i + 1; j < n_diff; ++j)
+        if (!(theta_distance_degree(ti, F.st[F.diff[j]]) > 5.0f)) m |= 1ull << j;
+      F.fx_tmask[i] = m;
+    }
+  }
+  __syncwarp();
   E.a = -1;
-  E.m = E.n_pairs = E.pbase = 0;
+  E.a_open = false;
+  E.cand[0] = E.cand[1] = 0ull;
   E.q_head = E.q_n = 0;
   E.exhausted = n_diff < 2;
 }
@@ -585,7 +591,7 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
       continue;
     }
     if (E.exhausted) return true;
-    if (E.pbase >= E.n_pairs) {
+    if (!E.a_open) {
       // next `same` entry that passes the (s0, s1)-only gate
       int a = E.a + 1;
       while (a < E.n_same && !((E.diag_ok[a >> 5] >> (a & 31)) & 1u)) ++a;
@@ -596,46 +602,72 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
       }
       const int s1 = F.same[a];
       const float v02x = fsub(F.sx[s1], x0), v02y = fsub(F.sy[s1], y0);
-      // per diff entry: side of the diagonal (cross) and the dot gate (saddle.rs:40-45, :55-59)
-      int m = 0;
-      __syncwarp();
+      // Per diff entry d: c = cross(v0d, v02) (side of the diagonal s0 -> s1) and the dot gate
+      // (saddle.rs:55-59).  The side gate (:40-45) rejects a pair iff c0 * c1 < 0 with
+      // c0 = cross(v01, v02) = c[i] and c1 = cross(v02, v03) = -c[j] exactly (the products commute,
+      // x - y = -(y - x)), i.e. iff c[i] * c[j] > 0.  Pairs whose c have the same sign and are far
+      // from underflowing the product are dropped here; everything else is re-checked exactly by
+      // quad_rest_ok, so the prefilter can only pass too much, never too little.
+      unsigned long long el = 0ull, pos = 0ull, neg = 0ull;
       for (int base = 0; base < E.n_diff; base += 32) {
         const int d = base + F.lane;
-        bool el = false;
+        bool e = false, ps = false, ng = false;
         if (d < E.n_diff) {
           const float vx = F.fx_dvx[d], vy = F.fx_dvy[d];
-          F.fx_dc[d] = cross2(vx, vy, v02x, v02y);
-          el = !(dot2(vx, vy, v02x, v02y) < 0.0f);
+          const float c = cross2(vx, vy, v02x, v02y);
+          e = !(dot2(vx, vy, v02x, v02y) < 0.0f);
+          ps = c > 1.0e-18f;
+          ng = c < -1.0e-18f;
         }
-        const unsigned me = __ballot_sync(0xffffffffu, el);
-        if (el) F.fx_elig[m + __popc(me & lt)] = (uint8_t)d;
-        m += __popc(me);
+        el |= (unsigned long long)__ballot_sync(0xffffffffu, e) << base;
+        pos |= (unsigned long long)__ballot_sync(0xffffffffu, ps) << base;
+        neg |= (unsigned long long)__ballot_sync(0xffffffffu, ng) << base;
       }
-      __syncwarp();
-      E.m = m;
-      E.n_pairs = m * (m - 1) / 2;
-      E.pbase = 0;
-      continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = F.lane + 32 * h;
+        unsigned long long m = 0ull;
+        if (i < E.n_diff && ((el >> i) & 1ull)) {
+          const unsigned long long same_side = ((pos >> i) & 1ull) ? pos : (((neg >> i) & 1ull) ? neg : 0ull);
+          m = F.fx_tmask[i] & el & ~same_side;
+        }
+        E.cand[h] = m;
+      }
+      E.a_open = true;
     }
-    // cheap gates on the next 32 pairs (lexicographic over the eligible diff entries)
+    // queue the open entry's pairs in combinations(2) order (i ascending, then j ascending), as
+    // many as the ring holds
     {
-      const int c = E.pbase + F.lane;
-      bool pass = false;
-      unsigned entry = 0;
-      if (c < E.n_pairs) {
-        int p, q;
-        unrank_pair_fast(c, E.m, &p, &q);
-        const int i = F.fx_elig[p], j = F.fx_elig[q];
-        // saddle.rs:21-24 (theta of d0 vs d1) and :40-45: c0 * c1 < 0 with c0 = cross(v01, v02) =
-        // dc[i] and c1 = cross(v02, v03) = -dc[j] exactly (the products commute, x - y = -(y - x))
-        pass = !(theta_distance_degree(F.fx_dth[i], F.fx_dth[j]) > 5.0f) &&
-               !(fmul(F.fx_dc[i], -F.fx_dc[j]) < 0.0f);
-        entry = (unsigned)E.a | ((unsigned)i << 8) | ((unsigned)j << 16);
+      int space = 64 - E.q_n;
+      bool left = false;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        unsigned long long m = E.cand[h];
+        const int cnt = __popcll(m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (F.lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int pos_q = incl - cnt;  // position of this lane's first pair among the half's pairs
+        const int i = F.lane + 32 * h;
+        while (m != 0ull && pos_q < space) {
+          const int j = __ffsll((long long)m) - 1;
+          m &= m - 1ull;
+          F.fx_squeue[(E.q_head + E.q_n + pos_q) & 63] = (unsigned)E.a | ((unsigned)i << 8) | ((unsigned)j << 16);
+          ++pos_q;
+        }
+        E.cand[h] = m;
+        const int put = total < space ? total : space;
+        E.q_n += put;
+        space -= put;
+        left |= __any_sync(0xffffffffu, m != 0ull);
+        if (left) break;  // the second half must wait until the first is queued completely
       }
-      const unsigned mp = __ballot_sync(0xffffffffu, pass);
-      if (pass) F.fx_squeue[(E.q_head + E.q_n + __popc(mp & lt)) & 63] = entry;
-      E.q_n += __popc(mp);
-      E.pbase += 32;
+      if (!left) left = __any_sync(0xffffffffu, E.cand[1] != 0ull);
+      E.a_open = left;
       __syncwarp();
     }
   }
