@@ -161,11 +161,22 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
       }
     }
     const float bsz = 1.0f / F.g_inv;  // bucket side, a power of two: bucket indices are exact
-    int e = 0, e1 = 0;
-    for (;;) {
-      if (e >= e1 && t < t_end) {  // step to the next row of the window (one row per iteration)
+    // shared-memory addresses of the grid arrays (32-bit, LDS instead of generic loads)
+    const unsigned a_start = (unsigned)__cvta_generic_to_shared(F.g_start);
+    const unsigned a_pos = (unsigned)__cvta_generic_to_shared(F.g_pos);
+    const unsigned a_item = (unsigned)__cvta_generic_to_shared(F.g_item);
+    auto lds_u16 = [](unsigned addr) -> int {
+      unsigned short v;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+      return (int)v;
+    };
+    // Outer loop: row offset t is the same for every lane (each lane's rows are counted from its own
+    // query row), so the row set-up is executed once per t for the whole warp; inner loop: one
+    // candidate per lane and iteration.
+    for (; __any_sync(full, t < t_end); ++t) {
+      int e = 0, e1 = 0;
+      if (t < t_end) {
         const int j = (t + 1) >> 1, yy = (t & 1) ? cy - j : cy + j;
-        ++t;
         if (yy >= y0 && yy <= y1) {
           float R = r;
           bool row_ok = true;
@@ -173,7 +184,7 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
             const float d3 = __uint_as_float((unsigned)(k2 >> 32));
             const float lb = (float)(j > 0 ? j - 1 : 0) * bsz;  // every saddle of the row is farther than this
             if (lb * lb * 0.9999f > d3) {                        // ... and so are the remaining rows
-              t = t_end;
+              t_end = 0;
               row_ok = false;
             }
             R = fminf(r, sqrtf(d3) * 1.0001f + 0.01f);
@@ -184,20 +195,22 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
             bx1 = bx1 > x1 ? x1 : bx1;
             if (bx0 <= bx1) {
               const int b0 = yy * F.g_nx;
-              e = F.g_start[b0 + bx0];
-              e1 = F.g_start[b0 + bx1 + 1];
+              e = lds_u16(a_start + 2u * (unsigned)(b0 + bx0));
+              e1 = lds_u16(a_start + 2u * (unsigned)(b0 + bx1 + 1));
             }
           }
         }
       }
-      if (e < e1) {
-        const float2 p = F.g_pos[e];
-        const float ddx = fsub(qx, p.x), ddy = fsub(qy, p.y);  // dist2(): (0 + dx*dx) + dy*dy
-        const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
-        if (d <= r2) insert(d, F.g_item[e]);
-        ++e;
+      while (__any_sync(full, e < e1)) {
+        if (e < e1) {
+          float px_, py_;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(px_), "=f"(py_) : "r"(a_pos + 8u * (unsigned)e));
+          const float ddx = fsub(qx, px_), ddy = fsub(qy, py_);  // dist2(): (0 + dx*dx) + dy*dy
+          const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
+          if (d <= r2) insert(d, lds_u16(a_item + 2u * (unsigned)e));
+          ++e;
+        }
       }
-      if (!__any_sync(full, e < e1 || t < t_end)) break;
     }
     if (on && !windowed)  // degenerate radius (NaN / huge): exhaustive
       for (int i = 0; i < F.n; ++i) {
