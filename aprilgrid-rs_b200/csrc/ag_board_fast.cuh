@@ -173,31 +173,33 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
     // Outer loop: row offset t is the same for every lane (each lane's rows are counted from its own
     // query row), so the row set-up is executed once per t for the whole warp; inner loop: one
     // candidate per lane and iteration.
+    // column range and row cut-off for the current third-best distance; recomputed only when the
+    // third-best candidate changes (sqrt / floor are the expensive part of the row set-up)
+    unsigned long long k2_seen = kInf;
+    int bx0 = x0, bx1 = x1;
+    float stop_d3 = 3.0e38f;  // rows whose lower bound lb satisfies lb^2 * 0.9999 > stop_d3 end the search
     for (; __any_sync(full, t < t_end); ++t) {
       int e = 0, e1 = 0;
       if (t < t_end) {
         const int j = (t + 1) >> 1, yy = (t & 1) ? cy - j : cy + j;
         if (yy >= y0 && yy <= y1) {
-          float R = r;
-          bool row_ok = true;
-          if (k2 != kInf) {
+          if (k2 != k2_seen) {
+            k2_seen = k2;
             const float d3 = __uint_as_float((unsigned)(k2 >> 32));
-            const float lb = (float)(j > 0 ? j - 1 : 0) * bsz;  // every saddle of the row is farther than this
-            if (lb * lb * 0.9999f > d3) {                        // ... and so are the remaining rows
-              t_end = 0;
-              row_ok = false;
-            }
-            R = fminf(r, sqrtf(d3) * 1.0001f + 0.01f);
-          }
-          if (row_ok) {
-            int bx0 = (int)floorf((qx - R) * F.g_inv), bx1 = (int)floorf((qx + R) * F.g_inv);
+            stop_d3 = d3;
+            const float R = fminf(r, sqrtf(d3) * 1.0001f + 0.01f);
+            bx0 = (int)floorf((qx - R) * F.g_inv);
+            bx1 = (int)floorf((qx + R) * F.g_inv);
             bx0 = bx0 < x0 ? x0 : bx0;
             bx1 = bx1 > x1 ? x1 : bx1;
-            if (bx0 <= bx1) {
-              const int b0 = yy * F.g_nx;
-              e = lds_u16(a_start + 2u * (unsigned)(b0 + bx0));
-              e1 = lds_u16(a_start + 2u * (unsigned)(b0 + bx1 + 1));
-            }
+          }
+          const float lb = (float)(j > 0 ? j - 1 : 0) * bsz;  // every saddle of the row is farther than this
+          if (lb * lb * 0.9999f > stop_d3) {                   // ... and so are the remaining rows
+            t_end = 0;
+          } else if (bx0 <= bx1) {
+            const int b0 = yy * F.g_nx;
+            e = lds_u16(a_start + 2u * (unsigned)(b0 + bx0));
+            e1 = lds_u16(a_start + 2u * (unsigned)(b0 + bx1 + 1));
           }
         }
       }
