@@ -652,8 +652,8 @@ int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_
   cudaStream_t s = stream ? (cudaStream_t)stream : D.stream;
   // all board slots are sized up front: an allocation (which synchronises the device) must not
   // happen in the middle of a streaming sequence of calls
-  for (int i = 0; i < std::min(kBoardSlots, std::max(2, 2 * ((n_frames + chunk - 1) / chunk))); ++i)
-    if ((rc = ensure_board_slot(det, det->bslot[i], chunk, false))) return rc;
+  for (auto& B : det->bslot)
+    if ((rc = ensure_board_slot(det, B, chunk, false))) return rc;
   // the dense buffers are shared by every device-batch call: order this call after the front end
   // of the previous one even if the caller switched streams
   if (det->device_path_busy) AG_CUDA(det, cudaStreamWaitEvent(s, D.done, 0));
