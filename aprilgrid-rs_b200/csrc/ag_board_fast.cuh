@@ -171,48 +171,64 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
       return (int)v;
     };
     // Outer loop: row offset t is the same for every lane (each lane's rows are counted from its own
-    // query row), so the row set-up is executed once per t for the whole warp; inner loop: one
-    // candidate per lane and iteration.
-    // column range and row cut-off for the current third-best distance; recomputed only when the
-    // third-best candidate changes (sqrt / floor are the expensive part of the row set-up)
+    // query row), so the row set-up is executed once per t for the whole warp; it is issued one
+    // row AHEAD (its shared-memory loads overlap the candidate loop of the current row; the bounds
+    // it uses are those known before the current row, i.e. only looser).  Inner loop: two
+    // candidates per lane and iteration.
+    // Column range and row cut-off follow the third-best distance; they are recomputed only when
+    // the third-best candidate changes (sqrt / floor are the expensive part of the row set-up).
     unsigned long long k2_seen = kInf;
     int bx0 = x0, bx1 = x1;
-    float stop_d3 = 3.0e38f;  // rows whose lower bound lb satisfies lb^2 * 0.9999 > stop_d3 end the search
-    for (; __any_sync(full, t < t_end); ++t) {
-      int e = 0, e1 = 0;
-      if (t < t_end) {
-        const int j = (t + 1) >> 1, yy = (t & 1) ? cy - j : cy + j;
-        if (yy >= y0 && yy <= y1) {
-          if (k2 != k2_seen) {
-            k2_seen = k2;
-            const float d3 = __uint_as_float((unsigned)(k2 >> 32));
-            stop_d3 = d3;
-            const float R = fminf(r, sqrtf(d3) * 1.0001f + 0.01f);
-            bx0 = (int)floorf((qx - R) * F.g_inv);
-            bx1 = (int)floorf((qx + R) * F.g_inv);
-            bx0 = bx0 < x0 ? x0 : bx0;
-            bx1 = bx1 > x1 ? x1 : bx1;
-          }
-          const float lb = (float)(j > 0 ? j - 1 : 0) * bsz;  // every saddle of the row is farther than this
-          if (lb * lb * 0.9999f > stop_d3) {                   // ... and so are the remaining rows
-            t_end = 0;
-          } else if (bx0 <= bx1) {
-            const int b0 = yy * F.g_nx;
-            e = lds_u16(a_start + 2u * (unsigned)(b0 + bx0));
-            e1 = lds_u16(a_start + 2u * (unsigned)(b0 + bx1 + 1));
-          }
-        }
+    float stop_d3 = 3.0e38f;  // a row whose lower bound lb has lb^2 * 0.9999 > stop_d3 ends the search
+    auto row_setup = [&](int tt, int& re, int& re1) {
+      re = re1 = 0;
+      if (tt >= t_end) return;
+      const int j = (tt + 1) >> 1, yy = (tt & 1) ? cy - j : cy + j;
+      if (yy < y0 || yy > y1) return;
+      if (k2 != k2_seen) {
+        k2_seen = k2;
+        const float d3 = __uint_as_float((unsigned)(k2 >> 32));
+        stop_d3 = d3;
+        const float R = fminf(r, sqrtf(d3) * 1.0001f + 0.01f);
+        bx0 = (int)floorf((qx - R) * F.g_inv);
+        bx1 = (int)floorf((qx + R) * F.g_inv);
+        bx0 = bx0 < x0 ? x0 : bx0;
+        bx1 = bx1 > x1 ? x1 : bx1;
       }
+      const float lb = (float)(j > 0 ? j - 1 : 0) * bsz;  // every saddle of the row is farther than this
+      if (lb * lb * 0.9999f > stop_d3) {                   // ... and so are the remaining rows
+        t_end = 0;
+      } else if (bx0 <= bx1) {
+        const int b0 = yy * F.g_nx;
+        re = lds_u16(a_start + 2u * (unsigned)(b0 + bx0));
+        re1 = lds_u16(a_start + 2u * (unsigned)(b0 + bx1 + 1));
+      }
+    };
+    int e = 0, e1 = 0;
+    row_setup(0, e, e1);
+    t = 1;
+    while (__any_sync(full, e < e1 || t < t_end)) {
+      int ne, ne1;
+      row_setup(t, ne, ne1);
+      ++t;
       while (__any_sync(full, e < e1)) {
         if (e < e1) {
-          float px_, py_;
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(px_), "=f"(py_) : "r"(a_pos + 8u * (unsigned)e));
-          const float ddx = fsub(qx, px_), ddy = fsub(qy, py_);  // dist2(): (0 + dx*dx) + dy*dy
-          const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
-          if (d <= r2) insert(d, lds_u16(a_item + 2u * (unsigned)e));
-          ++e;
+          const bool two = e + 1 < e1;
+          const unsigned ea = a_pos + 8u * (unsigned)e, eb = two ? ea + 8u : ea;
+          float pax, pay, pbx, pby;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pax), "=f"(pay) : "r"(ea));
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pbx), "=f"(pby) : "r"(eb));
+          const float dax = fsub(qx, pax), day = fsub(qy, pay);  // dist2(): (0 + dx*dx) + dy*dy
+          const float dbx = fsub(qx, pbx), dby = fsub(qy, pby);
+          const float da = fadd(fmul(dax, dax), fmul(day, day));
+          const float db = fadd(fmul(dbx, dbx), fmul(dby, dby));
+          if (da <= r2) insert(da, lds_u16(a_item + 2u * (unsigned)e));
+          if (two && db <= r2) insert(db, lds_u16(a_item + 2u * (unsigned)(e + 1)));
+          e += 2;
         }
       }
+      e = ne;
+      e1 = ne1;
     }
     if (on && !windowed)  // degenerate radius (NaN / huge): exhaustive
       for (int i = 0; i < F.n; ++i) {
