@@ -126,12 +126,15 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
   const unsigned full = 0xffffffffu;
   const unsigned long long kInf = ~0ull;
   unsigned long long k0 = kInf, k1 = kInf, k2 = kInf;
+  float d3f = 3.4e38f;  // distance of the current third-best candidate (cheap first reject)
   auto insert = [&](float d, int i) {
+    if (d > d3f) return;
     const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
     if (k < k2) {
       k2 = k;
       if (k2 < k1) { const unsigned long long t = k1; k1 = k2; k2 = t; }
       if (k1 < k0) { const unsigned long long t = k0; k0 = k1; k1 = t; }
+      if (k2 != kInf) d3f = __uint_as_float((unsigned)(k2 >> 32));
     }
   };
   float qx = 0.0f, qy = 0.0f, r2 = -1.0f, r = 0.0f;
