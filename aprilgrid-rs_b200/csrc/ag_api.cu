@@ -198,7 +198,11 @@ int regrow(ag_detector* det, T** p, size_t count) {
 int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
   int rc;
   if (!B.bstream) {
-    AG_CUDA(det, cudaStreamCreateWithFlags(&B.bstream, cudaStreamNonBlocking));
+    // lowest priority: the long-lived board-search blocks must not keep the bandwidth-bound
+    // front end of the following chunks (caller's stream, default priority) off the SMs
+    int prio_least = 0, prio_greatest = 0;
+    AG_CUDA(det, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    AG_CUDA(det, cudaStreamCreateWithPriority(&B.bstream, cudaStreamNonBlocking, prio_least));
     AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_front, cudaEventDisableTiming));
     AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_boards, cudaEventDisableTiming));
   }
