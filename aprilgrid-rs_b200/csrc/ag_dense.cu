@@ -169,7 +169,7 @@ struct BlurRow {  // one blurred row: v[1..4] = the lane's 4 columns, v[0] / v[5
 };
 
 template <bool WRITE_BLUR>
-__global__ void __launch_bounds__(S_WARPS * 32, 5)
+__global__ void __launch_bounds__(S_WARPS * 32, 8)
 k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __restrict__ blur,
                       float* __restrict__ resp, uint32_t* __restrict__ frame_min) {
   const int lane = threadIdx.x & 31;
