@@ -62,6 +62,17 @@ struct BoardSlot {
   int* d_tap_nquads = nullptr;
   BoardWsLayout layout{};        // sized for the largest warps-per-frame (allocation)
   BoardWsLayout layout_batch{};  // layout used when many frames are in flight
+  // host-frame path (ag_detect_batch): staged input of the chunk (K6 samples the tag bits from it,
+  // so it lives as long as the slot's board search), device results and pinned result staging
+  uint8_t* d_in = nullptr;
+  size_t cap_in_bytes = 0;
+  int hs_frames = 0, hs_tags = 0;
+  ag_tag* d_tags = nullptr;
+  int* d_ntags = nullptr;
+  ag_tag* h_tags = nullptr;
+  int* h_ntags = nullptr;
+  uint32_t* h_status = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_done = nullptr;  // upload done / results on the host
 };
 
 // Device buffers of one pipeline slot (one chunk in flight).
@@ -101,6 +112,7 @@ struct ag_detector {
   Slot slot[kSlots];
   BoardSlot bslot[kBoardSlots];
   int slot_rr = 0;            // next board slot of the device-batch pipeline (rotates across calls)
+  cudaStream_t up_stream = nullptr;  // host-frame path: uploads, ahead of the kernels
   bool device_path_busy = false;  // device-batch work may still be in flight on slot 0 / the board slots
   bool device_async = false;  // ag_detect_batch_device returns without ordering the results on the
                               // caller's stream; ag_detect_batch_device_wait does that
@@ -231,7 +243,41 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
   return AG_OK;
 }
 
+// Host-frame staging of a board slot: `frames` frames of `in_bytes_per_chunk` bytes in total,
+// `cap_tags` result records per frame.
+int ensure_host_stage(ag_detector* det, BoardSlot& B, size_t in_bytes, int frames, int cap_tags) {
+  int rc;
+  if (!B.ev_up) {
+    AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_up, cudaEventDisableTiming));
+    AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_done, cudaEventDisableTiming));
+  }
+  if (in_bytes > B.cap_in_bytes) {
+    if ((rc = regrow(det, &B.d_in, in_bytes))) return rc;
+    B.cap_in_bytes = in_bytes;
+  }
+  if (frames > B.hs_frames || cap_tags > B.hs_tags) {
+    const int F = std::max(frames, B.hs_frames), ct = std::max(cap_tags, B.hs_tags);
+    if ((rc = regrow(det, &B.d_tags, (size_t)F * ct))) return rc;
+    if ((rc = regrow(det, &B.d_ntags, (size_t)F))) return rc;
+    if (B.h_tags) cudaFreeHost(B.h_tags);
+    if (B.h_ntags) cudaFreeHost(B.h_ntags);
+    if (B.h_status) cudaFreeHost(B.h_status);
+    AG_CUDA(det, cudaMallocHost((void**)&B.h_tags, sizeof(ag_tag) * (size_t)F * ct));
+    AG_CUDA(det, cudaMallocHost((void**)&B.h_ntags, sizeof(int) * F));
+    AG_CUDA(det, cudaMallocHost((void**)&B.h_status, sizeof(uint32_t) * F));
+    B.hs_frames = F;
+    B.hs_tags = ct;
+  }
+  return AG_OK;
+}
+
 void free_board_slot(BoardSlot& B) {
+  cudaFree(B.d_in); cudaFree(B.d_tags); cudaFree(B.d_ntags);
+  if (B.h_tags) cudaFreeHost(B.h_tags);
+  if (B.h_ntags) cudaFreeHost(B.h_ntags);
+  if (B.h_status) cudaFreeHost(B.h_status);
+  if (B.ev_up) cudaEventDestroy(B.ev_up);
+  if (B.ev_done) cudaEventDestroy(B.ev_done);
   cudaFree(B.d_nref); cudaFree(B.d_status); cudaFree(B.d_refined); cudaFree(B.d_board_ws);
   cudaFree(B.d_tap_quads); cudaFree(B.d_tap_nquads); cudaFree(B.d_board_tm);
   if (B.ev_front) cudaEventDestroy(B.ev_front);
@@ -440,16 +486,16 @@ void rochade_tables_host(float cone[25], float pinv[150]) {
     }
 }
 
-// Sort-free host copy-out of one chunk's results.
-void copy_out(const Slot& S, int n, int cap, int slot_cap, ag_tag* out, int* n_per_frame,
-              uint32_t* frame_status, int frame0, bool* truncated) {
+// Host copy-out of one chunk's results from a board slot's pinned staging.
+void copy_out_b(const BoardSlot& B, int n, int cap, ag_tag* out, int* n_per_frame, uint32_t* frame_status,
+                int frame0, bool* truncated) {
   for (int i = 0; i < n; ++i) {
-    int cnt = S.h_ntags[i];
+    const int cnt = B.h_ntags[i];
     n_per_frame[frame0 + i] = cnt;
     if (cnt > cap) *truncated = true;
-    int m = std::min(cnt, cap);
-    memcpy(out + (size_t)(frame0 + i) * cap, S.h_tags + (size_t)i * slot_cap, sizeof(ag_tag) * m);
-    if (frame_status) frame_status[frame0 + i] = S.h_status[i];
+    const int m = std::min(cnt, cap);
+    memcpy(out + (size_t)(frame0 + i) * cap, B.h_tags + (size_t)i * B.hs_tags, sizeof(ag_tag) * m);
+    if (frame_status) frame_status[frame0 + i] = B.h_status[i];
   }
 }
 
@@ -553,6 +599,7 @@ void ag_destroy(ag_detector* det) {
   cudaDeviceSynchronize();
   for (auto& S : det->slot) free_slot(S);
   for (auto& B : det->bslot) free_board_slot(B);
+  if (det->up_stream) cudaStreamDestroy(det->up_stream);
   for (auto e : det->ev_pool) cudaEventDestroy(e);
   cudaFree(det->d_codes);
   cudaFree(det->d_f32_a); cudaFree(det->d_f32_b); cudaFree(det->d_f32_c); cudaFree(det->d_taps);
@@ -736,49 +783,64 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
   if (n_frames == 0) return AG_OK;
-  // host frames: smaller chunks than the device path so that uploads, kernels and downloads of
-  // up to kSlots chunks overlap (each slot has its own stream)
+  // Host frames go through the same pipeline as device-resident ones: one set of dense buffers,
+  // eight board slots.  A chunk is uploaded on the upload stream (ahead of the kernels), K1-K4
+  // run on the dense stream, K6 and the download of the results on the board slot's stream, so
+  // uploads, front end, board searches and downloads of up to eight chunks overlap.  The staged
+  // input of a chunk stays in its board slot until K6 (which samples the tag bits) is done.
   const int chunk = (int)std::min<long>(std::min<long>(det->chunk_frames, det->host_chunk_frames), n_frames);
-  const int n_slots = std::min(kSlots, (n_frames + chunk - 1) / chunk);
-  for (int i = 0; i < n_slots; ++i)
-    if ((rc = ensure_slot(det, det->slot[i], g, chunk, cap_per_frame, true))) return rc;
+  Slot& D = det->slot[0];
+  if ((rc = ensure_slot(det, D, g, chunk, 1, false, false))) return rc;
+  if (!det->up_stream) AG_CUDA(det, cudaStreamCreateWithFlags(&det->up_stream, cudaStreamNonBlocking));
+  cudaStream_t s = D.stream, up = det->up_stream;
+  const size_t chunk_bytes = (size_t)chunk * g.frame_stride;
   bool truncated = false;
-  // Software pipeline over the slots: while one slot computes chunk i, the next ones upload
-  // chunks i+1, i+2, ...; a slot's results are copied out just before the slot is reused.
-  struct Pending { int f0, n; bool live; } pend[kSlots] = {};
-  int which = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk, which = (which + 1) % n_slots) {
-    Slot& S = det->slot[which];
-    if (pend[which].live) {
-      AG_CUDA(det, cudaEventSynchronize(S.done));
-      copy_out(S, pend[which].n, cap_per_frame, S.cap_tags, out, n_per_frame, frame_status,
-               pend[which].f0, &truncated);
-      pend[which].live = false;
+  struct Pending { int f0, n; bool live; } pend[kBoardSlots] = {};
+  int first = det->slot_rr, used = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    const int bi = det->slot_rr;
+    BoardSlot& B = det->bslot[bi];
+    det->slot_rr = (det->slot_rr + 1) % kBoardSlots;
+    if (pend[bi].live) {  // the slot's previous chunk: wait for its results, hand them out
+      AG_CUDA(det, cudaEventSynchronize(B.ev_done));
+      copy_out_b(B, pend[bi].n, cap_per_frame, out, n_per_frame, frame_status, pend[bi].f0, &truncated);
+      pend[bi].live = false;
+      B.pending = false;
     }
+    if ((rc = ensure_board_slot(det, B, chunk, true))) return rc;
+    if ((rc = ensure_host_stage(det, B, chunk_bytes, chunk, cap_per_frame))) return rc;
     const int n = std::min(chunk, n_frames - f0);
     const uint8_t* src = (const uint8_t*)frames + (size_t)f0 * g.frame_stride;
     const size_t bytes = (size_t)(n - 1) * g.frame_stride + g.row_stride * (size_t)(g.h - 1) +
                          (size_t)g.w * bytes_per_px(g.format);
-    AG_CUDA(det, cudaMemcpyAsync(S.d_in, src, bytes, cudaMemcpyHostToDevice, S.stream));
-    if ((rc = run_chunk(det, S, S.d_in, g, n, S.d_tags, S.cap_tags, S.d_ntags, S.d_status, false,
-                        S.stream)))
+    AG_CUDA(det, cudaMemcpyAsync(B.d_in, src, bytes, cudaMemcpyHostToDevice, up));
+    AG_CUDA(det, cudaEventRecord(B.ev_up, up));
+    AG_CUDA(det, cudaStreamWaitEvent(s, B.ev_up, 0));
+    if ((rc = run_dense(det, D, B.d_in, g, n, true, s))) return rc;
+    if ((rc = run_sparse(det, D, B, g, n, B.d_status, s))) return rc;
+    AG_CUDA(det, cudaEventRecord(B.ev_front, s));
+    AG_CUDA(det, cudaStreamWaitEvent(B.bstream, B.ev_front, 0));
+    if ((rc = run_boards(det, B, B.d_in, g, n, B.d_tags, B.hs_tags, B.d_ntags, B.d_status, false, B.bstream)))
       return rc;
-    AG_CUDA(det, cudaMemcpyAsync(S.h_ntags, S.d_ntags, sizeof(int) * n, cudaMemcpyDeviceToHost, S.stream));
-    AG_CUDA(det, cudaMemcpyAsync(S.h_status, S.d_status, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost,
-                                 S.stream));
-    AG_CUDA(det, cudaMemcpyAsync(S.h_tags, S.d_tags, sizeof(ag_tag) * (size_t)n * S.cap_tags,
-                                 cudaMemcpyDeviceToHost, S.stream));
-    AG_CUDA(det, cudaEventRecord(S.done, S.stream));
-    pend[which] = {f0, n, true};
+    AG_CUDA(det, cudaMemcpyAsync(B.h_ntags, B.d_ntags, sizeof(int) * n, cudaMemcpyDeviceToHost, B.bstream));
+    AG_CUDA(det, cudaMemcpyAsync(B.h_status, B.d_status, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost,
+                                 B.bstream));
+    AG_CUDA(det, cudaMemcpyAsync(B.h_tags, B.d_tags, sizeof(ag_tag) * (size_t)n * B.hs_tags,
+                                 cudaMemcpyDeviceToHost, B.bstream));
+    AG_CUDA(det, cudaEventRecord(B.ev_done, B.bstream));
+    B.pending = true;
+    pend[bi] = {f0, n, true};
+    if (used < kBoardSlots) ++used;
   }
-  for (int k = 0; k < n_slots; ++k) {  // oldest first
-    const int i = (which + k) % n_slots;
-    if (!pend[i].live) continue;
-    Slot& S = det->slot[i];
-    AG_CUDA(det, cudaEventSynchronize(S.done));
-    copy_out(S, pend[i].n, cap_per_frame, S.cap_tags, out, n_per_frame, frame_status, pend[i].f0,
-             &truncated);
+  for (int k = 0; k < kBoardSlots; ++k) {  // oldest first
+    const int bi = (first + k) % kBoardSlots;
+    if (!pend[bi].live) continue;
+    BoardSlot& B = det->bslot[bi];
+    AG_CUDA(det, cudaEventSynchronize(B.ev_done));
+    copy_out_b(B, pend[bi].n, cap_per_frame, out, n_per_frame, frame_status, pend[bi].f0, &truncated);
+    B.pending = false;
   }
+  (void)used;
   if (truncated) return fail(det, AG_ERR_CAPACITY, "cap_per_frame too small for at least one frame");
   return AG_OK;
 }
