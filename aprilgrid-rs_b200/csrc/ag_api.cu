@@ -60,8 +60,8 @@ struct BoardSlot {
   uint32_t* d_board_tm = nullptr;  // optional per-frame timing of the board kernel ([frames][16])
   int32_t* d_tap_quads = nullptr;
   int* d_tap_nquads = nullptr;
-  BoardWsLayout layout{};        // sized for the largest warps-per-frame (allocation)
-  BoardWsLayout layout_batch{};  // layout used when many frames are in flight
+  BoardWsLayout layout[2]{};        // [tier] sized for the largest warps-per-frame (allocation)
+  BoardWsLayout layout_batch[2]{};  // [tier] layout used when many frames are in flight
   // host-frame path (ag_detect_batch): staged input of the chunk (K6 samples the tag bits from it,
   // so it lives as long as the slot's board search), device results and pinned result staging
   uint8_t* d_in = nullptr;
@@ -132,6 +132,7 @@ struct ag_detector {
   // fill the GPU with one-warp blocks, 4 otherwise), or 1 / 2 / 4 / 8
   long board_warps = 0;
   long board_batch_frames = 148;  // automatic mode: launches with at least this many frames use 2 warps per frame
+  long board_saddle_tier = -1;  // -1 automatic, 0 = 512, 1 = 1024 saddles on chip in the board kernel
   bool label_list = true;  // K3 over a compact pixel list (0 = word-oriented version only)
   bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
   bool board_fast = true;  // four-lane group scoring of candidate boards (0 = general path only)
@@ -230,10 +231,15 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
   if ((rc = regrow(det, &B.d_nref, (size_t)F))) return rc;
   if ((rc = regrow(det, &B.d_status, (size_t)F))) return rc;
   if ((rc = regrow(det, &B.d_refined, (size_t)F * nsd))) return rc;
-  B.layout = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 8);
-  B.layout_batch = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 2);
-  if ((rc = regrow(det, &B.d_board_ws, (size_t)F * B.layout.bytes_per_frame))) return rc;
-  if ((rc = regrow(det, &B.d_tap_quads, (size_t)F * B.layout.max_quads * 4))) return rc;
+  // layouts for both tiers of on-chip saddle capacity (chosen per launch from the image size)
+  for (int tier = 0; tier < 2; ++tier) {
+    const int cap = tier == 0 ? 512 : 1024;
+    B.layout[tier] = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 8, cap);
+    B.layout_batch[tier] =
+        make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 2, cap);
+  }
+  if ((rc = regrow(det, &B.d_board_ws, (size_t)F * B.layout[0].bytes_per_frame))) return rc;
+  if ((rc = regrow(det, &B.d_tap_quads, (size_t)F * B.layout[0].max_quads * 4))) return rc;
   if ((rc = regrow(det, &B.d_tap_nquads, (size_t)F))) return rc;
   if ((rc = regrow(det, &B.d_board_tm, (size_t)F * 16))) return rc;
   B.cap_frames = F;
@@ -418,11 +424,16 @@ int run_boards(ag_detector* det, BoardSlot& S, const uint8_t* d_frames, const Fr
   prof_mark(det, -1, s);
   // automatic warps per frame: throughput (2 warps: most frames resident per SM) once a launch can
   // fill the GPU, latency (8 warps share one frame's seeds) for a handful of frames
-  const BoardWsLayout& BL = (det->board_warps == 0 && n >= det->board_batch_frames) ? S.layout_batch : S.layout;
+  // on-chip saddle capacity: 512 up to 1.5 Mpx (more frames per SM), 1024 above (larger images
+  // carry more saddles); frames beyond the tier take the general path inside the kernel
+  const int tier = det->board_saddle_tier >= 0 ? (int)det->board_saddle_tier
+                                               : ((long long)g.w * g.h > 1572864ll ? 1 : 0);
+  const BoardWsLayout& BL =
+      (det->board_warps == 0 && n >= det->board_batch_frames) ? S.layout_batch[tier] : S.layout[tier];
   det->launches += launch_boards_decode(
       d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->fam.n_codes, det->fam.edge,
       det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
-      d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout.max_quads,
+      d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout[0].max_quads,
       det->board_grid ? 1 : 0, det->board_fast ? 1 : 0, det->board_timing ? S.d_board_tm : nullptr, s);
   prof_mark(det, 4, s);
   AG_CUDA(det, cudaGetLastError());
@@ -636,6 +647,9 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "board_batch_frames")) {
     if (value < 1) return fail(det, AG_ERR_INVALID, "board_batch_frames must be positive");
     det->board_batch_frames = value;
+  } else if (!strcmp(key, "board_saddle_tier")) {
+    if (value < -1 || value > 1) return fail(det, AG_ERR_INVALID, "board_saddle_tier must be -1, 0 or 1");
+    det->board_saddle_tier = value;
   } else if (!strcmp(key, "label_list")) {
     det->label_list = value != 0;
   } else if (!strcmp(key, "board_timing")) {
@@ -969,7 +983,7 @@ int ag_stage_board_quads(ag_detector* det, int32_t* quads_out, int cap, int* n) 
   int cnt = 0;
   AG_CUDA(det, cudaMemcpy(&cnt, S.bb.d_tap_nquads, sizeof(int), cudaMemcpyDeviceToHost));
   *n = cnt;
-  int m = std::min(std::min(cnt, cap), S.bb.layout.max_quads);
+  int m = std::min(std::min(cnt, cap), S.bb.layout[0].max_quads);
   if (m > 0) AG_CUDA(det, cudaMemcpy(quads_out, S.bb.d_tap_quads, sizeof(int32_t) * 4 * m, cudaMemcpyDeviceToHost));
   return AG_OK;
 }

@@ -20,7 +20,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 constexpr int kMaxBoardWarps = 8;  // warps per frame (one block per frame): 1, 2, 4 or 8
 
-BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps) {
+BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles) {
   const int kBoardWarps = warps < 1 ? 1 : (warps > kMaxBoardWarps ? kMaxBoardWarps : warps);
   BoardWsLayout L;
   const int N = max_saddles;
@@ -62,7 +62,7 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps) {
   L.bytes_per_warp = align_up(w, 64);
   L.bytes_per_frame = align_up(L.off_warp0 + L.bytes_per_warp * kBoardWarps, 256);
   // shared memory of the block: frame-wide part, then one part per warp
-  L.smem_saddles = 512;
+  L.smem_saddles = smem_saddles <= 512 ? 512 : 1024;  // tier of the throughput path
   L.grid_cap_cells = 1408;  // 1280x1024 at 32 px buckets = 1280 buckets
   size_t sm = 0;
   auto stake = [&](size_t bytes) {

@@ -25,7 +25,8 @@
 
 namespace agb {
 
-constexpr int kFastMaxSaddles = 512;  // saddle list and bucket grid live in shared memory
+constexpr int kFastMaxSaddles = 1024;  // saddle list and bucket grid live in shared memory (two
+                                       // layout tiers: 512 and 1024 saddles, see make_board_layout)
 constexpr int kGroupLanes = 4;
 constexpr int kGroupsPerWarp = 8;
 constexpr int kGroupBytes = 1024;
@@ -37,7 +38,7 @@ constexpr int kScoreRedo = 0xffff;  // group board overflowed: score it with the
 constexpr int kGOffCell = 0;        // u8 [256]: 0 unvisited, 0xff None, q + 1 Some(q)
 constexpr int kGOffQuads = 256;     // i16 [64][4]
 constexpr int kGOffStack = 768;     // u16 [64]: cell | next direction << 8
-constexpr int kGOffActive = 896;    // u32 [16]: 512 saddles
+constexpr int kGOffActive = 896;    // u32 [32]: up to 1024 saddles
 constexpr int kDiffCap = 52;        // `diff` / `same` entries of a seed: at most 49 (50-NN minus the seed)
 
 }  // namespace agb
@@ -305,7 +306,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
 #pragma unroll
         for (int t = 0; t < 16; ++t) c32[jl + 4 * t] = 0u;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) active[jl + 4 * t] = 0xffffffffu;
+        for (int t = 0; t < 8; ++t) active[jl + 4 * t] = 0xffffffffu;
         __syncwarp(gmask);
         if (jl == 0) {
           const int16_t* quad = F.fx_qlist + 4 * k;
@@ -469,6 +470,7 @@ __device__ __noinline__ int nearest_k_fast(Frame& F, float qx, float qy, int k, 
   const int n = F.n;
   const int kk = k < n ? k : n;
   if (kk <= 0) return 0;
+  if (n > 512) return -1;  // 16 distances per lane; larger frames use nearest_k
   unsigned db[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {

@@ -263,3 +263,23 @@ def test_group_board_overflow_falls_back_to_general_build(pkg, oracle):
             assert_tags_match(det.detect(img), want)
         finally:
             det.close()
+
+
+def test_saddle_tiers_of_the_board_kernel(pkg, oracle):
+    """809 refined saddles (12 x 9 board): with the 512-saddle tier the frame takes the general
+    board path, with the 1024-saddle tier the four-lane group path; 108 tags either way, and the
+    board is far wider than a group's 16 x 16 window (general re-scoring inside the group path)."""
+    img = synth.render_board_numpy(1280, 1024, cols=12, rows=9, seed=4, tag_px=58.0)
+    fe = oracle.front_end(img, want_labels=False)
+    assert 512 < len(fe["refined"]) <= 1024
+    want = oracle.detect(img)
+    assert len(want) >= 100
+    for tier in (0, 1):
+        for warps in (2, 8):
+            det = pkg.TagDetector(pkg.TagFamily.T36H11)
+            try:
+                det.set_option("board_saddle_tier", tier)
+                det.set_option("board_warps", warps)
+                assert_tags_match(det.detect(img, cap=256), want)
+            finally:
+                det.close()
