@@ -96,7 +96,8 @@ struct Slot {
   int* h_ntags = nullptr;
   uint32_t* h_status = nullptr;
   // taps
-  uint32_t* d_pixlist = nullptr;   // K3: compact list of mask pixels, [frames][pix_cap]
+  int* d_label_fallback = nullptr;  // K3: frames the run-based kernel handed to the pixel-list kernel
+  uint32_t* d_pixlist = nullptr;   // K3: compact list of mask pixels / runs, [frames][pix_cap]
   int pix_cap = 0;
 };
 
@@ -132,6 +133,7 @@ struct ag_detector {
   // fill the GPU with one-warp blocks, 4 otherwise), or 1 / 2 / 4 / 8
   long board_warps = 0;
   long board_batch_frames = 148;  // automatic mode: launches with at least this many frames use 2 warps per frame
+  long label_variant = 0;  // K3: 0 = run-based in shared memory, 1 = pixel list with per-pixel parents
   long board_saddle_tier = -1;  // -1 automatic, 0 = 512, 1 = 1024 saddles on chip in the board kernel
   bool label_list = true;  // K3 over a compact pixel list (0 = word-oriented version only)
   bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
@@ -315,7 +317,7 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     if ((rc = regrow(det, &S.d_mask, (size_t)F * words))) return rc;
     // the saddle mask is 1-4 % full; a list of 1/8 of the pixels covers every real image, fuller
     // masks (noise) take the word-oriented labelling path
-    S.pix_cap = (int)std::min<size_t>(std::max<size_t>(px / 8, 1024), (size_t)1 << 20);
+    S.pix_cap = (int)std::min<size_t>(std::max<size_t>(px / 8, 32768), (size_t)1 << 20);
     if ((rc = regrow(det, &S.d_pixlist, (size_t)F * S.pix_cap))) return rc;
     S.cap_px = px;
     S.cap_words = words;
@@ -327,6 +329,7 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     if ((rc = regrow(det, &S.d_status, (size_t)F))) return rc;
     if ((rc = regrow(det, &S.d_ncl, (size_t)F))) return rc;
     if ((rc = regrow(det, &S.d_ntags, (size_t)F))) return rc;
+    if ((rc = regrow(det, &S.d_label_fallback, (size_t)F))) return rc;
     if ((rc = regrow(det, &S.d_acc, (size_t)F * ncl * 3))) return rc;
     if ((rc = regrow(det, &S.d_centers, (size_t)F * ncl))) return rc;
     if ((rc = regrow(det, &S.d_raw, (size_t)F * ncl))) return rc;
@@ -362,7 +365,7 @@ void free_slot(Slot& S) {
   cudaFree(S.d_in); cudaFree(S.d_blur); cudaFree(S.d_resp); cudaFree(S.d_min); cudaFree(S.d_mask);
   cudaFree(S.d_status); cudaFree(S.d_parent); cudaFree(S.d_acc); cudaFree(S.d_ncl);
   cudaFree(S.d_ntags); cudaFree(S.d_centers); cudaFree(S.d_raw);
-  cudaFree(S.d_raw_valid); cudaFree(S.d_tags); cudaFree(S.d_pixlist);
+  cudaFree(S.d_raw_valid); cudaFree(S.d_tags); cudaFree(S.d_pixlist); cudaFree(S.d_label_fallback);
   free_board_slot(S.bb);
   if (S.h_tags) cudaFreeHost(S.h_tags);
   if (S.h_ntags) cudaFreeHost(S.h_ntags);
@@ -402,12 +405,15 @@ int run_dense(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeo
 
 // Sparse stages up to the refined saddle list.
 int run_sparse(ag_detector* det, Slot& S, BoardSlot& B, const FrameGeom& g, int n, uint32_t* d_status,
-               cudaStream_t s) {
+               cudaStream_t s, bool want_pixel_parents = false) {
   AG_CUDA(det, cudaMemsetAsync(d_status, 0, sizeof(uint32_t) * n, s));
   prof_mark(det, -1, s);
+  // label_variant 0: run-based (no per-pixel parent array) unless the labels tap needs one
+  const int variant = (det->label_variant == 0 && !want_pixel_parents) ? 0 : 1;
   det->launches += launch_label_clusters(S.d_mask, g, n, S.d_parent, S.cap_clusters, S.d_acc,
                                          S.d_centers, S.d_ncl, d_status,
-                                         det->label_list ? S.d_pixlist : nullptr, S.pix_cap, s);
+                                         det->label_list ? S.d_pixlist : nullptr, S.pix_cap, variant,
+                                         S.d_label_fallback, s);
   prof_mark(det, 2, s);
   det->launches += launch_refine_filter(S.d_blur, g, n, S.d_centers, S.d_ncl, S.cap_clusters, S.d_raw,
                                         S.d_raw_valid, det->params.min_saddle_angle,
@@ -445,6 +451,9 @@ int run_chunk(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeo
               cudaStream_t s) {
   int rc;
   if ((rc = run_dense(det, S, d_frames, g, n, true, s))) return rc;
+  // taps: the labels tap reads the per-pixel parent array, which only the pixel-list kernel writes;
+  // run it first, then the regular (run-based) labelling, whose centres the pipeline continues with
+  if (taps && det->label_variant == 0 && (rc = run_sparse(det, S, S.bb, g, n, d_status, s, true))) return rc;
   if ((rc = run_sparse(det, S, S.bb, g, n, d_status, s))) return rc;
   return run_boards(det, S.bb, d_frames, g, n, d_tags, cap, d_ntags, d_status, taps, s);
 }
@@ -647,6 +656,9 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "board_batch_frames")) {
     if (value < 1) return fail(det, AG_ERR_INVALID, "board_batch_frames must be positive");
     det->board_batch_frames = value;
+  } else if (!strcmp(key, "label_variant")) {
+    if (value < 0 || value > 1) return fail(det, AG_ERR_INVALID, "label_variant must be 0 or 1");
+    det->label_variant = value;
   } else if (!strcmp(key, "board_saddle_tier")) {
     if (value < -1 || value > 1) return fail(det, AG_ERR_INVALID, "board_saddle_tier must be -1, 0 or 1");
     det->board_saddle_tier = value;

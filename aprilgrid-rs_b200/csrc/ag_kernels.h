@@ -41,7 +41,8 @@ int launch_unorm_table(float* out8, float* out16, float* ref8, float* ref16, cud
 int upload_rochade_tables(const float* cone25, const float* pinv150);
 int launch_label_clusters(const uint32_t* mask, const FrameGeom& g, int n_frames, int* parent,
                           int max_clusters, int* acc, float2* centers, int* n_clusters,
-                          uint32_t* frame_status, uint32_t* pixlist, int list_cap, cudaStream_t s);
+                          uint32_t* frame_status, uint32_t* pixlist, int list_cap, int variant,
+                          int* fallback, cudaStream_t s);
 int launch_labels_tap(const uint32_t* mask, const FrameGeom& g, const int* parent, int32_t* labels,
                       uint8_t* mask_u8, cudaStream_t s);
 int launch_refine_filter(const float* blur, const FrameGeom& g, int n_frames, const float2* centers,

@@ -215,10 +215,12 @@ __global__ void __launch_bounds__(kCclThreads)
 k_label_clusters(const uint32_t* __restrict__ mask, FrameGeom g, int* __restrict__ parent,
                  int max_clusters, int* __restrict__ acc /*[F][max_clusters][3]*/,
                  float2* __restrict__ centers, int* __restrict__ n_clusters,
-                 uint32_t* __restrict__ frame_status, uint32_t* __restrict__ pixlist, int list_cap) {
+                 uint32_t* __restrict__ frame_status, uint32_t* __restrict__ pixlist, int list_cap,
+                 const int* __restrict__ only_if /*[F] or null: run only the frames flagged here*/) {
   __shared__ int s_warp[32];
   __shared__ int s_total;
   const int f = blockIdx.x;
+  if (only_if && !only_if[f]) return;  // the run-based kernel handled this frame
   const uint32_t* M = mask + (size_t)f * g.n_words;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int wpr = g.wpr, w = g.w;
@@ -314,6 +316,199 @@ k_label_clusters(const uint32_t* __restrict__ mask, FrameGeom g, int* __restrict
       atomicAdd(A + 3 * cid + 0, x);
       atomicAdd(A + 3 * cid + 1, row);
       atomicAdd(A + 3 * cid + 2, 1);
+    }
+  }
+  __syncthreads();
+  float2* Cn = centers + (size_t)f * max_clusters;
+  for (int c = tid; c < n_used; c += nt) {
+    float n = (float)__ldcg(A + 3 * c + 2);
+    float sx = (float)__ldcg(A + 3 * c + 0), sy = (float)__ldcg(A + 3 * c + 1);
+    Cn[c] = make_float2(__fdiv_rn(sx, n), __fdiv_rn(sy, n));  // detector.rs:427
+  }
+  if (tid == 0) {
+    n_clusters[f] = n_used;
+    if (total > max_clusters) atomicOr(frame_status + f, (uint32_t)AG_FRAME_CLUSTER_OVERFLOW);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// K3, run-based.  One CTA per frame; the whole union-find lives in SHARED memory.
+//
+// The nodes are the maximal horizontal RUNS of set pixels (a few thousand per frame instead of
+// ~20 k pixels), numbered in raster order, so the minimum run index of a component is the run
+// that contains its minimum raster pixel:
+//   A  count run starts per thread (contiguous word ranges), block scan -> run ids
+//   B  write the runs (row << 16 | x0, x1) to a compact buffer; runs per row -> row starts
+//   C  one thread per pair of adjacent rows merges their run lists (two pointers) and unites
+//      overlapping runs with atomicMin hooking on the shared parent array
+//   D  flatten; number the roots in run (= raster) order with a block scan -- the reference's
+//      discovery order (detector.rs:174-185)
+//   E  per run, closed-form sums (n, sum x, sum y) into the cluster accumulators
+// No per-pixel parent array is written (the labels tap uses the pixel-list version).
+// Falls back (returns false, block-uniform) when the frame has too many runs or rows.
+// ----------------------------------------------------------------------------------------
+constexpr int kRunCap = 12288;  // runs per frame held in shared memory (48 KB of parents)
+constexpr int kRowCap = 4096;   // rows per frame (row starts in shared memory)
+
+AG_D int suf_find(volatile int* P, int p) {
+  int q;
+  while ((q = P[p]) != p) p = q;
+  return p;
+}
+AG_D void suf_union(int* P, int a, int b) {
+  while (true) {
+    a = suf_find(P, a);
+    b = suf_find(P, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    int old = atomicMin(P + a, b);  // hang the larger root under the smaller one
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(kCclThreads)
+k_label_runs(const uint32_t* __restrict__ mask, FrameGeom g, int max_clusters,
+             int* __restrict__ acc /*[F][max_clusters][3]*/, float2* __restrict__ centers,
+             int* __restrict__ n_clusters, uint32_t* __restrict__ frame_status,
+             uint32_t* __restrict__ runbuf /*[F][2 * kRunCap]*/, int* __restrict__ fallback /*[F]*/) {
+  extern __shared__ __align__(16) int s_dyn[];
+  int* s_parent = s_dyn;                 // [kRunCap]
+  int* s_rowstart = s_dyn + kRunCap;     // [kRowCap + 1]
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int f = blockIdx.x;
+  const uint32_t* M = mask + (size_t)f * g.n_words;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int wpr = g.wpr;
+  // A: run starts in this thread's contiguous word range
+  const int per = (g.n_words + nt - 1) / nt;
+  const int w_begin = min(tid * per, g.n_words), w_end = min(w_begin + per, g.n_words);
+  int my_runs = 0;
+  {
+    int wc = w_begin % wpr;
+    for (int wi = w_begin; wi < w_end; ++wi) {
+      const uint32_t m = M[wi];
+      const uint32_t carry = wc > 0 ? (M[wi - 1] >> 31) : 0u;
+      my_runs += __popc(m & ~((m << 1) | carry));
+      if (++wc == wpr) wc = 0;
+    }
+  }
+  int rid = block_exclusive_scan(my_runs, s_warp, &s_total);
+  const int R = s_total;
+  __syncthreads();
+  if (R > kRunCap || g.h > kRowCap || g.w > 65535) {  // block-uniform
+    if (tid == 0) fallback[f] = 1;
+    return;
+  }
+  if (tid == 0) fallback[f] = 0;
+  uint32_t* RB = runbuf + (size_t)f * 2 * kRunCap;
+  for (int i = tid; i <= g.h; i += nt) s_rowstart[i] = 0;
+  __syncthreads();
+  // B: write the runs; count runs per row into s_rowstart[row + 1]
+  if (my_runs) {
+    int row = w_begin / wpr, wc = w_begin - row * wpr;
+    for (int wi = w_begin; wi < w_end; ++wi) {
+      const uint32_t m = M[wi];
+      const uint32_t carry = wc > 0 ? (M[wi - 1] >> 31) : 0u;
+      uint32_t starts = m & ~((m << 1) | carry);
+      while (starts) {
+        const int b = __ffs(starts) - 1;
+        starts &= starts - 1;
+        // end of the run: first clear bit at or after b, possibly in a following word of the row
+        int x1;
+        {
+          uint32_t rest = ~(m >> b);  // bit k set <=> pixel b + k is clear (or beyond the word)
+          int len = __ffs(rest) - 1;  // rest != 0 unless b == 0 and m == all ones
+          if (rest == 0u) len = 32;
+          int xe = wc * 32 + b + len;  // one past the run inside this word
+          if (b + len == 32) {         // the run touches the word's end: follow it
+            int wj = wi + 1, wcj = wc + 1;
+            while (wcj < wpr) {
+              const uint32_t mj = M[wj];
+              if (mj == 0xffffffffu) { xe += 32; ++wj; ++wcj; continue; }
+              xe += __ffs(~mj) - 1;
+              break;
+            }
+          }
+          x1 = xe - 1;
+        }
+        RB[2 * rid] = ((uint32_t)row << 16) | (uint32_t)(wc * 32 + b);
+        RB[2 * rid + 1] = (uint32_t)x1;
+        s_parent[rid] = rid;
+        atomicAdd(&s_rowstart[row + 1], 1);
+        ++rid;
+      }
+      if (++wc == wpr) { wc = 0; ++row; }
+    }
+  }
+  __syncthreads();
+  // exclusive scan of the per-row counts: s_rowstart[y] = first run of row y, [h] = R
+  {
+    const int rper = (g.h + 1 + nt - 1) / nt;
+    const int r0 = min(tid * rper, g.h + 1), r1 = min(r0 + rper, g.h + 1);
+    int sum = 0;
+    for (int y = r0; y < r1; ++y) sum += s_rowstart[y];
+    int off = block_exclusive_scan(sum, s_warp, &s_total);
+    for (int y = r0; y < r1; ++y) {  // inclusive over the shifted counts == start of row y
+      off += s_rowstart[y];
+      s_rowstart[y] = off;
+    }
+  }
+  __syncthreads();
+  // C: unite overlapping runs of adjacent rows (4-connectivity: they share a column)
+  for (int y = 1 + tid; y < g.h; y += nt) {
+    int a = s_rowstart[y], a_end = s_rowstart[y + 1];
+    int b = s_rowstart[y - 1], b_end = a;
+    if (a == a_end || b == b_end) continue;
+    uint32_t ax0 = RB[2 * a] & 0xffffu, ax1 = RB[2 * a + 1];
+    uint32_t bx0 = RB[2 * b] & 0xffffu, bx1 = RB[2 * b + 1];
+    while (true) {
+      if (ax0 <= bx1 && bx0 <= ax1) suf_union(s_parent, a, b);
+      if (ax1 <= bx1) {
+        if (++a == a_end) break;
+        ax0 = RB[2 * a] & 0xffffu;
+        ax1 = RB[2 * a + 1];
+      } else {
+        if (++b == b_end) break;
+        bx0 = RB[2 * b] & 0xffffu;
+        bx1 = RB[2 * b + 1];
+      }
+    }
+  }
+  __syncthreads();
+  // D: flatten, then number the roots in run order
+  for (int i = tid; i < R; i += nt) {
+    const int r = suf_find(s_parent, i);
+    if (r != i) s_parent[i] = r;
+  }
+  __syncthreads();
+  const int lper = (R + nt - 1) / nt;
+  const int l_begin = min(tid * lper, R), l_end = min(l_begin + lper, R);
+  int my_roots = 0;
+  for (int i = l_begin; i < l_end; ++i) my_roots += s_parent[i] == i ? 1 : 0;
+  int roff = block_exclusive_scan(my_roots, s_warp, &s_total);
+  const int total = s_total;
+  for (int i = l_begin; i < l_end; ++i)
+    if (s_parent[i] == i) {
+      s_parent[i] = -(roff + 1);  // root now carries its cluster id, encoded negative
+      ++roff;
+    }
+  int* A = acc + (size_t)f * max_clusters * 3;
+  const int n_used = min(total, max_clusters);
+  for (int i = tid; i < n_used * 3; i += nt) A[i] = 0;
+  __syncthreads();
+  // E: per run, n = len, sum x = len * x0 + len (len - 1) / 2, sum y = len * row (exact integers;
+  // the reference's f32 sums of integers below 2^24 equal them, detector.rs:424-426)
+  for (int i = tid; i < R; i += nt) {
+    const int v = s_parent[i];
+    const int cid = v < 0 ? -v - 1 : -s_parent[v] - 1;
+    if (cid < max_clusters) {
+      const uint32_t e = RB[2 * i];
+      const int row = (int)(e >> 16), x0 = (int)(e & 0xffffu), len = (int)RB[2 * i + 1] - x0 + 1;
+      atomicAdd(A + 3 * cid + 0, len * x0 + len * (len - 1) / 2);
+      atomicAdd(A + 3 * cid + 1, len * row);
+      atomicAdd(A + 3 * cid + 2, len);
     }
   }
   __syncthreads();
@@ -522,9 +717,23 @@ k_refine_filter(const float* __restrict__ blur, FrameGeom g, const float2* __res
 
 int launch_label_clusters(const uint32_t* mask, const FrameGeom& g, int n_frames, int* parent,
                           int max_clusters, int* acc, float2* centers, int* n_clusters,
-                          uint32_t* frame_status, uint32_t* pixlist, int list_cap, cudaStream_t s) {
+                          uint32_t* frame_status, uint32_t* pixlist, int list_cap, int variant,
+                          int* fallback, cudaStream_t s) {
+  // variant 0: run-based kernel (shared-memory union-find; no per-pixel parents), followed by the
+  // pixel-list kernel for the frames it declined; 1: pixel-list kernel for every frame (writes the
+  // per-pixel parent array the labels tap reads)
+  if (variant == 0 && pixlist && fallback && list_cap >= 2 * kRunCap) {
+    const size_t smem = sizeof(int) * (kRunCap + kRowCap + 1);
+    if (cudaFuncSetAttribute(k_label_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return 0;
+    k_label_runs<<<n_frames, kCclThreads, smem, s>>>(mask, g, max_clusters, acc, centers, n_clusters,
+                                                     frame_status, pixlist, fallback);
+    k_label_clusters<<<n_frames, kCclThreads, 0, s>>>(mask, g, parent, max_clusters, acc, centers,
+                                                      n_clusters, frame_status, pixlist, list_cap, fallback);
+    return 2;
+  }
   k_label_clusters<<<n_frames, kCclThreads, 0, s>>>(mask, g, parent, max_clusters, acc, centers,
-                                                    n_clusters, frame_status, pixlist, list_cap);
+                                                    n_clusters, frame_status, pixlist, list_cap, nullptr);
   return 1;
 }
 
