@@ -437,7 +437,7 @@ int run_boards(ag_detector* det, BoardSlot& S, const uint8_t* d_frames, const Fr
   const BoardWsLayout& BL =
       (det->board_warps == 0 && n >= det->board_batch_frames) ? S.layout_batch[tier] : S.layout[tier];
   det->launches += launch_boards_decode(
-      d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->fam.n_codes, det->fam.edge,
+      d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->d_codes, det->fam.n_codes, det->fam.edge,
       det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
       d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout[0].max_quads,
       det->board_grid ? 1 : 0, det->board_fast ? 1 : 0, det->board_timing ? S.d_board_tm : nullptr, s);
@@ -601,7 +601,7 @@ int ag_create(int family, const ag_params* params, int device, ag_detector** out
   }
   float cone[25], pinv[150];
   rochade_tables_host(cone, pinv);
-  if (upload_rochade_tables(cone, pinv) != 0 || upload_codes(fam.codes, fam.n_codes) != 0 ||
+  if (upload_rochade_tables(cone, pinv) != 0 ||
       cudaMalloc((void**)&det->d_codes, sizeof(uint64_t) * fam.n_codes) != cudaSuccess ||
       cudaMemcpy(det->d_codes, fam.codes, sizeof(uint64_t) * fam.n_codes, cudaMemcpyHostToDevice) !=
           cudaSuccess) {

@@ -9,12 +9,9 @@
 
 namespace ag {
 
-__constant__ uint64_t c_codes[agb::kMaxCodes];
-
-int upload_codes(const uint64_t* codes, int n) {
-  if (n > agb::kMaxCodes) return -1;
-  return (int)cudaMemcpyToSymbol(c_codes, codes, sizeof(uint64_t) * n);
-}
+// The family's code table is read from global memory (the detector's own copy): lanes read
+// consecutive codes (coalesced, L1-resident), whereas constant memory would serialise the 32
+// different addresses of a warp; it also keeps detectors of different families independent.
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -103,7 +100,8 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
 __global__ void __launch_bounds__(kMaxBoardWarps * 32)
 k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
                 const ag_saddle* __restrict__ refined, const int* __restrict__ n_refined,
-                uint8_t* __restrict__ ws, BoardWsLayout L, int n_codes, int edge, int border,
+                uint8_t* __restrict__ ws, BoardWsLayout L, const uint64_t* __restrict__ codes,
+                int n_codes, int edge, int border,
                 int hamming, int max_boards, ag_tag* __restrict__ out, int cap,
                 int* __restrict__ n_out, uint32_t* __restrict__ frame_status,
                 int32_t* __restrict__ tap_quads, int* __restrict__ tap_n_quads, int tap_cap,
@@ -176,7 +174,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.h = g.h;
   F.format = g.format;
   F.row_stride = g.row_stride;
-  F.codes = c_codes;
+  F.codes = codes;
   F.n_codes = n_codes;
   F.edge = edge;
   F.border = border;
@@ -267,7 +265,8 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
 
 int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames,
                          const ag_saddle* refined, const int* n_refined, uint8_t* ws,
-                         const BoardWsLayout& L, int n_codes, int edge, int border, int hamming,
+                         const BoardWsLayout& L, const uint64_t* d_codes, int n_codes, int edge, int border,
+                         int hamming,
                          int max_boards, ag_tag* out, int cap, int* n_out, uint32_t* frame_status,
                          int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid, int fast,
                          uint32_t* timing, cudaStream_t s) {
@@ -281,7 +280,7 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
                            cudaSharedmemCarveoutMaxShared) != cudaSuccess)
     return 0;
   k_boards_decode<<<blocks, L.warps * 32, smem, s>>>(
-      frames, g, n_frames, refined, n_refined, ws, L, n_codes, edge, border, hamming, max_boards,
+      frames, g, n_frames, refined, n_refined, ws, L, d_codes, n_codes, edge, border, hamming, max_boards,
       out, cap, n_out, frame_status, tap_quads, tap_n_quads, tap_cap, use_grid, fast, timing);
   return 1;
 }

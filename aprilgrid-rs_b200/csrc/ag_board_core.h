@@ -1090,6 +1090,40 @@ AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
   const float h3 = (float)h3d, h4 = (float)h4d, h5 = (float)(mcy - h3d * mx - h4d * my);
   // sample (bit_code :80-93): sample s = (x - border) * edge + (y - border), x outer
   const int ns = F.edge * F.edge;
+#if AGB_DEVICE
+  uint64_t bits = 0;
+  {
+    // Device: lane s holds sample s (and s + 32); min / max by warp reduction, the bit pattern and
+    // the count of undecided samples by ballot (first sample = most significant bit, :101).
+    int v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int s = F.lane + 32 * h;
+      v[h] = -2;  // no such sample
+      if (s < ns) {
+        const float fx = (float)(F.border + s / F.edge), fy = (float)(F.border + s % F.edge);
+        const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
+        const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
+        const uint32_t x = sat_u32(roundf(px)), y = sat_u32(roundf(py));
+        v[h] = (x < (uint32_t)F.w && y < (uint32_t)F.h) ? luma8_at(F, x, y) : -1;
+      }
+    }
+    if (__any_sync(0xffffffffu, v[0] == -1 || v[1] == -1)) return false;  // a sample outside the image
+    const int lo0 = v[0] >= 0 ? v[0] : 255, lo1 = v[1] >= 0 ? v[1] : 255;
+    const int hi0 = v[0] >= 0 ? v[0] : 0, hi1 = v[1] >= 0 ? v[1] : 0;
+    const int min_b = __reduce_min_sync(0xffffffffu, lo0 < lo1 ? lo0 : lo1);
+    const int max_b = __reduce_max_sync(0xffffffffu, hi0 > hi1 ? hi0 : hi1);
+    if (max_b - min_b < 50) return false;  // :97
+    const int mid_b = (int)sat_u32(roundf(fdiv(fadd((float)min_b, (float)max_b), 2.0f)));
+    auto near_mid = [&](int x) { const int d = mid_b - x; return x >= 0 && (d < 0 ? -d : d) < 10; };
+    const int invalid = __popc(__ballot_sync(0xffffffffu, near_mid(v[0]))) +
+                        __popc(__ballot_sync(0xffffffffu, near_mid(v[1])));
+    if (invalid > 3) return false;
+    const uint64_t set = (uint64_t)__ballot_sync(0xffffffffu, v[0] > mid_b) |
+                         ((uint64_t)__ballot_sync(0xffffffffu, v[1] >= 0 && v[1] > mid_b) << 32);
+    bits = __brevll(set) >> (64 - ns);  // sample s -> bit ns - 1 - s
+  }
+#else
   for (int s = F.lane; s < ns; s += AGB_LANES) {
     const float fx = (float)(F.border + s / F.edge), fy = (float)(F.border + s % F.edge);
     const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
@@ -1122,6 +1156,7 @@ AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
   }
   AGB_SYNC();
   if (invalid > 3) return false;
+#endif
   // best_tag :142-169
   int id = -1, rot = 0;
   for (int rotated = 0; rotated < 4; ++rotated) {

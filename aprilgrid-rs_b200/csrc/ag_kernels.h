@@ -51,10 +51,10 @@ int launch_refine_filter(const float* blur, const FrameGeom& g, int n_frames, co
                          int* n_refined, uint32_t* frame_status, cudaStream_t s);
 
 // ag_board.cu
-int upload_codes(const uint64_t* codes, int n);
 int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames,
                          const ag_saddle* refined, const int* n_refined, uint8_t* ws,
-                         const BoardWsLayout& L, int n_codes, int edge, int border, int hamming,
+                         const BoardWsLayout& L, const uint64_t* d_codes, int n_codes, int edge, int border,
+                         int hamming,
                          int max_boards, ag_tag* out, int cap, int* n_out, uint32_t* frame_status,
                          int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid, int fast,
                          uint32_t* timing, cudaStream_t s);
