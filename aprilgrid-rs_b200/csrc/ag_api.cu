@@ -656,6 +656,8 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "board_batch_frames")) {
     if (value < 1) return fail(det, AG_ERR_INVALID, "board_batch_frames must be positive");
     det->board_batch_frames = value;
+  } else if (!strcmp(key, "board_smem_pad")) {
+    ag::g_board_smem_pad = (int)value;
   } else if (!strcmp(key, "label_variant")) {
     if (value < 0 || value > 1) return fail(det, AG_ERR_INVALID, "label_variant must be 0 or 1");
     det->label_variant = value;

@@ -17,6 +17,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 constexpr int kMaxBoardWarps = 8;  // warps per frame (one block per frame): 1, 2, 4 or 8
 
+int g_board_smem_pad = 0;  // experiment: extra dynamic shared memory per block (limits blocks per SM)
+
 BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles) {
   const int kBoardWarps = warps < 1 ? 1 : (warps > kMaxBoardWarps ? kMaxBoardWarps : warps);
   BoardWsLayout L;
@@ -272,7 +274,7 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
                          uint32_t* timing, cudaStream_t s) {
   const int blocks = n_frames;
   if (blocks == 0) return 0;
-  const size_t smem = L.smem_per_block;
+  const size_t smem = L.smem_per_block + (size_t)g_board_smem_pad;
   // per-device function attributes (cheap host calls; a process may drive several devices)
   if (cudaFuncSetAttribute(k_boards_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
           cudaSuccess ||

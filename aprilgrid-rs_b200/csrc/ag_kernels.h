@@ -51,6 +51,7 @@ int launch_refine_filter(const float* blur, const FrameGeom& g, int n_frames, co
                          int* n_refined, uint32_t* frame_status, cudaStream_t s);
 
 // ag_board.cu
+extern int g_board_smem_pad;
 int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames,
                          const ag_saddle* refined, const int* n_refined, uint8_t* ws,
                          const BoardWsLayout& L, const uint64_t* d_codes, int n_codes, int edge, int border,
