@@ -38,7 +38,7 @@ std::string g_create_error;
 // Pipeline slots.  The device-batch path keeps up to kSlots chunks in flight: the dense + sparse
 // front end of chunk i+1 runs on the caller's stream while the latency-bound board searches of
 // chunks i, i-1, ... run on their slots' own streams, side by side.
-constexpr int kSlots = 4;
+constexpr int kSlots = 2;
 // Device-batch path: the dense buffers of ONE slot are reused chunk after chunk (K1-K4 of
 // consecutive chunks are serial on the caller's stream anyway); only the light board-search side
 // is multi-buffered, so the board searches of up to kBoardSlots chunks overlap each other and
@@ -114,6 +114,9 @@ struct ag_detector {
   BoardSlot bslot[kBoardSlots];
   int slot_rr = 0;            // next board slot of the device-batch pipeline (rotates across calls)
   cudaStream_t up_stream = nullptr;  // host-frame path: uploads, ahead of the kernels
+  long dense_streams = 1;   // device-batch path: 2 = alternate chunks between two dense streams / buffer sets (measured: no gain)
+  int dense_rr = 0;
+  cudaEvent_t ev_call = nullptr;
   bool device_path_busy = false;  // device-batch work may still be in flight on slot 0 / the board slots
   bool device_async = false;  // ag_detect_batch_device returns without ordering the results on the
                               // caller's stream; ag_detect_batch_device_wait does that
@@ -460,8 +463,9 @@ int run_chunk(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeo
 
 int quiesce_device_path(ag_detector* det) {
   if (!det->device_path_busy) return AG_OK;
-  Slot& D = det->slot[0];
-  if (D.done) AG_CUDA(det, cudaEventSynchronize(D.done));
+  for (auto& D : det->slot)
+    if (D.done) AG_CUDA(det, cudaEventSynchronize(D.done));
+  det->dense_rr = 0;
   for (auto& B : det->bslot)
     if (B.pending) {
       AG_CUDA(det, cudaEventSynchronize(B.ev_boards));
@@ -620,6 +624,7 @@ void ag_destroy(ag_detector* det) {
   for (auto& S : det->slot) free_slot(S);
   for (auto& B : det->bslot) free_board_slot(B);
   if (det->up_stream) cudaStreamDestroy(det->up_stream);
+  if (det->ev_call) cudaEventDestroy(det->ev_call);
   for (auto e : det->ev_pool) cudaEventDestroy(e);
   cudaFree(det->d_codes);
   cudaFree(det->d_f32_a); cudaFree(det->d_f32_b); cudaFree(det->d_f32_c); cudaFree(det->d_taps);
@@ -656,6 +661,9 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "board_batch_frames")) {
     if (value < 1) return fail(det, AG_ERR_INVALID, "board_batch_frames must be positive");
     det->board_batch_frames = value;
+  } else if (!strcmp(key, "dense_streams")) {
+    if (value < 1 || value > 2) return fail(det, AG_ERR_INVALID, "dense_streams must be 1 or 2");
+    det->dense_streams = value;
   } else if (!strcmp(key, "board_smem_pad")) {
     ag::g_board_smem_pad = (int)value;
   } else if (!strcmp(key, "label_variant")) {
@@ -726,17 +734,30 @@ int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_
   // searches of up to kBoardSlots chunks (of this call and of earlier calls) overlap each other
   // and the front end of the following chunks.  A board slot is reused only after its kernel has
   // finished (K4 of the new chunk writes the slot's saddle list).
-  Slot& D = det->slot[0];
-  if ((rc = ensure_slot(det, D, g, chunk, 1, false, false))) return rc;
-  cudaStream_t s = stream ? (cudaStream_t)stream : D.stream;
+  // With dense_streams = 2 a second set of dense buffers and a second (internal) stream take every
+  // other chunk, so the latency-bound K3 / K4 of one chunk overlap the issue-bound K1 of the next.
+  const int n_dense = det->dense_streams >= 2 ? 2 : 1;
+  for (int i = 0; i < n_dense; ++i)
+    if ((rc = ensure_slot(det, det->slot[i], g, chunk, 1, false, false))) return rc;
+  cudaStream_t s0 = stream ? (cudaStream_t)stream : det->slot[0].stream;
+  cudaStream_t s1 = det->slot[n_dense - 1].stream;
   // all board slots are sized up front: an allocation (which synchronises the device) must not
   // happen in the middle of a streaming sequence of calls
   for (auto& B : det->bslot)
     if ((rc = ensure_board_slot(det, B, chunk, false))) return rc;
   // the dense buffers are shared by every device-batch call: order this call after the front end
   // of the previous one even if the caller switched streams
-  if (det->device_path_busy) AG_CUDA(det, cudaStreamWaitEvent(s, D.done, 0));
+  if (det->device_path_busy) AG_CUDA(det, cudaStreamWaitEvent(s0, det->slot[0].done, 0));
+  if (n_dense == 2) {  // the internal stream starts after the caller's earlier work (the frames)
+    if (!det->ev_call) AG_CUDA(det, cudaEventCreateWithFlags(&det->ev_call, cudaEventDisableTiming));
+    AG_CUDA(det, cudaEventRecord(det->ev_call, s0));
+    AG_CUDA(det, cudaStreamWaitEvent(s1, det->ev_call, 0));
+  }
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    const int which = n_dense == 2 ? det->dense_rr : 0;
+    if (n_dense == 2) det->dense_rr ^= 1;
+    Slot& D = det->slot[which];
+    cudaStream_t s = which ? s1 : s0;
     BoardSlot& B = det->bslot[det->slot_rr];
     det->slot_rr = (det->slot_rr + 1) % kBoardSlots;
     if ((rc = ensure_board_slot(det, B, chunk, false))) return rc;
@@ -754,13 +775,15 @@ int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_
     AG_CUDA(det, cudaEventRecord(B.ev_boards, B.bstream));
     B.pending = true;
   }
-  AG_CUDA(det, cudaEventRecord(D.done, s));
+  AG_CUDA(det, cudaEventRecord(det->slot[0].done, s0));
+  if (n_dense == 2) AG_CUDA(det, cudaEventRecord(det->slot[1].done, s1));
   det->device_path_busy = true;
   // results become visible in the caller's stream order (unless the caller asked to do that
-  // itself with ag_detect_batch_device_wait, which lets consecutive calls overlap)
+  // itself with ag_detect_batch_device_wait, which lets consecutive calls overlap); every chunk's
+  // board kernel follows its front end, so waiting for the board kernels covers both dense streams
   if (!det->device_async)
     for (auto& B : det->bslot)
-      if (B.pending) AG_CUDA(det, cudaStreamWaitEvent(s, B.ev_boards, 0));
+      if (B.pending) AG_CUDA(det, cudaStreamWaitEvent(s0, B.ev_boards, 0));
   return AG_OK;
 }
 
