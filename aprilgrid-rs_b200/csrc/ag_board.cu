@@ -201,6 +201,10 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.fx_tmask = (unsigned long long*)(F.fx_dvy + agb::kDiffCap);  // 416 bytes in: 8-byte aligned
   F.fx_squeue = (uint32_t*)(SW + L.smw_squeue);
   F.fx_gstate = SW + L.smw_cell;
+  // the seed-best arrays of the general path are free on the throughput path: they hold each
+  // warp's saved best board there
+  F.fx_save0 = W + L.off_warp0 + L.woff_sb_touched;
+  F.fx_save_stride = L.bytes_per_warp;
   F.fx_wscore = (uint16_t*)(smem + L.sm_wave);
   F.fx_wquad = (int16_t*)(F.fx_wscore + 32);
   // block-uniform: the whole frame takes the throughput path or the general one

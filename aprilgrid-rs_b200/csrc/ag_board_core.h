@@ -133,6 +133,8 @@ struct Frame {
   uint8_t* fx_gstate;    // this warp's group states (aliases bs.cell)
   uint16_t* fx_wscore;   // [32] per wave slot: best score of the seed so far
   int16_t* fx_wquad;     // [32][4] ... and its quad
+  uint8_t* fx_save0;     // global: warp 0's saved best board (header + group state); warp w's at
+  size_t fx_save_stride; //   fx_save0 + w * fx_save_stride
   uint32_t* tm;          // optional per-frame timing / work counters ([16], may be null)
 };
 

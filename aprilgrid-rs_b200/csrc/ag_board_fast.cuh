@@ -275,7 +275,16 @@ __device__ __forceinline__ int packed_cand(unsigned p, int k) { return (int)((p 
 // for all eight boards.  A group that finishes its board takes the next quad of the list
 // of the warp's list, so long and short boards overlap.
 constexpr int kCtlNext = 6;  // slot of F.ctl: next wave slot (seed) to hand to a warp
+// A board of at least kSaveMin quads (a real board, not the few-quad debris of tag interiors) is
+// worth keeping: each warp keeps the state of its best such board (first one of the highest score)
+// in global memory, and when the search's winner is one of them it is converted instead of being
+// grown a second time by the general path.  Layout: int score, i16 quad[4], pad to 16 bytes, then
+// the group state's cell window (256 B) and quads (512 B).
+constexpr int kSaveMin = 12;
+constexpr int kSaveBytes = 16 + 256 + 512;
 __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
+  uint8_t* const save = F.fx_save0 + (size_t)F.warp * F.fx_save_stride;
+  int save_score = *(const int*)save;  // warp-uniform
   const unsigned full = 0xffffffffu;
   const int grp = F.lane >> 2, jl = F.lane & 3, gshift = grp * 4;
   const unsigned gmask = 0xfu << gshift;
@@ -364,6 +373,27 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
       }
     }
     __syncwarp();
+    {
+      // keep the state of the warp's best large board: among the boards that finished in this
+      // iteration the highest score wins, ties go to the earlier list entry; an earlier
+      // iteration's board is replaced only by a strictly higher score
+      const bool big = result >= kSaveMin && result != kScoreRedo;
+      const unsigned key = (big && jl == 0) ? (((unsigned)result << 16) | (unsigned)(0xffff - k)) : 0u;
+      const unsigned best = __reduce_max_sync(full, key);
+      if ((int)(best >> 16) > save_score) {  // warp-uniform
+        const int src_lane = __ffs((int)__ballot_sync(full, key == best)) - 1;  // leader of the winning group
+        const uint8_t* src = F.fx_gstate + (src_lane >> 2) * kGroupBytes;
+        save_score = (int)(best >> 16);
+        const int kk = 0xffff - (int)(best & 0xffffu);
+        if (F.lane == 0) *(int*)save = save_score;
+        if (F.lane < 4) ((int16_t*)(save + 4))[F.lane] = F.fx_qlist[4 * kk + F.lane];
+        const uint32_t* s32 = (const uint32_t*)src;  // cell window [0, 256) and quads [256, 768)
+        uint32_t* d32 = (uint32_t*)(save + 16);
+#pragma unroll
+        for (int t = 0; t < 6; ++t) d32[F.lane + 32 * t] = s32[F.lane + 32 * t];
+        __syncwarp();
+      }
+    }
     {
       const unsigned nb = __ballot_sync(full, need);
       if (nb == 0u) continue;
@@ -744,6 +774,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
     grid_build_warp(F);
     select_seeds(F);
   }
+  if (F.lane == 0) *(int*)(F.fx_save0 + (size_t)F.warp * F.fx_save_stride) = 0;  // no board kept yet
   __syncthreads();
   AGB_TM_ADD(1, clock64() - t0);
   int seeds_left = F.ctl[0];
@@ -865,7 +896,42 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
   t0 = clock64();
   if (F.warp == 0) {
     general_state_init(F);
-    board_build(F, F.bs, best_quad);
+    // the winner may be one of the boards whose state a warp kept: convert it
+    const uint8_t* hit = nullptr;
+    if (best_score >= kSaveMin)
+      for (int w = 0; w < F.n_warps; ++w) {
+        const uint8_t* sv = F.fx_save0 + (size_t)w * F.fx_save_stride;
+        const int16_t* sq = (const int16_t*)(sv + 4);
+        if (*(const int*)sv == best_score && sq[0] == best_quad[0] && sq[1] == best_quad[1] &&
+            sq[2] == best_quad[2] && sq[3] == best_quad[3]) {
+          hit = sv + 16;
+          break;
+        }
+      }
+    if (hit) {
+      BoardState& B = F.bs;
+      const int16_t* sq = (const int16_t*)(hit + 256);
+      for (int i = F.lane; i < best_score * 4; i += 32) B.quads[i] = sq[i];
+      int n_t = 0;
+      for (int base = 0; base < kGWin * kGWin; base += 32) {  // window cell (x + 8) * 16 + (y + 8)
+        const int wc = base + F.lane;
+        const int v = hit[wc];
+        const unsigned m = __ballot_sync(0xffffffffu, v != 0);
+        if (v != 0) {
+          const int ci = cell_index(F, (wc >> 4) - 8, (wc & 15) - 8);
+          B.cell[ci] = v == 0xff ? (int16_t)-1 : (int16_t)v;
+          B.touched[n_t + __popc(m & ((1u << F.lane) - 1u))] = (int16_t)ci;
+        }
+        n_t += __popc(m);
+      }
+      B.n_touched = n_t;
+      B.n_quads = best_score;
+      B.score = best_score;
+      __syncwarp();
+      AGB_TM_ADD(12, 100);
+    } else {
+      board_build(F, F.bs, best_quad);
+    }
     board_fix_missing(F, F.bs);
   }
   AGB_TM_ADD(6, clock64() - t0);
