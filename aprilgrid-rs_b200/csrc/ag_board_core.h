@@ -1074,22 +1074,33 @@ AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
   // tag_affine (image_util.rs:39-70): least-squares affine from the tag frame to the image.
   // The four source corners form a square, so the centred normal equations are diagonal.
   const int side = F.border * 2 + F.edge;
-  const float lo = -0.5f, hi = (float)side - 1.0f + 0.5f;
-  const double sxs[4] = {lo, lo, hi, hi};
-  const double sys[4] = {lo, hi, hi, lo};
-  double mx = 0, my = 0, mcx = 0, mcy = 0;
-  for (int p = 0; p < 4; ++p) { mx += sxs[p]; my += sys[p]; mcx += qx[p]; mcy += qy[p]; }
-  mx /= 4; my /= 4; mcx /= 4; mcy /= 4;
-  double sxx = 0, syy = 0, axx = 0, axy = 0, ayx = 0, ayy = 0;
-  for (int p = 0; p < 4; ++p) {
-    double dx = sxs[p] - mx, dy = sys[p] - my;
-    sxx += dx * dx; syy += dy * dy;
-    axx += dx * qx[p]; axy += dy * qx[p];
-    ayx += dx * qy[p]; ayy += dy * qy[p];
+  float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f, h4 = 0.0f, h5 = 0.0f;
+#if AGB_DEVICE
+  if (F.lane == 0)  // the f64 arithmetic on one lane (FP64 throughput is per lane), then broadcast
+#endif
+  {
+    const float lo = -0.5f, hi = (float)side - 1.0f + 0.5f;
+    const double sxs[4] = {lo, lo, hi, hi};
+    const double sys[4] = {lo, hi, hi, lo};
+    double mx = 0, my = 0, mcx = 0, mcy = 0;
+    for (int p = 0; p < 4; ++p) { mx += sxs[p]; my += sys[p]; mcx += qx[p]; mcy += qy[p]; }
+    mx /= 4; my /= 4; mcx /= 4; mcy /= 4;
+    double sxx = 0, syy = 0, axx = 0, axy = 0, ayx = 0, ayy = 0;
+    for (int p = 0; p < 4; ++p) {
+      double dx = sxs[p] - mx, dy = sys[p] - my;
+      sxx += dx * dx; syy += dy * dy;
+      axx += dx * qx[p]; axy += dy * qx[p];
+      ayx += dx * qy[p]; ayy += dy * qy[p];
+    }
+    const double h0d = axx / sxx, h1d = axy / syy, h3d = ayx / sxx, h4d = ayy / syy;
+    h0 = (float)h0d; h1 = (float)h1d; h2 = (float)(mcx - h0d * mx - h1d * my);
+    h3 = (float)h3d; h4 = (float)h4d; h5 = (float)(mcy - h3d * mx - h4d * my);
   }
-  const double h0d = axx / sxx, h1d = axy / syy, h3d = ayx / sxx, h4d = ayy / syy;
-  const float h0 = (float)h0d, h1 = (float)h1d, h2 = (float)(mcx - h0d * mx - h1d * my);
-  const float h3 = (float)h3d, h4 = (float)h4d, h5 = (float)(mcy - h3d * mx - h4d * my);
+#if AGB_DEVICE
+  h0 = __shfl_sync(0xffffffffu, h0, 0); h1 = __shfl_sync(0xffffffffu, h1, 0);
+  h2 = __shfl_sync(0xffffffffu, h2, 0); h3 = __shfl_sync(0xffffffffu, h3, 0);
+  h4 = __shfl_sync(0xffffffffu, h4, 0); h5 = __shfl_sync(0xffffffffu, h5, 0);
+#endif
   // sample (bit_code :80-93): sample s = (x - border) * edge + (y - border), x outer
   const int ns = F.edge * F.edge;
 #if AGB_DEVICE
@@ -1161,6 +1172,45 @@ AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
 #endif
   // best_tag :142-169
   int id = -1, rot = 0;
+#if AGB_DEVICE
+  {
+    // all four rotations of the pattern first (rotate_bits, one output bit per lane and ballot),
+    // then ONE pass over the code table with the four Hamming distances side by side; per rotation
+    // the smallest (distance, id) -- the reference's first minimum -- by warp reduction; the first
+    // rotation whose best distance is below the limit wins, as in the sequential loop
+    uint64_t br[4];
+    br[0] = bits;
+#pragma unroll
+    for (int r = 1; r < 4; ++r) {
+      uint64_t o = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int count = F.lane + 32 * h;
+        bool b = false;
+        if (count < ns) {
+          const int rr = F.edge - 1 - count / F.edge, cc = count % F.edge;
+          b = (br[r - 1] >> (rr + cc * F.edge)) & 1ull;
+        }
+        o |= (uint64_t)__ballot_sync(0xffffffffu, b) << (32 * h);
+      }
+      br[r] = o;
+    }
+    unsigned key[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    for (int c = F.lane; c < F.n_codes; c += 32) {
+      const uint64_t code = F.codes[c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const unsigned k = ((unsigned)__popcll(code ^ br[r]) << 16) | (unsigned)c;
+        key[r] = k < key[r] ? k : key[r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) key[r] = __reduce_min_sync(0xffffffffu, key[r]);
+#pragma unroll
+    for (int r = 3; r >= 0; --r)
+      if ((int)(key[r] >> 16) < F.hamming) { id = (int)(key[r] & 0xffffu); rot = r; }
+  }
+#else
   for (int rotated = 0; rotated < 4; ++rotated) {
     float bs = 1.0e9f;  // score as float so warp_argmin can be reused; popcount <= 64 is exact
     int bi = kNone;
@@ -1177,6 +1227,7 @@ AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
     if (rotated == 3) break;
     bits = rotate_bits(bits, F.edge);
   }
+#endif
   if (id < 0) return false;
   out->id = (uint32_t)id;
   for (int j = 0; j < 4; ++j) {  // rotate_left(rot) then reverse() (:467-469)
