@@ -260,7 +260,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
       F.tm[0] = (uint32_t)(t_end - t_start);
       F.tm[11] = (uint32_t)n_refined[f];
-      F.tm[12] = (uint32_t)F.fast_on;
+      F.tm[12] |= (uint32_t)F.fast_on << 31;
     }
     n_out[f] = n;
     uint32_t st = F.status;

@@ -1255,6 +1255,9 @@ AGB_FN void detect_boards(Frame& F, int max_boards) {
     const int found = find_best_board(F);
 #endif
     if (found < 0) continue;  // block-uniform
+#if AGB_DEVICE
+    const long long t_dec = clock64();
+#endif
     if (F.warp == 0) {
       BoardState& B = F.bs;
       for (int i = F.lane; i < F.n; i += AGB_LANES) F.remove[i] = 0;
@@ -1321,6 +1324,9 @@ AGB_FN void detect_boards(Frame& F, int max_boards) {
         n_new += cnt;
       }
       if (F.lane == 0) F.ctl[1] = n_new;
+#if AGB_DEVICE
+      if (F.tm && F.lane == 0) F.tm[12] += (uint32_t)(clock64() - t_dec) & 0x7fffffffu;
+#endif
     }
     // saddle indices changed: every warp forgets its board
     if (!F.fast_on) board_reset(F, F.bs);

@@ -44,7 +44,8 @@ print("phase cycles per frame (mean, share of instrumented):")
 for k, nm in names.items():
     print("  %-30s %10.0f  %5.1f%%" % (nm, t[:, k].mean(), 100.0 * t[:, k].sum() / tot.sum()))
 print("  seeds processed %.1f  quads scored %.1f  redo batches %.2f  saddles %.0f  fast %.2f"
-      % (t[:, 8].mean(), t[:, 9].mean(), t[:, 10].mean(), t[:, 11].mean(), t[:, 12].mean()))
+      % (t[:, 8].mean(), t[:, 9].mean(), t[:, 10].mean(), t[:, 11].mean(), (t[:, 12].astype(np.uint32) >> 31).mean()))
+print("  decode + removal of used saddles: %.0f cycles per frame" % (t[:, 12].astype(np.uint32) & 0x7fffffff).mean())
 print("  lockstep iterations %.0f  expansion attempts %.0f (%.2f groups / iteration)  tuple passes %.0f"
       % (t[:, 13].mean(), t[:, 14].mean(), t[:, 14].sum() / max(t[:, 13].sum(), 1), t[:, 15].mean()))
 print("  lockstep cycles: take-work %.0f  advance %.0f  queries %.0f  tuples %.0f  (per frame, warp 0)"
