@@ -1243,6 +1243,105 @@ AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
 // Every warp of the frame's block calls it; warp 0 decodes and compacts.
 #if AGB_DEVICE
 __device__ int find_best_board_fast(Frame& F);  // ag_board_fast.cuh
+
+// Device decode, phase 1: ONE LANE per quad.  decode_positions + tag_affine + bit_code
+// (detector.rs:42-122) up to the bit pattern; returns the pattern with bit 63 set, or 0 when the
+// quad is rejected.  32 quads run side by side, which hides the f64 arithmetic of the affine fit
+// and the memory latency of the 36 samples that a whole warp per quad would wait for serially.
+__device__ __noinline__ uint64_t decode_bits_lane(const Frame& F, int q0, int q1, int q2, int q3) {
+  const float qx[4] = {F.sx[q0], F.sx[q1], F.sx[q2], F.sx[q3]};
+  const float qy[4] = {F.sy[q0], F.sy[q1], F.sy[q2], F.sy[q3]};
+  for (int j = 0; j < 4; ++j) {  // decode_positions :50-56
+    const uint32_t x = sat_u32(roundf(qx[j])), y = sat_u32(roundf(qy[j]));
+    if (x >= (uint32_t)F.w || y >= (uint32_t)F.h) return 0ull;
+  }
+  // tag_affine (image_util.rs:39-70), same arithmetic as decode_quad
+  const int side = F.border * 2 + F.edge;
+  const float lo = -0.5f, hi = (float)side - 1.0f + 0.5f;
+  const double sxs[4] = {lo, lo, hi, hi};
+  const double sys[4] = {lo, hi, hi, lo};
+  double mx = 0, my = 0, mcx = 0, mcy = 0;
+  for (int p = 0; p < 4; ++p) { mx += sxs[p]; my += sys[p]; mcx += qx[p]; mcy += qy[p]; }
+  mx /= 4; my /= 4; mcx /= 4; mcy /= 4;
+  double sxx = 0, syy = 0, axx = 0, axy = 0, ayx = 0, ayy = 0;
+  for (int p = 0; p < 4; ++p) {
+    double dx = sxs[p] - mx, dy = sys[p] - my;
+    sxx += dx * dx; syy += dy * dy;
+    axx += dx * qx[p]; axy += dy * qx[p];
+    ayx += dx * qy[p]; ayy += dy * qy[p];
+  }
+  const double h0d = axx / sxx, h1d = axy / syy, h3d = ayx / sxx, h4d = ayy / syy;
+  const float h0 = (float)h0d, h1 = (float)h1d, h2 = (float)(mcx - h0d * mx - h1d * my);
+  const float h3 = (float)h3d, h4 = (float)h4d, h5 = (float)(mcy - h3d * mx - h4d * my);
+  // bit_code :80-122; sample s = (x - border) * edge + (y - border), x outer; two passes over the
+  // samples (the second one hits the cache): min / max, then the bits
+  int min_b = 255, max_b = 0;
+  for (int ix = 0; ix < F.edge; ++ix)
+    for (int iy = 0; iy < F.edge; ++iy) {
+      const float fx = (float)(F.border + ix), fy = (float)(F.border + iy);
+      const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
+      const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
+      const uint32_t x = sat_u32(roundf(px)), y = sat_u32(roundf(py));
+      if (x >= (uint32_t)F.w || y >= (uint32_t)F.h) return 0ull;  // a sample outside the image
+      const int v = luma8_at(F, x, y);
+      min_b = v < min_b ? v : min_b;
+      max_b = v > max_b ? v : max_b;
+    }
+  if (max_b - min_b < 50) return 0ull;  // :97
+  const int mid_b = (int)sat_u32(roundf(fdiv(fadd((float)min_b, (float)max_b), 2.0f)));
+  uint64_t bits = 0;
+  int invalid = 0;
+  const int ns = F.edge * F.edge;
+  int sidx = 0;
+  for (int ix = 0; ix < F.edge; ++ix)
+    for (int iy = 0; iy < F.edge; ++iy, ++sidx) {
+      const float fx = (float)(F.border + ix), fy = (float)(F.border + iy);
+      const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
+      const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
+      const int v = luma8_at(F, sat_u32(roundf(px)), sat_u32(roundf(py)));
+      const int dlt = mid_b - v;
+      if ((dlt < 0 ? -dlt : dlt) < 10) ++invalid;
+      if (v > mid_b) bits |= 1ull << (ns - 1 - sidx);  // the first sample is the most significant bit
+    }
+  if (invalid > 3) return 0ull;
+  return bits | (1ull << 63);
+}
+
+// Device decode, phase 2: best_tag (detector.rs:142-169) for one pattern on the whole warp.
+// Returns the id (and the rotation) or -1.
+__device__ __noinline__ int best_tag_warp(const Frame& F, uint64_t bits, int* rot_out) {
+  const int ns = F.edge * F.edge;
+  uint64_t br[4];
+  br[0] = bits;
+  int src[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // rotate_bits: output bit `count` <- input bit r + c * edge
+    const int count = F.lane + 32 * h;
+    src[h] = count < ns ? (F.edge - 1 - count / F.edge) + (count % F.edge) * F.edge : -1;
+  }
+#pragma unroll
+  for (int r = 1; r < 4; ++r) {
+    const unsigned lo = __ballot_sync(0xffffffffu, src[0] >= 0 && ((br[r - 1] >> src[0]) & 1ull));
+    const unsigned hi = __ballot_sync(0xffffffffu, src[1] >= 0 && ((br[r - 1] >> src[1]) & 1ull));
+    br[r] = (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+  unsigned key[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+  for (int c = F.lane; c < F.n_codes; c += 32) {
+    const uint64_t code = F.codes[c];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const unsigned k = ((unsigned)__popcll(code ^ br[r]) << 16) | (unsigned)c;
+      key[r] = k < key[r] ? k : key[r];
+    }
+  }
+  int id = -1;
+#pragma unroll
+  for (int r = 3; r >= 0; --r) {
+    const unsigned k = __reduce_min_sync(0xffffffffu, key[r]);
+    if ((int)(k >> 16) < F.hamming) { id = (int)(k & 0xffffu); *rot_out = r; }
+  }
+  return id;
+}
 #endif
 AGB_FN void detect_boards(Frame& F, int max_boards) {
   for (int round = 0; round < max_boards; ++round) {
@@ -1265,7 +1364,57 @@ AGB_FN void detect_boards(Frame& F, int max_boards) {
       int n_tap = 0;
       // all_tag_indexes in ascending (x, y) order
       const int n_cells = F.lat * F.lat;
+#if AGB_DEVICE
+      // (1) the board's quads in visiting order -> list (the seed-best arrays are free here)
+      int16_t* qlist = F.seedbest.quads;
+      uint64_t* qbits = (uint64_t*)F.seedbest.vals;
+      int n_list = 0;
+      for (int base = 0; base < n_cells; base += 32) {
+        const int cv = F.bs.cell[base + F.lane];
+        const unsigned m = __ballot_sync(0xffffffffu, cv > 0);
+        if (cv > 0) {
+          const int dst = n_list + __popc(m & ((1u << F.lane) - 1u));
+          for (int j = 0; j < 4; ++j) qlist[4 * dst + j] = B.quads[(cv - 1) * 4 + j];
+        }
+        n_list += __popc(m);
+      }
+      __syncwarp();
+      if (round == 0 && F.tap_quads) {
+        for (int i = F.lane; i < n_list && i < F.tap_cap; i += 32)
+          for (int j = 0; j < 4; ++j) F.tap_quads[i * 4 + j] = qlist[4 * i + j];
+        n_tap = n_list;
+      }
+      // (2) one lane per quad: positions, affine fit, samples, bit pattern
+      for (int base = 0; base < n_list; base += 32) {
+        const int i = base + F.lane;
+        if (i < n_list) qbits[i] = decode_bits_lane(F, qlist[4 * i], qlist[4 * i + 1], qlist[4 * i + 2], qlist[4 * i + 3]);
+      }
+      __syncwarp();
+      // (3) in visiting order: code-table search on the whole warp, result map (a repeated id overwrites)
+      for (int i = 0; i < n_list; ++i) {
+        const uint64_t b = qbits[i];
+        if (!(b >> 63)) continue;  // warp-uniform
+        int rot = 0;
+        const int id = best_tag_warp(F, b & ~(1ull << 63), &rot);
+        if (id < 0) continue;
+        if (F.lane == 0) {
+          TagRec t;
+          t.id = (uint32_t)id;
+          for (int j = 0; j < 4; ++j) {  // rotate_left(rot) then reverse() (:467-469)
+            const int sq = qlist[4 * i + (((3 - j) + rot) & 3)];
+            t.xy[2 * j] = F.sx[sq];
+            t.xy[2 * j + 1] = F.sy[sq];
+          }
+          F.tag_by_id[t.id] = t;
+          F.tag_valid[t.id] = 1;
+          for (int j = 0; j < 4; ++j) F.remove[qlist[4 * i + j]] = 1;
+        }
+        __syncwarp();
+      }
+      for (int base = n_cells; base < n_cells; base += AGB_LANES) {  // (host loop below, not used on the device)
+#else
       for (int base = 0; base < n_cells; base += AGB_LANES) {
+#endif
         const int ci = base + F.lane;
         unsigned m = agb_ballot(B.cell[ci] > 0);
         while (m) {
