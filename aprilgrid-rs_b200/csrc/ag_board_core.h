@@ -1273,35 +1273,45 @@ __device__ __noinline__ uint64_t decode_bits_lane(const Frame& F, int q0, int q1
   const double h0d = axx / sxx, h1d = axy / syy, h3d = ayx / sxx, h4d = ayy / syy;
   const float h0 = (float)h0d, h1 = (float)h1d, h2 = (float)(mcx - h0d * mx - h1d * my);
   const float h3 = (float)h3d, h4 = (float)h4d, h5 = (float)(mcy - h3d * mx - h4d * my);
-  // bit_code :80-122; sample s = (x - border) * edge + (y - border), x outer; two passes over the
-  // samples (the second one hits the cache): min / max, then the bits
+  // bit_code :80-122; sample s = (x - border) * edge + (y - border), x outer.  All (up to 36)
+  // samples are loaded first, with no use in between, so their memory latencies overlap.
+  const int ns = F.edge * F.edge;
+  int v[36];
+  bool oob = false;
+  {
+    int ix = 0, iy = 0;
+#pragma unroll
+    for (int sidx = 0; sidx < 36; ++sidx) {
+      v[sidx] = 0;
+      if (sidx < ns) {
+        const float fx = (float)(F.border + ix), fy = (float)(F.border + iy);
+        const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
+        const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
+        const uint32_t x = sat_u32(roundf(px)), y = sat_u32(roundf(py));
+        if (x < (uint32_t)F.w && y < (uint32_t)F.h) v[sidx] = luma8_at(F, x, y);
+        else oob = true;  // a sample outside the image
+        if (++iy == F.edge) { iy = 0; ++ix; }
+      }
+    }
+  }
+  if (oob) return 0ull;
   int min_b = 255, max_b = 0;
-  for (int ix = 0; ix < F.edge; ++ix)
-    for (int iy = 0; iy < F.edge; ++iy) {
-      const float fx = (float)(F.border + ix), fy = (float)(F.border + iy);
-      const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
-      const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
-      const uint32_t x = sat_u32(roundf(px)), y = sat_u32(roundf(py));
-      if (x >= (uint32_t)F.w || y >= (uint32_t)F.h) return 0ull;  // a sample outside the image
-      const int v = luma8_at(F, x, y);
-      min_b = v < min_b ? v : min_b;
-      max_b = v > max_b ? v : max_b;
+#pragma unroll
+  for (int sidx = 0; sidx < 36; ++sidx)
+    if (sidx < ns) {
+      min_b = v[sidx] < min_b ? v[sidx] : min_b;
+      max_b = v[sidx] > max_b ? v[sidx] : max_b;
     }
   if (max_b - min_b < 50) return 0ull;  // :97
   const int mid_b = (int)sat_u32(roundf(fdiv(fadd((float)min_b, (float)max_b), 2.0f)));
   uint64_t bits = 0;
   int invalid = 0;
-  const int ns = F.edge * F.edge;
-  int sidx = 0;
-  for (int ix = 0; ix < F.edge; ++ix)
-    for (int iy = 0; iy < F.edge; ++iy, ++sidx) {
-      const float fx = (float)(F.border + ix), fy = (float)(F.border + iy);
-      const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
-      const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
-      const int v = luma8_at(F, sat_u32(roundf(px)), sat_u32(roundf(py)));
-      const int dlt = mid_b - v;
+#pragma unroll
+  for (int sidx = 0; sidx < 36; ++sidx)
+    if (sidx < ns) {
+      const int dlt = mid_b - v[sidx];
       if ((dlt < 0 ? -dlt : dlt) < 10) ++invalid;
-      if (v > mid_b) bits |= 1ull << (ns - 1 - sidx);  // the first sample is the most significant bit
+      if (v[sidx] > mid_b) bits |= 1ull << (ns - 1 - sidx);  // the first sample is the most significant bit
     }
   if (invalid > 3) return 0ull;
   return bits | (1ull << 63);
