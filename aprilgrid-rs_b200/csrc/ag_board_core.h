@@ -1320,14 +1320,16 @@ __device__ __noinline__ uint64_t decode_bits_lane(const Frame& F, int q0, int q1
 // Device decode, phase 2: best_tag (detector.rs:142-169) for one pattern on the whole warp.
 // Returns the id (and the rotation) or -1.
 __device__ __noinline__ int best_tag_warp(const Frame& F, uint64_t bits, int* rot_out) {
-  const int ns = F.edge * F.edge;
+  const uint64_t* __restrict__ codes = F.codes;  // the frame's fields, once (F lives in local memory)
+  const int n_codes = F.n_codes, hamming = F.hamming, edge = F.edge, lane = F.lane;
+  const int ns = edge * edge;
   uint64_t br[4];
   br[0] = bits;
   int src[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {  // rotate_bits: output bit `count` <- input bit r + c * edge
-    const int count = F.lane + 32 * h;
-    src[h] = count < ns ? (F.edge - 1 - count / F.edge) + (count % F.edge) * F.edge : -1;
+    const int count = lane + 32 * h;
+    src[h] = count < ns ? (edge - 1 - count / edge) + (count % edge) * edge : -1;
   }
 #pragma unroll
   for (int r = 1; r < 4; ++r) {
@@ -1336,8 +1338,9 @@ __device__ __noinline__ int best_tag_warp(const Frame& F, uint64_t bits, int* ro
     br[r] = (uint64_t)lo | ((uint64_t)hi << 32);
   }
   unsigned key[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-  for (int c = F.lane; c < F.n_codes; c += 32) {
-    const uint64_t code = F.codes[c];
+#pragma unroll 4
+  for (int c = lane; c < n_codes; c += 32) {
+    const uint64_t code = __ldg(codes + c);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const unsigned k = ((unsigned)__popcll(code ^ br[r]) << 16) | (unsigned)c;
@@ -1348,7 +1351,7 @@ __device__ __noinline__ int best_tag_warp(const Frame& F, uint64_t bits, int* ro
 #pragma unroll
   for (int r = 3; r >= 0; --r) {
     const unsigned k = __reduce_min_sync(0xffffffffu, key[r]);
-    if ((int)(k >> 16) < F.hamming) { id = (int)(k & 0xffffu); *rot_out = r; }
+    if ((int)(k >> 16) < hamming) { id = (int)(k & 0xffffu); *rot_out = r; }
   }
   return id;
 }
