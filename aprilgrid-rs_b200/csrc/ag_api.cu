@@ -848,7 +848,20 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
   bool truncated = false;
   struct Pending { int f0, n; bool live; } pend[kBoardSlots] = {};
   int first = det->slot_rr, used = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+  // Chunk schedule: the pipeline fills while the first chunk uploads and drains while the last one
+  // is searched, so a large batch starts and ends with quarter and half chunks.
+  auto next_chunk = [&](int f0) {
+    const int left = n_frames - f0;
+    if (n_frames < 4 * chunk) return std::min(chunk, left);
+    if (f0 == 0) return chunk / 4 > 0 ? chunk / 4 : 1;
+    if (f0 < chunk) return std::min(chunk / 2 > 0 ? chunk / 2 : 1, left);
+    if (left <= chunk / 4) return left;
+    if (left <= chunk / 4 + chunk / 2) return std::min(left - chunk / 4 > 0 ? left - chunk / 4 : left, left);
+    if (left < chunk + chunk / 4 + chunk / 2) return left - (chunk / 4 + chunk / 2);
+    return chunk;
+  };
+  for (int f0 = 0, n_this = 0; f0 < n_frames; f0 += n_this) {
+    n_this = next_chunk(f0);
     const int bi = det->slot_rr;
     BoardSlot& B = det->bslot[bi];
     det->slot_rr = (det->slot_rr + 1) % kBoardSlots;
@@ -860,7 +873,7 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
     }
     if ((rc = ensure_board_slot(det, B, chunk, true))) return rc;
     if ((rc = ensure_host_stage(det, B, chunk_bytes, chunk, cap_per_frame))) return rc;
-    const int n = std::min(chunk, n_frames - f0);
+    const int n = n_this;
     const uint8_t* src = (const uint8_t*)frames + (size_t)f0 * g.frame_stride;
     const size_t bytes = (size_t)(n - 1) * g.frame_stride + g.row_stride * (size_t)(g.h - 1) +
                          (size_t)g.w * bytes_per_px(g.format);
