@@ -122,6 +122,7 @@ struct Frame {
   int lane;  // 0 on host
   // throughput path (device only, ag_board_fast.cuh); unused when fast_on == 0
   int fast_on;
+  int round;             // board round being searched (0 = first board)
   uint16_t* g_base;      // unshifted bucket-grid array ([cells + 2])
   float2* g_pos;         // [n] saddle positions in g_item order (one load per scanned candidate)
   int active_words;      // words of bs.active
@@ -1362,6 +1363,7 @@ AGB_FN void detect_boards(Frame& F, int max_boards) {
     agb_work_counters[31] = round;
 #endif
 #if AGB_DEVICE
+    F.round = round;
     const int found = F.fast_on ? find_best_board_fast(F) : find_best_board(F);
 #else
     const int found = find_best_board(F);

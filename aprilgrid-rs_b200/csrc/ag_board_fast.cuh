@@ -780,7 +780,11 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
   int seeds_left = F.ctl[0];
   F.g_on = F.ctl[5];
   if (F.g_on) F.g_start = F.g_base + 1;
-  int best_score = 0, count = 0, wave = F.n_warps > 1 ? 2 : 1;
+  // first wave: two seeds (the first board is usually found by the first or second seed); after the
+  // first board the leftovers rarely hold another one and every seed will be visited, so a block
+  // with many warps (latency mode) starts with one seed per warp
+  int best_score = 0, count = 0;
+  int wave = (F.round > 0 && F.n_warps > 2) ? F.n_warps : (F.n_warps > 1 ? 2 : 1);
   int best_quad[4] = {0, 0, 0, 0};
   SeedEnum E;
   while (seeds_left > 0 && count < 30 && best_score < 36) {
