@@ -31,6 +31,12 @@
 struct float2 { float x, y; };  // host test build: the CUDA vector type is not available
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define AGB_UNROLL _Pragma("unroll")
+#else
+#define AGB_UNROLL
+#endif
+
 #if defined(__CUDACC__)
 #define AGB_FN __host__ __device__ inline
 #define AGB_NOINLINE __host__ __device__ __noinline__
@@ -1060,196 +1066,11 @@ AGB_FN uint64_t rotate_bits(uint64_t bits, int edge) {
   return b;
 }
 
-// try_decode_quad: on success fills *out (id + rotated, reversed corners).
-AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
-  float qx[4], qy[4];
-  for (int j = 0; j < 4; ++j) {
-    qx[j] = F.sx[q[j]];
-    qy[j] = F.sy[q[j]];
-  }
-  // decode_positions :50-56
-  for (int j = 0; j < 4; ++j) {
-    uint32_t x = sat_u32(roundf(qx[j])), y = sat_u32(roundf(qy[j]));
-    if (x >= (uint32_t)F.w || y >= (uint32_t)F.h) return false;
-  }
-  // tag_affine (image_util.rs:39-70): least-squares affine from the tag frame to the image.
-  // The four source corners form a square, so the centred normal equations are diagonal.
-  const int side = F.border * 2 + F.edge;
-  float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f, h4 = 0.0f, h5 = 0.0f;
-#if AGB_DEVICE
-  if (F.lane == 0)  // the f64 arithmetic on one lane (FP64 throughput is per lane), then broadcast
-#endif
-  {
-    const float lo = -0.5f, hi = (float)side - 1.0f + 0.5f;
-    const double sxs[4] = {lo, lo, hi, hi};
-    const double sys[4] = {lo, hi, hi, lo};
-    double mx = 0, my = 0, mcx = 0, mcy = 0;
-    for (int p = 0; p < 4; ++p) { mx += sxs[p]; my += sys[p]; mcx += qx[p]; mcy += qy[p]; }
-    mx /= 4; my /= 4; mcx /= 4; mcy /= 4;
-    double sxx = 0, syy = 0, axx = 0, axy = 0, ayx = 0, ayy = 0;
-    for (int p = 0; p < 4; ++p) {
-      double dx = sxs[p] - mx, dy = sys[p] - my;
-      sxx += dx * dx; syy += dy * dy;
-      axx += dx * qx[p]; axy += dy * qx[p];
-      ayx += dx * qy[p]; ayy += dy * qy[p];
-    }
-    const double h0d = axx / sxx, h1d = axy / syy, h3d = ayx / sxx, h4d = ayy / syy;
-    h0 = (float)h0d; h1 = (float)h1d; h2 = (float)(mcx - h0d * mx - h1d * my);
-    h3 = (float)h3d; h4 = (float)h4d; h5 = (float)(mcy - h3d * mx - h4d * my);
-  }
-#if AGB_DEVICE
-  h0 = __shfl_sync(0xffffffffu, h0, 0); h1 = __shfl_sync(0xffffffffu, h1, 0);
-  h2 = __shfl_sync(0xffffffffu, h2, 0); h3 = __shfl_sync(0xffffffffu, h3, 0);
-  h4 = __shfl_sync(0xffffffffu, h4, 0); h5 = __shfl_sync(0xffffffffu, h5, 0);
-#endif
-  // sample (bit_code :80-93): sample s = (x - border) * edge + (y - border), x outer
-  const int ns = F.edge * F.edge;
-#if AGB_DEVICE
-  uint64_t bits = 0;
-  {
-    // Device: lane s holds sample s (and s + 32); min / max by warp reduction, the bit pattern and
-    // the count of undecided samples by ballot (first sample = most significant bit, :101).
-    int v[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int s = F.lane + 32 * h;
-      v[h] = -2;  // no such sample
-      if (s < ns) {
-        const float fx = (float)(F.border + s / F.edge), fy = (float)(F.border + s % F.edge);
-        const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
-        const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
-        const uint32_t x = sat_u32(roundf(px)), y = sat_u32(roundf(py));
-        v[h] = (x < (uint32_t)F.w && y < (uint32_t)F.h) ? luma8_at(F, x, y) : -1;
-      }
-    }
-    if (__any_sync(0xffffffffu, v[0] == -1 || v[1] == -1)) return false;  // a sample outside the image
-    const int lo0 = v[0] >= 0 ? v[0] : 255, lo1 = v[1] >= 0 ? v[1] : 255;
-    const int hi0 = v[0] >= 0 ? v[0] : 0, hi1 = v[1] >= 0 ? v[1] : 0;
-    const int min_b = __reduce_min_sync(0xffffffffu, lo0 < lo1 ? lo0 : lo1);
-    const int max_b = __reduce_max_sync(0xffffffffu, hi0 > hi1 ? hi0 : hi1);
-    if (max_b - min_b < 50) return false;  // :97
-    const int mid_b = (int)sat_u32(roundf(fdiv(fadd((float)min_b, (float)max_b), 2.0f)));
-    auto near_mid = [&](int x) { const int d = mid_b - x; return x >= 0 && (d < 0 ? -d : d) < 10; };
-    const int invalid = __popc(__ballot_sync(0xffffffffu, near_mid(v[0]))) +
-                        __popc(__ballot_sync(0xffffffffu, near_mid(v[1])));
-    if (invalid > 3) return false;
-    const uint64_t set = (uint64_t)__ballot_sync(0xffffffffu, v[0] > mid_b) |
-                         ((uint64_t)__ballot_sync(0xffffffffu, v[1] >= 0 && v[1] > mid_b) << 32);
-    bits = __brevll(set) >> (64 - ns);  // sample s -> bit ns - 1 - s
-  }
-#else
-  for (int s = F.lane; s < ns; s += AGB_LANES) {
-    const float fx = (float)(F.border + s / F.edge), fy = (float)(F.border + s % F.edge);
-    const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
-    const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
-    const uint32_t x = sat_u32(roundf(px)), y = sat_u32(roundf(py));
-    int v = -1;
-    if (x < (uint32_t)F.w && y < (uint32_t)F.h) v = luma8_at(F, x, y);
-    F.samp[s] = (int16_t)v;
-  }
-  AGB_SYNC();
-  int min_b = 255, max_b = 0;
-  bool oob = false;
-  for (int s = 0; s < ns; ++s) {
-    const int v = F.samp[s];
-    if (v < 0) oob = true;
-    min_b = v < min_b ? v : min_b;
-    max_b = v > max_b ? v : max_b;
-  }
-  AGB_SYNC();
-  if (oob) return false;
-  if (max_b - min_b < 50) return false;  // :97
-  const int mid_b = (int)sat_u32(roundf(fdiv(fadd((float)min_b, (float)max_b), 2.0f)));
-  uint64_t bits = 0;
-  int invalid = 0;
-  for (int i = 0; i < ns; ++i) {  // iter().rev().enumerate(): the last sample is bit 0
-    const int v = F.samp[ns - 1 - i];
-    const int dlt = mid_b - v;
-    if ((dlt < 0 ? -dlt : dlt) < 10) ++invalid;
-    if (v > mid_b) bits |= (1ull << i);
-  }
-  AGB_SYNC();
-  if (invalid > 3) return false;
-#endif
-  // best_tag :142-169
-  int id = -1, rot = 0;
-#if AGB_DEVICE
-  {
-    // all four rotations of the pattern first (rotate_bits, one output bit per lane and ballot),
-    // then ONE pass over the code table with the four Hamming distances side by side; per rotation
-    // the smallest (distance, id) -- the reference's first minimum -- by warp reduction; the first
-    // rotation whose best distance is below the limit wins, as in the sequential loop
-    uint64_t br[4];
-    br[0] = bits;
-#pragma unroll
-    for (int r = 1; r < 4; ++r) {
-      uint64_t o = 0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int count = F.lane + 32 * h;
-        bool b = false;
-        if (count < ns) {
-          const int rr = F.edge - 1 - count / F.edge, cc = count % F.edge;
-          b = (br[r - 1] >> (rr + cc * F.edge)) & 1ull;
-        }
-        o |= (uint64_t)__ballot_sync(0xffffffffu, b) << (32 * h);
-      }
-      br[r] = o;
-    }
-    unsigned key[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-    for (int c = F.lane; c < F.n_codes; c += 32) {
-      const uint64_t code = F.codes[c];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const unsigned k = ((unsigned)__popcll(code ^ br[r]) << 16) | (unsigned)c;
-        key[r] = k < key[r] ? k : key[r];
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) key[r] = __reduce_min_sync(0xffffffffu, key[r]);
-#pragma unroll
-    for (int r = 3; r >= 0; --r)
-      if ((int)(key[r] >> 16) < F.hamming) { id = (int)(key[r] & 0xffffu); rot = r; }
-  }
-#else
-  for (int rotated = 0; rotated < 4; ++rotated) {
-    float bs = 1.0e9f;  // score as float so warp_argmin can be reused; popcount <= 64 is exact
-    int bi = kNone;
-    for (int c = F.lane; c < F.n_codes; c += AGB_LANES) {
-      const float sc = (float)agb_popcll(F.codes[c] ^ bits);
-      if (nn_less(sc, c, bs, bi)) { bs = sc; bi = c; }
-    }
-    warp_argmin(bs, bi);
-    if (bs < (float)F.hamming) {
-      id = bi;
-      rot = rotated;
-      break;
-    }
-    if (rotated == 3) break;
-    bits = rotate_bits(bits, F.edge);
-  }
-#endif
-  if (id < 0) return false;
-  out->id = (uint32_t)id;
-  for (int j = 0; j < 4; ++j) {  // rotate_left(rot) then reverse() (:467-469)
-    const int src = ((3 - j) + rot) & 3;
-    out->xy[2 * j] = qx[src];
-    out->xy[2 * j + 1] = qy[src];
-  }
-  return true;
-}
-
-// TagDetector::detect from the refined saddle list on (detector.rs:510-538).
-// Workspace must be initialised by the caller: cells 0, active bits 1, tag_valid 0, counters 0.
-// Every warp of the frame's block calls it; warp 0 decodes and compacts.
-#if AGB_DEVICE
-__device__ int find_best_board_fast(Frame& F);  // ag_board_fast.cuh
-
-// Device decode, phase 1: ONE LANE per quad.  decode_positions + tag_affine + bit_code
+// Decode, phase 1: ONE LANE per quad (on the device; the host test build runs the same code).  decode_positions + tag_affine + bit_code
 // (detector.rs:42-122) up to the bit pattern; returns the pattern with bit 63 set, or 0 when the
 // quad is rejected.  32 quads run side by side, which hides the f64 arithmetic of the affine fit
 // and the memory latency of the 36 samples that a whole warp per quad would wait for serially.
-__device__ __noinline__ uint64_t decode_bits_lane(const Frame& F, int q0, int q1, int q2, int q3) {
+AGB_NOINLINE uint64_t decode_bits_lane(const Frame& F, int q0, int q1, int q2, int q3) {
   const float qx[4] = {F.sx[q0], F.sx[q1], F.sx[q2], F.sx[q3]};
   const float qy[4] = {F.sy[q0], F.sy[q1], F.sy[q2], F.sy[q3]};
   for (int j = 0; j < 4; ++j) {  // decode_positions :50-56
@@ -1281,7 +1102,7 @@ __device__ __noinline__ uint64_t decode_bits_lane(const Frame& F, int q0, int q1
   bool oob = false;
   {
     int ix = 0, iy = 0;
-#pragma unroll
+AGB_UNROLL
     for (int sidx = 0; sidx < 36; ++sidx) {
       v[sidx] = 0;
       if (sidx < ns) {
@@ -1297,7 +1118,7 @@ __device__ __noinline__ uint64_t decode_bits_lane(const Frame& F, int q0, int q1
   }
   if (oob) return 0ull;
   int min_b = 255, max_b = 0;
-#pragma unroll
+AGB_UNROLL
   for (int sidx = 0; sidx < 36; ++sidx)
     if (sidx < ns) {
       min_b = v[sidx] < min_b ? v[sidx] : min_b;
@@ -1307,7 +1128,7 @@ __device__ __noinline__ uint64_t decode_bits_lane(const Frame& F, int q0, int q1
   const int mid_b = (int)sat_u32(roundf(fdiv(fadd((float)min_b, (float)max_b), 2.0f)));
   uint64_t bits = 0;
   int invalid = 0;
-#pragma unroll
+AGB_UNROLL
   for (int sidx = 0; sidx < 36; ++sidx)
     if (sidx < ns) {
       const int dlt = mid_b - v[sidx];
@@ -1317,6 +1138,43 @@ __device__ __noinline__ uint64_t decode_bits_lane(const Frame& F, int q0, int q1
   if (invalid > 3) return 0ull;
   return bits | (1ull << 63);
 }
+
+// try_decode_quad for the host test build: the bit pattern by decode_bits_lane (the very function
+// the device runs, one lane per quad), then best_tag as a plain loop (the device searches the code
+// table with best_tag_warp below: all four rotations in one pass, same first-minimum rule).
+// On success fills *out (id + rotated, reversed corners).
+AGB_NOINLINE bool decode_quad(Frame& F, const int q[4], TagRec* out) {
+  const uint64_t packed = decode_bits_lane(F, q[0], q[1], q[2], q[3]);
+  if (!(packed >> 63)) return false;
+  uint64_t bits = packed & ~(1ull << 63);
+  // best_tag :142-169
+  int id = -1, rot = 0;
+  for (int rotated = 0; rotated < 4; ++rotated) {
+    int bs = 1000, bi = kNone;
+    for (int c = 0; c < F.n_codes; ++c) {
+      const int sc = agb_popcll(F.codes[c] ^ bits);
+      if (sc < bs) { bs = sc; bi = c; }  // first minimum
+    }
+    if (bs < F.hamming) {
+      id = bi;
+      rot = rotated;
+      break;
+    }
+    if (rotated == 3) break;
+    bits = rotate_bits(bits, F.edge);
+  }
+  if (id < 0) return false;
+  out->id = (uint32_t)id;
+  for (int j = 0; j < 4; ++j) {  // rotate_left(rot) then reverse() (:467-469)
+    const int src = ((3 - j) + rot) & 3;
+    out->xy[2 * j] = F.sx[q[src]];
+    out->xy[2 * j + 1] = F.sy[q[src]];
+  }
+  return true;
+}
+
+#if AGB_DEVICE
+__device__ int find_best_board_fast(Frame& F);  // ag_board_fast.cuh
 
 // Device decode, phase 2: best_tag (detector.rs:142-169) for one pattern on the whole warp.
 // Returns the id (and the rotation) or -1.
@@ -1426,10 +1284,9 @@ AGB_FN void detect_boards(Frame& F, int max_boards) {
         }
         __syncwarp();
       }
-      for (int base = n_cells; base < n_cells; base += AGB_LANES) {  // (host loop below, not used on the device)
 #else
+      // host test build (one lane): quad after quad through decode_quad
       for (int base = 0; base < n_cells; base += AGB_LANES) {
-#endif
         const int ci = base + F.lane;
         unsigned m = agb_ballot(B.cell[ci] > 0);
         while (m) {
@@ -1455,6 +1312,7 @@ AGB_FN void detect_boards(Frame& F, int max_boards) {
           }
         }
       }
+#endif
       if (round == 0 && F.tap_n_quads && F.lane == 0) *F.tap_n_quads = n_tap;
       AGB_SYNC();
       // refined.retain(not removed), order kept (:526-536).  In-place, order-preserving
