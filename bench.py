@@ -92,6 +92,30 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and so the first-touch placement of its pinned staging
+    buffers) to the NUMA node its GPU hangs off: with one rank per GPU the host-to-device traffic
+    of all ranks otherwise funnels through whatever node the ranks happened to start on."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args):
     """The reference's CPU path (oracle port of aprilgrid-rs detect), frame-parallel on all cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -159,6 +183,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         # NCCL prints its version banner on stdout at the first collective; keep stdout for the
         # single JSON line by pointing fd 1 at stderr until the communicator exists.
@@ -293,7 +318,8 @@ def main():
         e2e = {"value": world * B * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(world * B * W * H),
                "d2h_bytes_per_step": int(world * B * (cap * 36 + 8)),
-               "timing": "host wall clock around ag_detect_batch, pinned host frames, max over ranks"}
+               "timing": "host wall clock around ag_detect_batch, pinned host frames, max over ranks",
+               "numa_node_of_rank0": numa_node}
 
     # final gather of detections to host: counts only (the records are already on each rank's host)
     total_tags = int(cnt_host.sum()) if cnt_host is not None else 0
