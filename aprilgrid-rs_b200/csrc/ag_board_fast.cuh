@@ -699,7 +699,9 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
         }
         E.cand[h] = m;
       }
-      E.a_open = true;
+      // most diagonals leave no pair at all: nothing to queue
+      E.a_open = __any_sync(0xffffffffu, (E.cand[0] | E.cand[1]) != 0ull);
+      if (!E.a_open) continue;
     }
     // queue the open entry's pairs in combinations(2) order (i ascending, then j ascending), as
     // many as the ring holds
