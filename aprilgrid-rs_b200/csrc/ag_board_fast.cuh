@@ -783,10 +783,11 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
   F.g_on = F.ctl[5];
   if (F.g_on) F.g_start = F.g_base + 1;
   // first wave: two seeds (the first board is usually found by the first or second seed); after the
-  // first board the leftovers rarely hold another one and every seed will be visited, so a block
-  // with many warps (latency mode) starts with one seed per warp
+  // first board the leftovers rarely hold another one and every seed will be visited: all (up to
+  // 30) seeds form ONE wave, so the warps of the block meet at a barrier once instead of once per
+  // wave (the warps claim seeds dynamically; each barrier costs up to one seed of waiting)
   int best_score = 0, count = 0;
-  int wave = (F.round > 0 && F.n_warps > 2) ? F.n_warps : (F.n_warps > 1 ? 2 : 1);
+  int wave = F.round > 0 ? 30 : (F.n_warps > 1 ? 2 : 1);
   int best_quad[4] = {0, 0, 0, 0};
   SeedEnum E;
   while (seeds_left > 0 && count < 30 && best_score < 36) {
@@ -895,7 +896,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
       ++count;
     }
     seeds_left -= nw;
-    wave = wave < 4 ? 4 : (wave < kWaveMax ? wave * 2 : kWaveMax);
+    wave = wave < 4 ? 4 : (wave < kWaveMax ? wave * 2 : wave);
     __syncthreads();  // fx_wscore / fx_wquad are reused by the next wave
   }
   if (best_score == 0) return -1;
