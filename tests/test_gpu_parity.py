@@ -317,3 +317,75 @@ def test_label_kernel_variants_agree(pkg, oracle, images):
     finally:
         for d in dets:
             d.close()
+
+
+@pytest.mark.parametrize("kw", [dict(dtype=np.uint16), dict(rgb=True)])
+def test_detect_batch_other_formats(pkg, oracle, kw):
+    """16-bit gray and RGB frames through the batched host path (ragged chunks)."""
+    frames = np.stack([synth.render_board_numpy(640, 480, seed=60 + i, tag_px=42.0, **kw) for i in range(5)])
+    det = pkg.TagDetector(pkg.TagFamily.T36H11)
+    try:
+        det.set_option("host_chunk_frames", 2)
+        got = det.detect_batch(frames)
+    finally:
+        det.close()
+    want = oracle.detect_batch(frames)
+    assert len(got) == 5
+    for g, w in zip(got, want):
+        assert len(w) == 36
+        assert_tags_match(g, w)
+
+
+def test_streaming_device_calls_equal_synchronous_calls(pkg, oracle):
+    """ag_detect_batch_device with device_async + ag_detect_batch_device_wait: several calls in flight
+    over all board slots give byte-identical results to one synchronising call per batch."""
+    import torch
+    det = pkg.TagDetector(pkg.TagFamily.T36H11)
+    try:
+        n, w, h, cap = 80, 640, 480, 64
+        det.set_option("chunk_frames", 8)  # 10 chunks per call: more than the 8 board slots
+        frames = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+        det.render_boards_device(frames.data_ptr(), n, w, h, 6, 6, 2024)
+        torch.cuda.synchronize()
+
+        def run(k_calls, async_mode):
+            det.set_option("device_async", 1 if async_mode else 0)
+            outs = []
+            s = torch.cuda.current_stream().cuda_stream
+            for _ in range(k_calls):
+                tags = torch.zeros((n, cap * 9), dtype=torch.int32, device="cuda")
+                cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+                st = torch.zeros(n, dtype=torch.int32, device="cuda")
+                det.detect_batch_device(frames.data_ptr(), n, w, h, pkg.FMT_L8, tags.data_ptr(), cap,
+                                        cnt.data_ptr(), st.data_ptr(), stream=s)
+                outs.append((tags, cnt, st))
+            if async_mode:
+                det.detect_batch_device_wait(stream=s)
+            torch.cuda.synchronize()
+            det.set_option("device_async", 0)
+            return outs
+
+        ref = run(1, False)[0]
+        for tags, cnt, st in run(3, True):
+            assert torch.equal(cnt, ref[1]) and torch.equal(tags, ref[0]) and int(st.abs().sum()) == 0
+        # and the batch agrees with the oracle on a sample
+        host = frames[:4].cpu().numpy()
+        want = oracle.detect_batch(host)
+        rec = ref[0][:4].cpu().numpy().view(pkg.TAG_DTYPE).reshape(4, cap)
+        cn = ref[1][:4].cpu().numpy()
+        for i in range(4):
+            got = {int(t["id"]): t["xy"].reshape(4, 2) for t in rec[i, :cn[i]]}
+            assert_tags_match(got, want[i])
+    finally:
+        det.close()
+
+
+def test_label_kernel_row_limit_fallback(detector, oracle):
+    """More rows than the run-based labelling kernel keeps row starts for (4096): the frame is handed
+    to the pixel-list kernel; stages still match the oracle."""
+    rng = np.random.default_rng(21)
+    img = np.full((4200, 48), 120, np.uint8)
+    img[::9, ::5] = 20
+    img[3::17] = 230
+    img = (img.astype(np.int32) + rng.integers(-3, 4, img.shape)).clip(0, 255).astype(np.uint8)
+    check_stages(detector, oracle, img, check_board=False)
