@@ -53,7 +53,7 @@ print("repetitions %d, frames %d: %s; mean tags/frame %.3f, status bits %s"
          sorted(set(s0.cpu().numpy().tolist()))))
 # oracle on a sample
 oracle = entry.load_oracle()
-k = 16
+k = int(os.environ.get("AG_ORACLE_SAMPLE", "16"))
 sample = frames[:k].cpu().numpy()
 want = oracle.detect_batch(sample)
 tg = t0[:k].cpu().numpy().view(pkg.TAG_DTYPE).reshape(k, 64)
