@@ -230,40 +230,56 @@ AGB_FN float angle_degree_fast(float ax, float ay, float bx, float by) {
 // covers kGuardDeg of angle plus f32 rounding of the products: |dm / d angle| <= 1.02 * scale
 // per radian for the tests below, kGuardDeg = 7e-5 rad.
 constexpr float kGuardRel = 1.2e-4f;
-// |angle(a) - angle(b)| > limit ?  with a = angle(p, q), b = angle(r, s);  limit = 10 degrees.
-AGB_NOINLINE bool angle_gap_exceeds(float px, float py, float qx, float qy, float rx, float ry,
-                                    float sx, float sy, float limit) {
-  {
-    // Trigonometry-free decision.  a = atan2(y1, x1), b = atan2(y2, x2).  When y1 and y2 have the
-    // same strict sign both angles lie in the same open half turn, so a - b = atan2(Y, X) with
-    // Y = y1 x2 - x1 y2, X = x1 x2 + y1 y2, and |a - b| <= limit  <=>  |Y| <= tan(limit) X.
-    // Away from the threshold (margin: guard band + rounding) the verdict is certain.
-    const float y1 = py * qx - px * qy, x1 = px * qx + py * qy;  // atan2 arguments of angle_degree(p, q)
-    const float y2 = ry * sx - rx * sy, x2 = rx * sx + ry * sy;
-    if ((y1 > 0.0f && y2 > 0.0f) || (y1 < 0.0f && y2 < 0.0f)) {
-      const float a1 = y1 * x2, a2 = x1 * y2, b1 = x1 * x2, b2 = y1 * y2;
-      const float Y = a1 - a2, X = b1 + b2;
-      const float kTan10 = 0.17632698f;
-      const float m = fabsf(Y) - kTan10 * X;
-      const float scale = fabsf(a1) + fabsf(a2) + fabsf(b1) + fabsf(b2);
-      const float margin = (kGuardRel + 4.0e-7f) * scale;
-      if (limit == 10.0f && scale < 1.0e30f && scale > 1.0e-30f) {
-        if (m > margin) return true;
-        if (m < -margin) return false;
-      }
-    }
-  }
+// |angle(a) - angle(b)| > limit ?  with a = angle(p, q), b = angle(r, s): the atan2f path with
+// its guard band, then the exact expression (rarely reached: see angle_gap_exceeds).
+AGB_NOINLINE bool angle_gap_exceeds_slow(float px, float py, float qx, float qy, float rx, float ry,
+                                         float sx, float sy, float limit) {
   const float fa = angle_degree_fast(px, py, qx, qy), fb = angle_degree_fast(rx, ry, sx, sy);
   const float g = fabsf(fa - fb);
   if (g > limit + kGuardDeg) return true;
   if (g < limit - kGuardDeg) return false;
   return fabsf(fsub(angle_degree(px, py, qx, qy), angle_degree(rx, ry, sx, sy))) > limit;
 }
+// |angle(a) - angle(b)| > limit ?  limit = 10 degrees.  Inline part: the trigonometry-free
+// decision.  a = atan2(y1, x1), b = atan2(y2, x2).  When y1 and y2 have the same strict sign both
+// angles lie in the same open half turn, so a - b = atan2(Y, X) with Y = y1 x2 - x1 y2,
+// X = x1 x2 + y1 y2, and |a - b| <= limit  <=>  |Y| <= tan(limit) X.  Away from the threshold
+// (margin: guard band + rounding) the verdict is certain; otherwise the slow path decides.
+AGB_FN bool angle_gap_exceeds(float px, float py, float qx, float qy, float rx, float ry, float sx,
+                              float sy, float limit) {
+  const float y1 = py * qx - px * qy, x1 = px * qx + py * qy;  // atan2 arguments of angle_degree(p, q)
+  const float y2 = ry * sx - rx * sy, x2 = rx * sx + ry * sy;
+  if ((y1 > 0.0f && y2 > 0.0f) || (y1 < 0.0f && y2 < 0.0f)) {
+    const float a1 = y1 * x2, a2 = x1 * y2, b1 = x1 * x2, b2 = y1 * y2;
+    const float Y = a1 - a2, X = b1 + b2;
+    const float kTan10 = 0.17632698f;
+    const float m = fabsf(Y) - kTan10 * X;
+    const float scale = fabsf(a1) + fabsf(a2) + fabsf(b1) + fabsf(b2);
+    const float margin = (kGuardRel + 4.0e-7f) * scale;
+    if (limit == 10.0f && scale < 1.0e30f && scale > 1.0e-30f) {
+      if (m > margin) return true;
+      if (m < -margin) return false;
+    }
+  }
+  return angle_gap_exceeds_slow(px, py, qx, qy, rx, ry, sx, sy, limit);
+}
 
 // ---- saddle.rs:17-67, split in two so the (s0, s1)-only test can be hoisted ---------------
-AGB_NOINLINE bool quad_diag_ok(const Frame& F, int s0, int s1) {  // "filter white block", :26-38
-  float v02x = fsub(F.sx[s1], F.sx[s0]), v02y = fsub(F.sy[s1], F.sy[s0]);
-  float th = fmul(fdiv(F.st[s0], 180.0f), kPi);
+// Coordinate forms (inline; the throughput path loads the points once and passes them in
+// registers) and index forms (noinline wrappers for the general path).
+AGB_NOINLINE bool quad_diag_ok_slow(float v02x, float v02y, float th) {
+  {
+    const float fa = fabsf(angle_degree_fast(v02x, v02y, cosf(th), sinf(th)));
+    if (fa > 60.0f + kGuardDeg && fa < 120.0f - kGuardDeg) return true;
+    if (fa < 60.0f - kGuardDeg || fa > 120.0f + kGuardDeg) return false;
+  }
+  float vx = cos_cr(th), vy = sin_cr(th);
+  float a = fabsf(angle_degree(v02x, v02y, vx, vy));
+  return a >= 60.0f && a <= 120.0f;
+}
+AGB_FN bool quad_diag_ok_v(float x0, float y0, float t0, float x1, float y1) {  // "filter white block", :26-38
+  float v02x = fsub(x1, x0), v02y = fsub(y1, y0);
+  float th = fmul(fdiv(t0, 180.0f), kPi);
   {
     // |angle(v02, u)| in [60, 120] degrees  <=>  sqrt(3) |dot| <= |cross|  (u = unit vector of
     // theta); decided without atan2 away from the two thresholds.
@@ -282,40 +298,49 @@ AGB_NOINLINE bool quad_diag_ok(const Frame& F, int s0, int s1) {  // "filter whi
       if (m > margin) return false;
     }
   }
-  {
-    const float fa = fabsf(angle_degree_fast(v02x, v02y, cosf(th), sinf(th)));
-    if (fa > 60.0f + kGuardDeg && fa < 120.0f - kGuardDeg) return true;
-    if (fa < 60.0f - kGuardDeg || fa > 120.0f + kGuardDeg) return false;
-  }
-  float vx = cos_cr(th), vy = sin_cr(th);
-  float a = fabsf(angle_degree(v02x, v02y, vx, vy));
-  return a >= 60.0f && a <= 120.0f;
+  return quad_diag_ok_slow(v02x, v02y, th);
 }
 // The remaining gates of is_valid_quad.  They only ever reject, so they are evaluated
 // cheapest-first; the verdict equals the reference's (saddle.rs:18-66).
-AGB_NOINLINE bool quad_rest_ok(const Frame& F, int s0, int d0, int s1, int d1) {
-  if (theta_distance_degree(F.st[d0], F.st[d1]) > 5.0f) return false;
-  float v01x = fsub(F.sx[d0], F.sx[s0]), v01y = fsub(F.sy[d0], F.sy[s0]);
-  float v03x = fsub(F.sx[d1], F.sx[s0]), v03y = fsub(F.sy[d1], F.sy[s0]);
-  float v02x = fsub(F.sx[s1], F.sx[s0]), v02y = fsub(F.sy[s1], F.sy[s0]);
+// Points: s0 = (x0, y0), d0 = (xa, ya, theta ta), s1 = (x1, y1), d1 = (xb, yb, theta tb).
+AGB_FN bool quad_rest_ok_v(float x0, float y0, float xa, float ya, float ta, float x1, float y1, float xb,
+                           float yb, float tb) {
+  if (theta_distance_degree(ta, tb) > 5.0f) return false;
+  float v01x = fsub(xa, x0), v01y = fsub(ya, y0);
+  float v03x = fsub(xb, x0), v03y = fsub(yb, y0);
+  float v02x = fsub(x1, x0), v02y = fsub(y1, y0);
   float c0 = cross2(v01x, v01y, v02x, v02y);
   float c1 = cross2(v02x, v02y, v03x, v03y);
   if (fmul(c0, c1) < 0.0f) return false;
-  float v12x = fsub(F.sx[s1], F.sx[d0]), v12y = fsub(F.sy[s1], F.sy[d0]);
-  float v23x = fsub(F.sx[d1], F.sx[s1]), v23y = fsub(F.sy[d1], F.sy[s1]);
+  float v12x = fsub(x1, xa), v12y = fsub(y1, ya);
+  float v23x = fsub(xb, x1), v23y = fsub(yb, y1);
   float c01 = cross2(v01x, v01y, v12x, v12y);
   float c12 = cross2(v12x, v12y, v23x, v23y);
   if (fmul(c01, c12) < 0.0f) return false;
   if (dot2(v01x, v01y, v02x, v02y) < 0.0f || dot2(v03x, v03y, v02x, v02y) < 0.0f) return false;
-  float v30x = fsub(F.sx[s0], F.sx[d1]), v30y = fsub(F.sy[s0], F.sy[d1]);
+  float v30x = fsub(x0, xb), v30y = fsub(y0, yb);
   if (angle_gap_exceeds(v01x, v01y, v12x, v12y, v23x, v23y, v30x, v30y, 10.0f)) return false;  // a0, a2
   if (angle_gap_exceeds(v12x, v12y, v23x, v23y, v30x, v30y, v01x, v01y, 10.0f)) return false;  // a1, a3
   return true;
+}
+AGB_NOINLINE bool quad_diag_ok(const Frame& F, int s0, int s1) {
+  return quad_diag_ok_v(F.sx[s0], F.sy[s0], F.st[s0], F.sx[s1], F.sy[s1]);
+}
+AGB_NOINLINE bool quad_rest_ok(const Frame& F, int s0, int d0, int s1, int d1) {
+  return quad_rest_ok_v(F.sx[s0], F.sy[s0], F.sx[d0], F.sy[d0], F.st[d0], F.sx[s1], F.sy[s1], F.sx[d1],
+                        F.sy[d1], F.st[d1]);
 }
 AGB_FN bool is_valid_quad(const Frame& F, int s0, int d0, int s1, int d1) {
   // Both halves only ever return false early, so evaluating the diagonal test first gives
   // the same verdict as the reference's order (saddle.rs:18-38).
   return quad_diag_ok(F, s0, s1) && quad_rest_ok(F, s0, d0, s1, d1);
+}
+// is_valid_quad on points held through register pointers (throughput path: no call, no reload of
+// the frame's fields)
+AGB_FN bool is_valid_quad_p(const float* sx, const float* sy, const float* st, int s0, int d0, int s1, int d1) {
+  const float x0 = sx[s0], y0 = sy[s0], x1 = sx[s1], y1 = sy[s1];
+  if (!quad_diag_ok_v(x0, y0, st[s0], x1, y1)) return false;
+  return quad_rest_ok_v(x0, y0, sx[d0], sy[d0], st[d0], x1, y1, sx[d1], sy[d1], st[d1]);
 }
 
 // ---- nearest neighbours (kdtree 0.8 `nearest`, restated as exact search) -------------------

@@ -283,6 +283,9 @@ constexpr int kCtlNext = 6;  // slot of F.ctl: next wave slot (seed) to hand to 
 constexpr int kSaveMin = 12;
 constexpr int kSaveBytes = 16 + 256 + 512;
 __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
+  const float* const psx = F.sx;  // the frame's point arrays, once (F lives in local memory)
+  const float* const psy = F.sy;
+  const float* const pst = F.st;
   uint8_t* const save = F.fx_save0 + (size_t)F.warp * F.fx_save_stride;
   int save_score = *(const int*)save;  // warp-uniform
   const unsigned full = 0xffffffffu;
@@ -436,8 +439,8 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
         const int i3 = r % n3; r /= n3;
         const int i2 = r % n2; r /= n2;
         const int i1 = r % n1; r /= n1;
-        valid = is_valid_quad(F, packed_cand(p0, r), packed_cand(p1, i1), packed_cand(p2, i2),
-                              packed_cand(p3, i3));
+        valid = is_valid_quad_p(psx, psy, pst, packed_cand(p0, r), packed_cand(p1, i1), packed_cand(p2, i2),
+                                packed_cand(p3, i3));
       }
       const unsigned m = (__ballot_sync(full, valid) >> gshift) & 0xfu;
       if (!ok && m) {
@@ -598,7 +601,11 @@ __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
   E.diag_ok[0] = E.diag_ok[1] = 0u;
   for (int blk = 0; blk * 32 < n_same; ++blk) {  // n_same <= 49
     const int a = blk * 32 + F.lane;
-    const bool ok = a < n_same && quad_diag_ok(F, s0, F.same[a]);
+    bool ok = false;
+    if (a < n_same) {
+      const int s1 = F.same[a];
+      ok = quad_diag_ok_v(x0, y0, t0, F.sx[s1], F.sy[s1]);
+    }
     E.diag_ok[blk & 1] = __ballot_sync(0xffffffffu, ok);
   }
   // theta gate of is_valid_quad (saddle.rs:21-24) for every pair (i < j) of diff entries: it does
@@ -638,7 +645,8 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
         s1 = F.same[e & 0xffu];
         d0 = F.diff[(e >> 8) & 0xffu];
         d1 = F.diff[(e >> 16) & 0xffu];
-        valid = quad_rest_ok(F, E.s0, d0, s1, d1);
+        valid = quad_rest_ok_v(x0, y0, F.sx[d0], F.sy[d0], F.st[d0], F.sx[s1], F.sy[s1], F.sx[d1], F.sy[d1],
+                               F.st[d1]);
       }
       const unsigned m = __ballot_sync(0xffffffffu, valid);
       if (valid) {
