@@ -122,7 +122,24 @@ __device__ __noinline__ void grid_build_warp(Frame& F) {
 // distance -- a long edge a -> b gives a radius that covers most of the board although only
 // the three nearest saddles matter.  All bounds are conservative, so the result equals the
 // scan of the whole window.
-__device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* active, bool on, int a,
+// The frame's fields the neighbour search needs, read once per warp_score_quads call and kept in
+// registers (the Frame itself lives in local memory; the search runs hundreds of times per call).
+struct QueryCtx {
+  const float *sx, *sy, *st;
+  float g_inv;
+  int g_nx, g_ny, g_on, n;
+  unsigned a_start, a_pos, a_item;  // shared-memory addresses of the grid arrays
+};
+__device__ __forceinline__ QueryCtx make_query_ctx(const Frame& F) {
+  QueryCtx C;
+  C.sx = F.sx; C.sy = F.sy; C.st = F.st;
+  C.g_inv = F.g_inv; C.g_nx = F.g_nx; C.g_ny = F.g_ny; C.g_on = F.g_on; C.n = F.n;
+  C.a_start = F.g_on ? (unsigned)__cvta_generic_to_shared(F.g_start) : 0u;
+  C.a_pos = (unsigned)__cvta_generic_to_shared(F.g_pos);
+  C.a_item = (unsigned)__cvta_generic_to_shared(F.g_item);
+  return C;
+}
+__device__ __forceinline__ unsigned group_query(const QueryCtx& F, const uint32_t* active, bool on, int a,
                                                 int b, int self) {
   const unsigned full = 0xffffffffu;
   const unsigned long long kInf = ~0ull;
@@ -166,9 +183,7 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
     }
     const float bsz = 1.0f / F.g_inv;  // bucket side, a power of two: bucket indices are exact
     // shared-memory addresses of the grid arrays (32-bit, LDS instead of generic loads)
-    const unsigned a_start = (unsigned)__cvta_generic_to_shared(F.g_start);
-    const unsigned a_pos = (unsigned)__cvta_generic_to_shared(F.g_pos);
-    const unsigned a_item = (unsigned)__cvta_generic_to_shared(F.g_item);
+    const unsigned a_start = F.a_start, a_pos = F.a_pos, a_item = F.a_item;
     auto lds_u16 = [](unsigned addr) -> int {
       unsigned short v;
       asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
@@ -236,13 +251,15 @@ __device__ __forceinline__ unsigned group_query(const Frame& F, const uint32_t* 
     }
     if (on && !windowed)  // degenerate radius (NaN / huge): exhaustive
       for (int i = 0; i < F.n; ++i) {
-        const float d = dist2(F, qx, qy, i);
+        const float ddx = fsub(qx, F.sx[i]), ddy = fsub(qy, F.sy[i]);
+        const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
         if (d <= r2) insert(d, i);
       }
   } else {
     for (int i = 0; __any_sync(full, on && i < F.n); ++i)
       if (on && i < F.n) {
-        const float d = dist2(F, qx, qy, i);
+        const float ddx = fsub(qx, F.sx[i]), ddy = fsub(qy, F.sy[i]);
+        const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
         if (d <= r2) insert(d, i);
       }
   }
@@ -283,9 +300,11 @@ constexpr int kCtlNext = 6;  // slot of F.ctl: next wave slot (seed) to hand to 
 constexpr int kSaveMin = 12;
 constexpr int kSaveBytes = 16 + 256 + 512;
 __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
-  const float* const psx = F.sx;  // the frame's point arrays, once (F lives in local memory)
-  const float* const psy = F.sy;
-  const float* const pst = F.st;
+  const QueryCtx QC = make_query_ctx(F);
+  const float* const psx = QC.sx;  // the frame's point arrays, once (F lives in local memory)
+  const float* const psy = QC.sy;
+  const float* const pst = QC.st;
+  const int max_quads = F.max_quads;
   uint8_t* const save = F.fx_save0 + (size_t)F.warp * F.fx_save_stride;
   int save_score = *(const int*)save;  // warp-uniform
   const unsigned full = 0xffffffffu;
@@ -361,7 +380,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
         nci = (nx + 8) * kGWin + (ny + 8);
         const int cur = cell[nci];
         if (cur != 0 && cur != 0xff) continue;  // already Some (board.rs:131-135)
-        if (n_quads >= F.max_quads) {           // no room: the attempt fails, the cell becomes None
+        if (n_quads >= max_quads) {             // no room: the attempt fails, the cell becomes None
           if (jl == 0) cell[nci] = 0xff;
           __syncwarp(gmask);
           continue;
@@ -421,7 +440,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
       qself = (jl == 1 || jl == 2) ? qb : qa;
     }
     __syncwarp();
-    const unsigned mine = group_query(F, active, need, qa, qb, qself);  // whole warp, convergent
+    const unsigned mine = group_query(QC, active, need, qa, qb, qself);  // whole warp, convergent
     if (tmon) { const long long tc = clock64(); F.tm[7] += (uint32_t)(tc - tc0); tc0 = tc; }
     const unsigned p0 = __shfl_sync(full, mine, 0, 4), p1 = __shfl_sync(full, mine, 1, 4);
     const unsigned p2 = __shfl_sync(full, mine, 2, 4), p3 = __shfl_sync(full, mine, 3, 4);
