@@ -326,8 +326,8 @@ class TagDetector:
                     centers=centers, raw=raw, refined=ref, quads=quads, tags=_tags_to_dict(tags[:n.value]))
 
     def _board_times(self, slot, n_frames):
-        """Profiling hook: n_frames x 16 u32 timing taps of the last board-kernel launch of a slot."""
-        out = np.zeros((n_frames, 16), np.uint32)
+        """Profiling hook: n_frames x 32 u32 timing taps of the last board-kernel launch of a slot."""
+        out = np.zeros((n_frames, 32), np.uint32)
         self._check(lib().ag_test_board_times(self._h, slot, _p(out), n_frames))
         return out
 

@@ -57,7 +57,7 @@ struct BoardSlot {
   int* d_nref = nullptr;
   uint8_t* d_board_ws = nullptr;
   uint32_t* d_status = nullptr;
-  uint32_t* d_board_tm = nullptr;  // optional per-frame timing of the board kernel ([frames][16])
+  uint32_t* d_board_tm = nullptr;  // optional per-frame timing of the board kernel ([frames][32])
   int32_t* d_tap_quads = nullptr;
   int* d_tap_nquads = nullptr;
   BoardWsLayout layout[2]{};        // [tier] sized for the largest warps-per-frame (allocation)
@@ -246,7 +246,7 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
   if ((rc = regrow(det, &B.d_board_ws, (size_t)F * B.layout[0].bytes_per_frame))) return rc;
   if ((rc = regrow(det, &B.d_tap_quads, (size_t)F * B.layout[0].max_quads * 4))) return rc;
   if ((rc = regrow(det, &B.d_tap_nquads, (size_t)F))) return rc;
-  if ((rc = regrow(det, &B.d_board_tm, (size_t)F * 16))) return rc;
+  if ((rc = regrow(det, &B.d_board_tm, (size_t)F * 32))) return rc;
   B.cap_frames = F;
   B.cap_saddles = nsd;
   B.cfg_warps = det->board_warps;
@@ -1178,7 +1178,7 @@ AG_API int ag_test_board_times(ag_detector* det, int slot, uint32_t* out, int n_
   BoardSlot& S = det->bslot[slot];
   if (!S.d_board_tm || n_frames > S.cap_frames) return fail(det, AG_ERR_INVALID, "no timing data");
   AG_CUDA(det, cudaDeviceSynchronize());
-  AG_CUDA(det, cudaMemcpy(out, S.d_board_tm, sizeof(uint32_t) * 16 * (size_t)n_frames, cudaMemcpyDeviceToHost));
+  AG_CUDA(det, cudaMemcpy(out, S.d_board_tm, sizeof(uint32_t) * 32 * (size_t)n_frames, cudaMemcpyDeviceToHost));
   return AG_OK;
 }
 

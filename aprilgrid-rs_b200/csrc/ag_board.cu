@@ -44,6 +44,7 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   L.off_remove = take(N);
   L.off_tag_valid = take(agb::kMaxCodes);
   L.off_tag_by_id = take(sizeof(agb::TagRec) * agb::kMaxCodes);
+  L.off_qcache = take(sizeof(unsigned long long) * agb::kQCacheEntries);
   // ... and per warp of the frame's block
   L.off_warp0 = o;
   size_t w = 0;
@@ -188,10 +189,10 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.tap_cap = tap_cap;
   F.status = 0;
   F.active_words = (L.max_saddles + 31) / 32;
-  F.tm = timing ? timing + (size_t)f * 16 : nullptr;
+  F.tm = timing ? timing + (size_t)f * 32 : nullptr;
   unsigned long long t_start = 0;
   if (F.tm) {
-    if (threadIdx.x < 16) F.tm[threadIdx.x] = 0u;
+    if (threadIdx.x < 32) F.tm[threadIdx.x] = 0u;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   }
   F.fx_qlist = (int16_t*)(SW + L.smw_qlist);
@@ -205,6 +206,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   // warp's saved best board there
   F.fx_save0 = W + L.off_warp0 + L.woff_sb_touched;
   F.fx_save_stride = L.bytes_per_warp;
+  F.fx_qcache = (unsigned long long*)(W + L.off_qcache);
   F.fx_wscore = (uint16_t*)(smem + L.sm_wave);
   F.fx_wquad = (int16_t*)(F.fx_wscore + 32);
   // block-uniform: the whole frame takes the throughput path or the general one
@@ -222,6 +224,10 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
       if (F.tap_n_quads && lane == 0) *F.tap_n_quads = 0;
       if (lane < 16) F.ctl[lane] = 0;
     }
+  }
+  if (F.fast_on) {  // empty neighbour-search cache (tag 0 = no entry)
+    uint4* q = (uint4*)F.fx_qcache;
+    for (int i = threadIdx.x; i < agb::kQCacheEntries / 2; i += blockDim.x) __stcg(q + i, make_uint4(0u, 0u, 0u, 0u));
   }
   // saddles AoS -> SoA (block-wide)
   const ag_saddle* S = refined + (size_t)f * L.max_saddles;

@@ -142,6 +142,7 @@ struct Frame {
   int16_t* fx_wquad;     // [32][4] ... and its quad
   uint8_t* fx_save0;     // global: warp 0's saved best board (header + group state); warp w's at
   size_t fx_save_stride; //   fx_save0 + w * fx_save_stride
+  unsigned long long* fx_qcache;  // global: the frame's neighbour-search cache (kQCacheEntries entries)
   uint32_t* tm;          // optional per-frame timing / work counters ([16], may be null)
 };
 

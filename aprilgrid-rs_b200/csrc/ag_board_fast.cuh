@@ -25,6 +25,8 @@
 
 namespace agb {
 
+constexpr int kQCacheBits = 11;  // neighbour-search cache: 2^11 entries of 8 bytes per frame (group_query)
+constexpr int kQCacheEntries = 1 << kQCacheBits;
 constexpr int kFastMaxSaddles = 1024;  // saddle list and bucket grid live in shared memory (two
                                        // layout tiers: 512 and 1024 saddles, see make_board_layout)
 constexpr int kGroupLanes = 4;
@@ -139,8 +141,11 @@ __device__ __forceinline__ QueryCtx make_query_ctx(const Frame& F) {
   C.a_item = (unsigned)__cvta_generic_to_shared(F.g_item);
   return C;
 }
-__device__ __forceinline__ unsigned group_query(const QueryCtx& F, const uint32_t* active, bool on, int a,
-                                                int b, int self) {
+// group_knn: the search proper (the up to three nearest saddles within the radius, unfiltered,
+// packed as above).  It depends on (a, b, self == b) and the frame's saddle list only -- not on the
+// board being grown -- so its result is shared by every board of the frame through a cache
+// (group_query below).
+__device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a, int b, int self, uint32_t* tm = nullptr) {
   const unsigned full = 0xffffffffu;
   const unsigned long long kInf = ~0ull;
   unsigned long long k0 = kInf, k1 = kInf, k2 = kInf;
@@ -228,9 +233,11 @@ __device__ __forceinline__ unsigned group_query(const QueryCtx& F, const uint32_
     t = 1;
     while (__any_sync(full, e < e1 || t < t_end)) {
       int ne, ne1;
+      if (tm && (threadIdx.x & 31) == 0) tm[23] += 1;
       row_setup(t, ne, ne1);
       ++t;
       while (__any_sync(full, e < e1)) {
+        if (tm) { const unsigned mm = __ballot_sync(full, e < e1); if ((threadIdx.x & 31) == 0) { tm[24] += 1; tm[25] += __popc(mm); } }
         if (e < e1) {
           const bool two = e + 1 < e1;
           const unsigned ea = a_pos + 8u * (unsigned)e, eb = two ? ea + 8u : ea;
@@ -264,19 +271,57 @@ __device__ __forceinline__ unsigned group_query(const QueryCtx& F, const uint32_
       }
   }
   unsigned packed = 0, cnt = 0;
+  if (k0 != kInf) { packed |= ((unsigned)k0 & 0x3ffu) << 2; ++cnt; }
+  if (k1 != kInf) { packed |= ((unsigned)k1 & 0x3ffu) << 12; ++cnt; }
+  if (k2 != kInf) { packed |= ((unsigned)k2 & 0x3ffu) << 22; ++cnt; }
+  return packed | cnt;
+}
+// The frame's neighbour-search cache: direct-mapped, in global memory (L2), one 64-bit entry
+// = tag (valid bit, search round, a, b, self == b) << 32 | packed result.  Boards grown from
+// different quads of a frame walk the same tags, so most searches after the first board of a
+// warp are repeats.  An entry is written and read with single 64-bit accesses; a reader sees
+// the old or the new entry, both are complete, and a hit returns exactly what the search
+// would, so races between the warps of a frame do not change the result.
+__device__ __forceinline__ unsigned group_query(const QueryCtx& F, unsigned long long* qcache, unsigned round_tag,
+                                                const uint32_t* active, bool on, int a, int b, int self,
+                                                uint32_t* tm) {
+  unsigned knn = 0, tag = 0;
+  unsigned long long* slot = nullptr;
+  bool search = on;
+  if (on && qcache) {
+    const unsigned key = ((unsigned)a << 11) | ((unsigned)b << 1) | (self == a ? 0u : 1u);
+    tag = round_tag | key;
+    slot = qcache + ((key * 0x9E3779B1u) >> (32 - kQCacheBits));
+    const unsigned long long e = __ldcg(slot);
+    if ((unsigned)(e >> 32) == tag) {
+      knn = (unsigned)e;
+      search = false;
+    }
+  }
+  if (tm) {
+    const unsigned ms = __ballot_sync(0xffffffffu, search), mo = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0) { tm[20] += __popc(mo); tm[21] += __popc(ms); tm[22] += ms != 0u; }
+  }
+  if (__any_sync(0xffffffffu, search)) {
+    const unsigned r = group_knn(F, search, a, b, self, tm);
+    if (search) {
+      knn = r;
+      if (slot) __stcg(slot, ((unsigned long long)tag << 32) | r);
+    }
+  }
+  // active mask of the board and theta gate (board.rs:218-231), order kept
+  unsigned packed = 0, cnt = 0;
   if (on) {
     const float ts = F.st[self];
-    auto keep = [&](unsigned long long k) {
-      if (k == kInf) return;
-      const int i = (int)(unsigned)k;
+    const int n = (int)(knn & 3u);
+    for (int t = 0; t < 3; ++t) {
+      if (t >= n) break;
+      const int i = (int)((knn >> (2 + 10 * t)) & 0x3ffu);
       if (((active[i >> 5] >> (i & 31)) & 1u) && theta_distance_degree(ts, F.st[i]) < 5.0f) {
         packed |= (unsigned)i << (2 + 10 * cnt);
         ++cnt;
       }
-    };
-    keep(k0);
-    keep(k1);
-    keep(k2);
+    }
   }
   return packed | cnt;
 }
@@ -305,6 +350,9 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
   const float* const psy = QC.sy;
   const float* const pst = QC.st;
   const int max_quads = F.max_quads;
+  // searches are cached per (round, a, b, self); the 7-bit round tag bounds the rounds that may use it
+  unsigned long long* const qcache = F.round < 127 ? F.fx_qcache : nullptr;
+  const unsigned round_tag = 0x80000000u | ((unsigned)F.round << 24);
   uint8_t* const save = F.fx_save0 + (size_t)F.warp * F.fx_save_stride;
   int save_score = *(const int*)save;  // warp-uniform
   const unsigned full = 0xffffffffu;
@@ -356,7 +404,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
       __syncwarp();
     }
     if (!__any_sync(full, alive)) break;
-    if (tmon) { const long long tc = clock64(); F.tm[2] += (uint32_t)(tc - tc0); tc0 = tc; }
+    if (tmon) { const long long tc = clock64(); F.tm[16] += (uint32_t)(tc - tc0); tc0 = tc; }
     // (1) every running board advances to its next expansion attempt (or finishes)
     bool need = false;
     int dir = 0, nci = 0, result = -1;
@@ -425,7 +473,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
       }
     }
     // (2) the four neighbour searches of try_expand_one, one per lane
-    if (tmon) { const long long tc = clock64(); F.tm[5] += (uint32_t)(tc - tc0); tc0 = tc; }
+    if (tmon) { const long long tc = clock64(); F.tm[17] += (uint32_t)(tc - tc0); tc0 = tc; }
     int qa = 0, qb = 0, qself = 0;
     if (need) {
       const int qi = cell[cur_ci] - 1;
@@ -440,8 +488,8 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
       qself = (jl == 1 || jl == 2) ? qb : qa;
     }
     __syncwarp();
-    const unsigned mine = group_query(QC, active, need, qa, qb, qself);  // whole warp, convergent
-    if (tmon) { const long long tc = clock64(); F.tm[7] += (uint32_t)(tc - tc0); tc0 = tc; }
+    const unsigned mine = group_query(QC, qcache, round_tag, active, need, qa, qb, qself, F.warp == 0 ? F.tm : nullptr);  // whole warp, convergent
+    if (tmon) { const long long tc = clock64(); F.tm[18] += (uint32_t)(tc - tc0); tc0 = tc; }
     const unsigned p0 = __shfl_sync(full, mine, 0, 4), p1 = __shfl_sync(full, mine, 1, 4);
     const unsigned p2 = __shfl_sync(full, mine, 2, 4), p3 = __shfl_sync(full, mine, 3, 4);
     const int n0 = packed_count(p0), n1 = packed_count(p1), n2 = packed_count(p2), n3 = packed_count(p3);
@@ -472,7 +520,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
         ok = true;
       }
     }
-    if (tmon) { const long long tc = clock64(); F.tm[10] += (uint32_t)(tc - tc0); tc0 = tc; }
+    if (tmon) { const long long tc = clock64(); F.tm[19] += (uint32_t)(tc - tc0); tc0 = tc; }
     // (4) update the board
     if (need) {
       if (ok) {
