@@ -100,7 +100,7 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   return L;
 }
 
-__global__ void __launch_bounds__(kMaxBoardWarps * 32)
+__global__ void __launch_bounds__(kMaxBoardWarps * 32, 3)
 k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
                 const ag_saddle* __restrict__ refined, const int* __restrict__ n_refined,
                 uint8_t* __restrict__ ws, BoardWsLayout L, const uint64_t* __restrict__ codes,

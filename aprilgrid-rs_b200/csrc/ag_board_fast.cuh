@@ -126,15 +126,35 @@ __device__ __noinline__ void grid_build_warp(Frame& F) {
 // scan of the whole window.
 // The frame's fields the neighbour search needs, read once per warp_score_quads call and kept in
 // registers (the Frame itself lives in local memory; the search runs hundreds of times per call).
+// The saddle list of a throughput-path frame lives in shared memory (F.fast_on requires it): x, y
+// and theta arrays `stride` bytes apart, read with 32-bit shared addresses.
+struct Pts {
+  unsigned base, stride;
+  __device__ __forceinline__ float ld(unsigned addr) const {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+  }
+  __device__ __forceinline__ float x(int i) const { return ld(base + 4u * (unsigned)i); }
+  __device__ __forceinline__ float y(int i) const { return ld(base + stride + 4u * (unsigned)i); }
+  __device__ __forceinline__ float t(int i) const { return ld(base + 2u * stride + 4u * (unsigned)i); }
+};
+// is_valid_quad (saddle.rs:17-67) on the shared-memory saddle list: no call, no generic loads
+__device__ __forceinline__ bool is_valid_quad_s(const Pts& P, int s0, int d0, int s1, int d1) {
+  const float x0 = P.x(s0), y0 = P.y(s0), x1 = P.x(s1), y1 = P.y(s1);
+  if (!quad_diag_ok_v(x0, y0, P.t(s0), x1, y1)) return false;
+  return quad_rest_ok_v(x0, y0, P.x(d0), P.y(d0), P.t(d0), x1, y1, P.x(d1), P.y(d1), P.t(d1));
+}
 struct QueryCtx {
-  const float *sx, *sy, *st;
+  Pts P;
   float g_inv;
   int g_nx, g_ny, g_on, n;
   unsigned a_start, a_pos, a_item;  // shared-memory addresses of the grid arrays
 };
 __device__ __forceinline__ QueryCtx make_query_ctx(const Frame& F) {
   QueryCtx C;
-  C.sx = F.sx; C.sy = F.sy; C.st = F.st;
+  C.P.base = (unsigned)__cvta_generic_to_shared(F.sx);
+  C.P.stride = (unsigned)((const char*)F.sy - (const char*)F.sx);  // F.st = F.sy + the same stride
   C.g_inv = F.g_inv; C.g_nx = F.g_nx; C.g_ny = F.g_ny; C.g_on = F.g_on; C.n = F.n;
   C.a_start = F.g_on ? (unsigned)__cvta_generic_to_shared(F.g_start) : 0u;
   C.a_pos = (unsigned)__cvta_generic_to_shared(F.g_pos);
@@ -163,7 +183,7 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a,
   float qx = 0.0f, qy = 0.0f, r2 = -1.0f, r = 0.0f;
   if (on) {
     const float ratio0 = fadd(1.0f, 0.3f);  // 1.0 + spacing_ratio; detector.rs:621 passes 0.3
-    const float ax = F.sx[a], ay = F.sy[a], bx = F.sx[b], by = F.sy[b];
+    const float ax = F.P.x(a), ay = F.P.y(a), bx = F.P.x(b), by = F.P.y(b);
     const float dx = fsub(ax, bx), dy = fsub(ay, by);
     r2 = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
     const float v10x = fsub(bx, ax), v10y = fsub(by, ay);
@@ -233,11 +253,15 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a,
     t = 1;
     while (__any_sync(full, e < e1 || t < t_end)) {
       int ne, ne1;
+#ifdef AGB_LOOP_STATS
       if (tm && (threadIdx.x & 31) == 0) tm[23] += 1;
+#endif
       row_setup(t, ne, ne1);
       ++t;
       while (__any_sync(full, e < e1)) {
+#ifdef AGB_LOOP_STATS
         if (tm) { const unsigned mm = __ballot_sync(full, e < e1); if ((threadIdx.x & 31) == 0) { tm[24] += 1; tm[25] += __popc(mm); } }
+#endif
         if (e < e1) {
           const bool two = e + 1 < e1;
           const unsigned ea = a_pos + 8u * (unsigned)e, eb = two ? ea + 8u : ea;
@@ -258,14 +282,14 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a,
     }
     if (on && !windowed)  // degenerate radius (NaN / huge): exhaustive
       for (int i = 0; i < F.n; ++i) {
-        const float ddx = fsub(qx, F.sx[i]), ddy = fsub(qy, F.sy[i]);
+        const float ddx = fsub(qx, F.P.x(i)), ddy = fsub(qy, F.P.y(i));
         const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
         if (d <= r2) insert(d, i);
       }
   } else {
     for (int i = 0; __any_sync(full, on && i < F.n); ++i)
       if (on && i < F.n) {
-        const float ddx = fsub(qx, F.sx[i]), ddy = fsub(qy, F.sy[i]);
+        const float ddx = fsub(qx, F.P.x(i)), ddy = fsub(qy, F.P.y(i));
         const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
         if (d <= r2) insert(d, i);
       }
@@ -312,12 +336,12 @@ __device__ __forceinline__ unsigned group_query(const QueryCtx& F, unsigned long
   // active mask of the board and theta gate (board.rs:218-231), order kept
   unsigned packed = 0, cnt = 0;
   if (on) {
-    const float ts = F.st[self];
+    const float ts = F.P.t(self);
     const int n = (int)(knn & 3u);
     for (int t = 0; t < 3; ++t) {
       if (t >= n) break;
       const int i = (int)((knn >> (2 + 10 * t)) & 0x3ffu);
-      if (((active[i >> 5] >> (i & 31)) & 1u) && theta_distance_degree(ts, F.st[i]) < 5.0f) {
+      if (((active[i >> 5] >> (i & 31)) & 1u) && theta_distance_degree(ts, F.P.t(i)) < 5.0f) {
         packed |= (unsigned)i << (2 + 10 * cnt);
         ++cnt;
       }
@@ -346,9 +370,6 @@ constexpr int kSaveMin = 12;
 constexpr int kSaveBytes = 16 + 256 + 512;
 __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
   const QueryCtx QC = make_query_ctx(F);
-  const float* const psx = QC.sx;  // the frame's point arrays, once (F lives in local memory)
-  const float* const psy = QC.sy;
-  const float* const pst = QC.st;
   const int max_quads = F.max_quads;
   // searches are cached per (round, a, b, self); the 7-bit round tag bounds the rounds that may use it
   unsigned long long* const qcache = F.round < 127 ? F.fx_qcache : nullptr;
@@ -506,7 +527,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
         const int i3 = r % n3; r /= n3;
         const int i2 = r % n2; r /= n2;
         const int i1 = r % n1; r /= n1;
-        valid = is_valid_quad_p(psx, psy, pst, packed_cand(p0, r), packed_cand(p1, i1), packed_cand(p2, i2),
+        valid = is_valid_quad_s(QC.P, packed_cand(p0, r), packed_cand(p1, i1), packed_cand(p2, i2),
                                 packed_cand(p3, i3));
       }
       const unsigned m = (__ballot_sync(full, valid) >> gshift) & 0xfu;

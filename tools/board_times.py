@@ -52,8 +52,9 @@ print("  lockstep cycles: take-work %.0f  advance %.0f  queries %.0f  tuples %.0
       % (t[:, 16].mean(), t[:, 17].mean(), t[:, 18].mean(), t[:, 19].mean()))
 print("  searches: lanes asking %.0f  lanes searching (cache miss) %.0f = %.1f%%  iterations with a search %.0f"
       % (t[:, 20].mean(), t[:, 21].mean(), 100.0 * t[:, 21].sum() / max(t[:, 20].sum(), 1), t[:, 22].mean()))
-print("  search loops: bucket rows %.0f  candidate iterations %.0f  (%.1f lanes busy per iteration)"
-      % (t[:, 23].mean(), t[:, 24].mean(), t[:, 25].sum() / max(t[:, 24].sum(), 1)))
+if t[:, 24].sum() > 0:  # only in builds with -DAGB_LOOP_STATS
+    print("  search loops: bucket rows %.0f  candidate iterations %.0f  (%.1f lanes busy per iteration)"
+          % (t[:, 23].mean(), t[:, 24].mean(), t[:, 25].sum() / max(t[:, 24].sum(), 1)))
 worst = np.argsort(-ns)[:5]
 for f in worst[:3]:
     print("  slow frame %d: %.0f us, seeds %d quads %d redo %d saddles %d tags %d; cycles %s"
