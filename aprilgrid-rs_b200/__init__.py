@@ -93,6 +93,7 @@ def lib():
         L.ag_detect_batch.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp, ci, vp, vp]
         L.ag_detect_batch_device.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp, ci, vp, vp, vp]
         L.ag_detect_batch_device_wait.argtypes = [vp, vp]
+        L.ag_detect_batch_wait.argtypes = [vp, ci]
         L.ag_dense_batch_device.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp]
         L.ag_refined_saddle_points.argtypes = [vp, vp, ci, ci, sz, ci, vp, ci, vp]
         L.ag_gaussian_blur_f32.argtypes = [vp, vp, ci, ci, C.c_float, vp]
@@ -239,6 +240,11 @@ class TagDetector:
         fmt, w, h, st = image_format(frames[0])
         return self._check(lib().ag_detect_batch(self._h, _p(frames), frames.strides[0], n, w, h, st,
                                                  fmt, _p(out), out.shape[1], _p(cnt), _p(status)))
+
+    def detect_batch_wait(self, keep_in_flight=0):
+        """With option host_async = 1: block until all but the newest `keep_in_flight` detect_batch_into
+        calls have delivered their results."""
+        return self._check(lib().ag_detect_batch_wait(self._h, keep_in_flight))
 
     def detect_batch_device(self, d_frames_ptr, n_frames, width, height, fmt, d_out_ptr, cap_per_frame,
                             d_counts_ptr, d_status_ptr=None, stream=None, frame_stride=0, row_stride=0):

@@ -117,6 +117,19 @@ struct ag_detector {
   long dense_streams = 1;   // device-batch path: 2 = alternate chunks between two dense streams / buffer sets (measured: no gain)
   int dense_rr = 0;
   cudaEvent_t ev_call = nullptr;
+  // host-buffer path: chunks whose results still sit in a board slot's pinned staging, with the
+  // output arrays of the ag_detect_batch call they belong to (calls may overlap: "host_async")
+  struct HostPend {
+    bool live = false;
+    int f0 = 0, n = 0, cap = 0;
+    uint64_t seq = 0;
+    ag_tag* out = nullptr;
+    int* n_per_frame = nullptr;
+    uint32_t* status = nullptr;
+  } hpend[kBoardSlots];
+  uint64_t host_seq = 0;        // number of ag_detect_batch calls issued
+  bool host_async = false;      // ag_detect_batch returns without collecting its results
+  bool host_truncated = false;  // a collected frame had more tags than its call's cap_per_frame
   bool device_path_busy = false;  // device-batch work may still be in flight on slot 0 / the board slots
   bool device_async = false;  // ag_detect_batch_device returns without ordering the results on the
                               // caller's stream; ag_detect_batch_device_wait does that
@@ -169,7 +182,7 @@ namespace {
 
 // Host-buffer entry points and taps share slot 0 with the device-batch pipeline: wait until the
 // latter has drained before touching the buffers.
-int quiesce_device_path(ag_detector* det);
+int quiesce_device_path(ag_detector* det, bool host_too = true);
 
 int fail(ag_detector* det, int code, const char* msg) {
   if (det) det->err = msg;
@@ -461,7 +474,38 @@ int run_chunk(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeo
   return run_boards(det, S.bb, d_frames, g, n, d_tags, cap, d_ntags, d_status, taps, s);
 }
 
-int quiesce_device_path(ag_detector* det) {
+void copy_out_b(const BoardSlot& B, int n, int cap, ag_tag* out, int* n_per_frame, uint32_t* frame_status,
+                int frame0, bool* truncated);
+
+// Host-buffer path: wait for the chunk staged in board slot bi and hand its results to the output
+// arrays of the call that submitted it.
+int collect_host_slot(ag_detector* det, int bi) {
+  auto& P = det->hpend[bi];
+  if (!P.live) return AG_OK;
+  BoardSlot& B = det->bslot[bi];
+  AG_CUDA(det, cudaEventSynchronize(B.ev_done));
+  copy_out_b(B, P.n, P.cap, P.out, P.n_per_frame, P.status, P.f0, &det->host_truncated);
+  P.live = false;
+  B.pending = false;
+  return AG_OK;
+}
+// ... for every chunk of the calls up to sequence number `upto`, oldest first (board slots are
+// handed out round-robin, so the oldest chunk sits in the slot that is reused next)
+int collect_host(ag_detector* det, uint64_t upto) {
+  for (int k = 0; k < kBoardSlots; ++k) {
+    const int bi = (det->slot_rr + k) % kBoardSlots;
+    if (!det->hpend[bi].live || det->hpend[bi].seq > upto) continue;
+    int rc = collect_host_slot(det, bi);
+    if (rc) return rc;
+  }
+  return AG_OK;
+}
+
+int quiesce_device_path(ag_detector* det, bool host_too) {
+  if (host_too) {
+    int rc = collect_host(det, det->host_seq);
+    if (rc) return rc;
+  }
   if (!det->device_path_busy) return AG_OK;
   for (auto& D : det->slot)
     if (D.done) AG_CUDA(det, cudaEventSynchronize(D.done));
@@ -658,6 +702,8 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     det->board_warps = value;
   } else if (!strcmp(key, "device_async")) {
     det->device_async = value != 0;
+  } else if (!strcmp(key, "host_async")) {
+    det->host_async = value != 0;
   } else if (!strcmp(key, "board_batch_frames")) {
     if (value < 1) return fail(det, AG_ERR_INVALID, "board_batch_frames must be positive");
     det->board_batch_frames = value;
@@ -829,10 +875,13 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
     return fail(det, AG_ERR_INVALID, "null pointer or bad count");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
-  { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
+  // streaming calls ("host_async") leave the chunks of earlier calls in flight
+  { int qrc = quiesce_device_path(det, !det->host_async); if (qrc) return qrc; }
+  if (!det->host_async) det->host_truncated = false;
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
+  const uint64_t seq = ++det->host_seq;
   if (n_frames == 0) return AG_OK;
   // Host frames go through the same pipeline as device-resident ones: one set of dense buffers,
   // eight board slots.  A chunk is uploaded on the upload stream (ahead of the kernels), K1-K4
@@ -845,14 +894,11 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
   if (!det->up_stream) AG_CUDA(det, cudaStreamCreateWithFlags(&det->up_stream, cudaStreamNonBlocking));
   cudaStream_t s = D.stream, up = det->up_stream;
   const size_t chunk_bytes = (size_t)chunk * g.frame_stride;
-  bool truncated = false;
-  struct Pending { int f0, n; bool live; } pend[kBoardSlots] = {};
-  int first = det->slot_rr, used = 0;
   // Chunk schedule: the pipeline fills while the first chunk uploads and drains while the last one
   // is searched, so a large batch starts and ends with quarter and half chunks.
   auto next_chunk = [&](int f0) {
     const int left = n_frames - f0;
-    if (n_frames < 4 * chunk) return std::min(chunk, left);
+    if (n_frames < 4 * chunk || det->host_async) return std::min(chunk, left);  // streaming: no fill / drain
     if (f0 == 0) return chunk / 4 > 0 ? chunk / 4 : 1;
     if (f0 < chunk) return std::min(chunk / 2 > 0 ? chunk / 2 : 1, left);
     if (left <= chunk / 4) return left;
@@ -865,12 +911,8 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
     const int bi = det->slot_rr;
     BoardSlot& B = det->bslot[bi];
     det->slot_rr = (det->slot_rr + 1) % kBoardSlots;
-    if (pend[bi].live) {  // the slot's previous chunk: wait for its results, hand them out
-      AG_CUDA(det, cudaEventSynchronize(B.ev_done));
-      copy_out_b(B, pend[bi].n, cap_per_frame, out, n_per_frame, frame_status, pend[bi].f0, &truncated);
-      pend[bi].live = false;
-      B.pending = false;
-    }
+    // the slot's previous chunk (of this call or an earlier one): wait for its results, hand them out
+    if ((rc = collect_host_slot(det, bi))) return rc;
     if ((rc = ensure_board_slot(det, B, chunk, true))) return rc;
     if ((rc = ensure_host_stage(det, B, chunk_bytes, chunk, cap_per_frame))) return rc;
     const int n = n_this;
@@ -893,19 +935,37 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
                                  cudaMemcpyDeviceToHost, B.bstream));
     AG_CUDA(det, cudaEventRecord(B.ev_done, B.bstream));
     B.pending = true;
-    pend[bi] = {f0, n, true};
-    if (used < kBoardSlots) ++used;
+    auto& P = det->hpend[bi];
+    P.live = true;
+    P.f0 = f0;
+    P.n = n;
+    P.cap = cap_per_frame;
+    P.seq = seq;
+    P.out = out;
+    P.n_per_frame = n_per_frame;
+    P.status = frame_status;
   }
-  for (int k = 0; k < kBoardSlots; ++k) {  // oldest first
-    const int bi = (first + k) % kBoardSlots;
-    if (!pend[bi].live) continue;
-    BoardSlot& B = det->bslot[bi];
-    AG_CUDA(det, cudaEventSynchronize(B.ev_done));
-    copy_out_b(B, pend[bi].n, cap_per_frame, out, n_per_frame, frame_status, pend[bi].f0, &truncated);
-    B.pending = false;
+  if (det->host_async) return AG_OK;  // results are collected by later calls / ag_detect_batch_wait
+  if ((rc = collect_host(det, seq))) return rc;
+  if (det->host_truncated) {
+    det->host_truncated = false;
+    return fail(det, AG_ERR_CAPACITY, "cap_per_frame too small for at least one frame");
   }
-  (void)used;
-  if (truncated) return fail(det, AG_ERR_CAPACITY, "cap_per_frame too small for at least one frame");
+  return AG_OK;
+}
+
+int ag_detect_batch_wait(ag_detector* det, int keep_in_flight) {
+  if (!det) return AG_ERR_INVALID;
+  if (keep_in_flight < 0) return fail(det, AG_ERR_INVALID, "keep_in_flight must be >= 0");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  if ((uint64_t)keep_in_flight >= det->host_seq) return AG_OK;
+  int rc = collect_host(det, det->host_seq - (uint64_t)keep_in_flight);
+  if (rc) return rc;
+  if (det->host_truncated) {
+    det->host_truncated = false;
+    return fail(det, AG_ERR_CAPACITY, "cap_per_frame too small for at least one frame");
+  }
   return AG_OK;
 }
 

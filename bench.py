@@ -170,6 +170,8 @@ def main():
                     help="order every step's results on the stream before the next step starts "
                          "(default: steps stream through the pipeline, one wait at the end)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-sync", action="store_true",
+                    help="e2e with synchronous ag_detect_batch calls (default: streaming, two calls in flight)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -305,20 +307,41 @@ def main():
         h_out = torch.zeros((B, cap * 9), dtype=torch.int32).pin_memory().numpy().view(pkg.TAG_DTYPE).reshape(B, cap)
         h_cnt = torch.zeros(B, dtype=torch.int32).pin_memory().numpy()
         h_status = torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-        for _ in range(2):
-            det.detect_batch_into(hf, h_out, h_cnt, h_status)
+        # streaming: a second set of output arrays, two calls in flight (the uploads of step i+1
+        # overlap the board searches of step i); every step still uploads its frames and
+        # delivers its tags to host memory inside the timed region
+        h_out2 = torch.zeros((B, cap * 9), dtype=torch.int32).pin_memory().numpy().view(pkg.TAG_DTYPE).reshape(B, cap)
+        h_cnt2 = torch.zeros(B, dtype=torch.int32).pin_memory().numpy()
+        h_status2 = torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        outs = [(h_out, h_cnt, h_status), (h_out2, h_cnt2, h_status2)]
+        streaming = not args.e2e_sync
+        det.set_option("host_async", 1 if streaming else 0)
+
+        def host_steps(k):
+            for i in range(k):
+                det.detect_batch_into(hf, *outs[i & 1])
+                if streaming:
+                    det.detect_batch_wait(1)
+            if streaming:
+                det.detect_batch_wait(0)
+
+        host_steps(2)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            det.detect_batch_into(hf, h_out, h_cnt, h_status)
+        host_steps(args.steps)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dt = shard.max_over_ranks(dt, device="cuda")
+        det.set_option("host_async", 0)
         assert np.array_equal(h_cnt, cnt_host), "host-path and device-path results differ"
+        assert args.steps < 2 or np.array_equal(h_cnt2, cnt_host), "host-path and device-path results differ"
+        assert args.steps < 2 or np.array_equal(h_out2, h_out), "streaming host calls disagree"
         e2e = {"value": world * B * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(world * B * W * H),
                "d2h_bytes_per_step": int(world * B * (cap * 36 + 8)),
                "timing": "host wall clock around ag_detect_batch, pinned host frames, max over ranks",
+               "calls": "streaming (host_async): 2 calls in flight, ag_detect_batch_wait" if streaming
+                        else "synchronous",
                "numa_node_of_rank0": numa_node}
 
     # final gather of detections to host: counts only (the records are already on each rank's host)

@@ -107,7 +107,7 @@ AG_API const char* ag_last_error(const ag_detector* det);
 
 /* Tunables.  key: "chunk_frames" (frames per pipeline chunk), "max_clusters",
  * "max_saddles" (per-frame capacities), "profile" (0/1, see ag_stage_times), "device_async"
- * (see ag_detect_batch_device_wait), "board_warps" (warps per frame in the board search:
+ * (see ag_detect_batch_device_wait), "host_async" (see ag_detect_batch_wait), "board_warps" (warps per frame in the board search:
  * 0 = automatic, 1/2/4/8), "board_fast" (0 = general board path only), "board_lattice".
  * Capacities must be set before the first detect call that needs them larger. */
 AG_API int ag_set_option(ag_detector* det, const char* key, long value);
@@ -140,6 +140,17 @@ AG_API int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t
  * host thread) wait for every call issued so far.  Output buffers of calls that are still in
  * flight must not be reused.  (detect_batch over an unbounded frame sequence.)            */
 AG_API int ag_detect_batch_device_wait(ag_detector* det, void* stream);
+
+/* Streaming use of ag_detect_batch (host buffers).  By default a call returns with its results in
+ * the output arrays, so the pipeline fills and drains once per call.  After
+ * ag_set_option(det, "host_async", 1) a call returns as soon as its chunks are enqueued (it
+ * blocks only to recycle staging buffers, handing out the results of older chunks while it does);
+ * ag_detect_batch_wait(det, keep_in_flight) then returns once all but the newest
+ * `keep_in_flight` calls are complete (0 = every call), so that the uploads of one call overlap
+ * the board searches of the one before.  The frames and the output arrays of a call must stay
+ * valid and untouched until a wait has covered it.  AG_ERR_CAPACITY is reported by the wait.
+ * (detect over an unbounded sequence of host images: src/detector.rs:651 `detect`, batched.)  */
+AG_API int ag_detect_batch_wait(ag_detector* det, int keep_in_flight);
 
 /* TagDetector::refined_saddle_points: refined saddles of one host image, reference order. */
 AG_API int ag_refined_saddle_points(ag_detector* det, const void* pixels, int width, int height,

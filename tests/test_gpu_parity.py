@@ -336,6 +336,58 @@ def test_detect_batch_other_formats(pkg, oracle, kw):
         assert_tags_match(g, w)
 
 
+def test_streaming_host_calls_equal_synchronous_calls(pkg):
+    """ag_detect_batch with host_async + ag_detect_batch_wait: calls overlap (a later call recycles the
+    staging of an earlier one and hands its results out), different batches and capacities in
+    flight; results are byte-identical to synchronous calls; AG_ERR_CAPACITY arrives at the wait."""
+    import torch
+    det = pkg.TagDetector(pkg.TagFamily.T36H11)
+    try:
+        n, w, h, cap = 44, 640, 480, 64
+        det.set_option("host_chunk_frames", 4)  # 11 chunks per call: more than the 8 board slots
+        d_frames = torch.empty((2 * n, h, w), dtype=torch.uint8, device="cuda")
+        det.render_boards_device(d_frames.data_ptr(), 2 * n, w, h, 6, 6, 77)
+        torch.cuda.synchronize()
+        frames = d_frames.cpu().numpy()
+        batches = [frames[:n], frames[n:], frames[5:n + 5]]
+
+        def new_out(c):
+            return (np.zeros((n, c), pkg.TAG_DTYPE), np.zeros(n, np.int32), np.zeros(n, np.uint32))
+
+        ref = []
+        for b in batches:
+            o = new_out(cap)
+            det.detect_batch_into(b, *o)
+            ref.append(o)
+        assert ref[0][1].sum() > 0 and not np.array_equal(ref[0][0], ref[1][0])
+        det.set_option("host_async", 1)
+        outs = [new_out(cap) for _ in batches]
+        for k, b in enumerate(batches):
+            det.detect_batch_into(b, *outs[k])
+            if k == 1:
+                det.detect_batch_wait(1)  # call 0 is complete, call 1 may still be in flight
+                assert np.array_equal(outs[0][1], ref[0][1]) and np.array_equal(outs[0][0], ref[0][0])
+        det.detect_batch_wait(0)
+        for o, r in zip(outs, ref):
+            assert np.array_equal(o[1], r[1]) and np.array_equal(o[0], r[0]) and np.array_equal(o[2], r[2])
+        # capacity overflow of a streaming call is reported by the wait; counts stay exact
+        small = new_out(2)
+        det.detect_batch_into(batches[0], *small)
+        with pytest.raises(RuntimeError, match="cap_per_frame"):
+            det.detect_batch_wait(0)
+        assert np.array_equal(small[1], ref[0][1])
+        assert np.array_equal(small[0], ref[0][0][:, :2])
+        det.detect_batch_wait(0)  # nothing pending, no error left over
+        # back to synchronous calls, and the device path after streaming host calls
+        det.detect_batch_into(batches[1], *outs[0])
+        det.set_option("host_async", 0)
+        o = new_out(cap)
+        det.detect_batch_into(batches[2], *o)
+        assert np.array_equal(outs[0][0], ref[1][0]) and np.array_equal(o[0], ref[2][0])
+    finally:
+        det.close()
+
+
 def test_streaming_device_calls_equal_synchronous_calls(pkg, oracle):
     """ag_detect_batch_device with device_async + ag_detect_batch_device_wait: several calls in flight
     over all board slots give byte-identical results to one synchronising call per batch."""
