@@ -167,9 +167,11 @@ __device__ __forceinline__ QueryCtx make_query_ctx(const Frame& F) {
 // (group_query below).
 __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a, int b, int self, uint32_t* tm = nullptr) {
   const unsigned full = 0xffffffffu;
-  const unsigned long long kInf = ~0ull;
+  // key = squared distance bits << 32 | index; "none" carries distance +inf, so the distance of the
+  // third-best candidate is the high word of k2 whether or not three are known
+  const unsigned long long kInf = (0x7f800000ull << 32) | 0xffffffffull;
   unsigned long long k0 = kInf, k1 = kInf, k2 = kInf;
-  float d3f = 3.4e38f;  // distance of the current third-best candidate (cheap first reject)
+  float d3f = __uint_as_float(0x7f800000u);  // distance of the current third-best candidate (cheap first reject)
   auto insert = [&](float d, int i) {
     if (d > d3f) return;
     const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
@@ -177,7 +179,7 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a,
       k2 = k;
       if (k2 < k1) { const unsigned long long t = k1; k1 = k2; k2 = t; }
       if (k1 < k0) { const unsigned long long t = k0; k0 = k1; k1 = t; }
-      if (k2 != kInf) d3f = __uint_as_float((unsigned)(k2 >> 32));
+      d3f = __uint_as_float((unsigned)(k2 >> 32));
     }
   };
   float qx = 0.0f, qy = 0.0f, r2 = -1.0f, r = 0.0f;
@@ -221,7 +223,7 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a,
     // candidates per lane and iteration.
     // Column range and row cut-off follow the third-best distance; they are recomputed only when
     // the third-best candidate changes (sqrt / floor are the expensive part of the row set-up).
-    unsigned long long k2_seen = kInf;
+    float d3_seen = d3f;
     int bx0 = x0, bx1 = x1;
     float stop_d3 = 3.0e38f;  // a row whose lower bound lb has lb^2 * 0.9999 > stop_d3 ends the search
     auto row_setup = [&](int tt, int& re, int& re1) {
@@ -229,9 +231,9 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a,
       if (tt >= t_end) return;
       const int j = (tt + 1) >> 1, yy = (tt & 1) ? cy - j : cy + j;
       if (yy < y0 || yy > y1) return;
-      if (k2 != k2_seen) {
-        k2_seen = k2;
-        const float d3 = __uint_as_float((unsigned)(k2 >> 32));
+      if (d3f != d3_seen) {
+        d3_seen = d3f;
+        const float d3 = d3f;
         stop_d3 = d3;
         const float R = fminf(r, sqrtf(d3) * 1.0001f + 0.01f);
         bx0 = (int)floorf((qx - R) * F.g_inv);
@@ -368,7 +370,9 @@ constexpr int kCtlNext = 6;  // slot of F.ctl: next wave slot (seed) to hand to 
 // the group state's cell window (256 B) and quads (512 B).
 constexpr int kSaveMin = 12;
 constexpr int kSaveBytes = 16 + 256 + 512;
-__device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
+// TM: the instantiation with the timing taps (option board_timing); the production one carries none.
+template <bool TM>
+__device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
   const QueryCtx QC = make_query_ctx(F);
   const int max_quads = F.max_quads;
   // searches are cached per (round, a, b, self); the 7-bit round tag bounds the rounds that may use it
@@ -388,9 +392,9 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
   bool alive = false, list_empty = false;
   int k = 0, n_quads = 0, depth = 0, cur_ci = 0, cur_i = 0;
   int next = 0;  // list cursor (warp-uniform)
-  const bool tmon = F.tm && F.warp == 0 && F.lane == 0;
+  const bool tmon = TM && F.tm && F.warp == 0 && F.lane == 0;
   for (;;) {
-    long long tc0 = clock64();
+    long long tc0 = TM ? clock64() : 0ll;
     // (0) idle groups take the next quads of the list
     const unsigned idle = __ballot_sync(full, !alive) & 0x11111111u;
     if (idle != 0u && !list_empty) {
@@ -488,7 +492,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
     {
       const unsigned nb = __ballot_sync(full, need);
       if (nb == 0u) continue;
-      if (F.tm && F.warp == 0 && F.lane == 0) {
+      if (tmon) {
         F.tm[13] += 1;
         F.tm[14] += __popc(nb) >> 2;
       }
@@ -509,7 +513,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
       qself = (jl == 1 || jl == 2) ? qb : qa;
     }
     __syncwarp();
-    const unsigned mine = group_query(QC, qcache, round_tag, active, need, qa, qb, qself, F.warp == 0 ? F.tm : nullptr);  // whole warp, convergent
+    const unsigned mine = group_query(QC, qcache, round_tag, active, need, qa, qb, qself, (TM && F.warp == 0) ? F.tm : nullptr);  // whole warp, convergent
     if (tmon) { const long long tc = clock64(); F.tm[18] += (uint32_t)(tc - tc0); tc0 = tc; }
     const unsigned p0 = __shfl_sync(full, mine, 0, 4), p1 = __shfl_sync(full, mine, 1, 4);
     const unsigned p2 = __shfl_sync(full, mine, 2, 4), p3 = __shfl_sync(full, mine, 3, 4);
@@ -519,7 +523,7 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
     bool ok = false;
     int nq0 = 0, nq1 = 0, nq2 = 0, nq3 = 0;
     for (int base = 0; __any_sync(full, !ok && base < total); base += 4) {
-      if (F.tm && F.warp == 0 && F.lane == 0) F.tm[15] += 1;
+      if (tmon) F.tm[15] += 1;
       const int t = base + jl;
       bool valid = false;
       if (!ok && t < total) {
@@ -567,6 +571,11 @@ __device__ __noinline__ void warp_score_quads(const Frame& F, int nq) {
     }
     __syncwarp();
   }
+}
+
+__device__ __forceinline__ void warp_score_quads(const Frame& F, int nq) {
+  if (F.tm) warp_score_quads_t<true>(F, nq);
+  else warp_score_quads_t<false>(F, nq);
 }
 
 // ---- init_quads, enumerated by one warp ----------------------------------------------------------
