@@ -140,7 +140,7 @@ k_blur_hessian_tile(const uint8_t* __restrict__ frames, FrameGeom g, float* __re
 }
 
 // -----------------------------------------------------------------------------------------
-// K1, streaming version for 8-bit gray input (the benchmark path).
+// K1, streaming version (8-bit gray is the benchmark path; 16-bit gray and RGB8 share it).
 //
 // One WARP owns a strip of 120 output columns (it computes 128: lanes 0 and 31 only provide the
 // blurred halo column their neighbours need) and marches down a chunk of rows.  Each lane owns
@@ -154,7 +154,8 @@ k_blur_hessian_tile(const uint8_t* __restrict__ frames, FrameGeom g, float* __re
 //     the symmetric taps need only 4 products;
 //   * Hessian: the last three blurred rows of the 4 columns plus one halo column per side.
 // No shared memory, no block barrier.  Clamp-to-edge is obtained by clamping the loaded row /
-// replicating the edge pixel.  Requires width % 4 == 0 and 4-byte aligned rows.
+// replicating the edge pixel.  Requires width % 4 == 0 and rows aligned to the lane's load
+// (4 bytes for L8 and RGB8 -- a lane's 4 RGB pixels are three words --, 8 bytes for L16).
 // -----------------------------------------------------------------------------------------
 constexpr int S_COLS = 120;  // output columns per warp
 constexpr int S_ROWS = 128;  // output rows per warp (chunk)
@@ -164,12 +165,44 @@ AG_D float u8_lane(uint32_t word, int k) {  // byte k of a packed pixel word -> 
   return unorm8_to_f32((float)((word >> (8 * k)) & 0xffu));
 }
 
+// A lane's 4 raw pixels of one row: 1 (L8), 2 (L16) or 3 (RGB8) 32-bit words.
+template <int FMT>
+struct RawPx {
+  static constexpr int NW = FMT == AG_L8 ? 1 : (FMT == AG_L16 ? 2 : 3);
+  uint32_t w[NW];
+};
+template <int FMT>
+AG_D RawPx<FMT> load_raw(const uint8_t* p) {
+  RawPx<FMT> r;
+  if (FMT == AG_L16) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    r.w[0] = v.x;
+    r.w[RawPx<FMT>::NW - 1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < RawPx<FMT>::NW; ++i) r.w[i] = __ldg(reinterpret_cast<const uint32_t*>(p) + i);
+  }
+  return r;
+}
+// luma f32 of pixel k (0..3) of the lane's raw pixels (image 0.25 to_luma32f, see load_luma)
+template <int FMT>
+AG_D float raw_luma(const RawPx<FMT>& r, int k) {
+  if (FMT == AG_L8) {
+    return u8_lane(r.w[0], k);
+  } else if (FMT == AG_L16) {
+    return unorm16_to_f32((float)((r.w[(k >> 1) % RawPx<FMT>::NW] >> (16 * (k & 1))) & 0xffffu));
+  } else {
+    auto byte = [&](int j) { return (r.w[(j >> 2) % RawPx<FMT>::NW] >> (8 * (j & 3))) & 0xffu; };
+    return unorm8_to_f32((float)rgb_luma_u8(byte(3 * k), byte(3 * k + 1), byte(3 * k + 2)));
+  }
+}
+
 struct BlurRow {  // one blurred row: v[1..4] = the lane's 4 columns, v[0] / v[5] = halo columns
   float v[6];
 };
 
-template <bool WRITE_BLUR>
-__global__ void __launch_bounds__(S_WARPS * 32, 8)
+template <int FMT, bool WRITE_BLUR>
+__global__ void __launch_bounds__(S_WARPS * 32, FMT == AG_L8 ? 8 : 6)
 k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __restrict__ blur,
                       float* __restrict__ resp, uint32_t* __restrict__ frame_min) {
   const int lane = threadIdx.x & 31;
@@ -180,7 +213,8 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
   const int Y0 = blockIdx.y * S_ROWS, Y1 = min(Y0 + S_ROWS, g.h);
   const int c0 = X0 - 4 + 4 * lane;  // first of this lane's 4 columns (may lie outside the image)
   const int cw = min(max(c0, 0), g.w - 4);  // column of the word actually loaded
-  const uint8_t* src = frames + (size_t)f * g.frame_stride + cw;
+  constexpr int kBpp = FMT == AG_L8 ? 1 : (FMT == AG_L16 ? 2 : 3);
+  const uint8_t* src = frames + (size_t)f * g.frame_stride + (size_t)cw * kBpp;
   const bool left_out = c0 < 0, right_out = c0 >= g.w;
   const bool writer = lane >= 1 && lane <= 30 && !right_out;
   const bool zero_first = c0 == 0, zero_last = c0 + 3 == g.w - 1;  // image border columns
@@ -188,9 +222,9 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
   const int h1 = g.h - 1;
   const size_t rs = g.row_stride;
 
-  auto load_row = [&](int r) -> uint32_t {
+  auto load_row = [&](int r) -> RawPx<FMT> {
     const int rr = min(max(r, 0), h1);
-    return __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)rr * rs));
+    return load_raw<FMT>(src + (size_t)rr * rs);
   };
 
   // vertical partial sums: aj[c] = what output row (r + 3 - j) has accumulated so far
@@ -205,20 +239,27 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
   float* blur_f = blur + (size_t)f * g.n_px + c0;
 
   const int r_begin = Y0 - 4, r_end = Y1 + 3;  // temp rows r_begin..r_end inclusive
-  uint32_t w_cur = load_row(r_begin), w_n1 = load_row(r_begin + 1), w_n2 = load_row(r_begin + 2);
+  RawPx<FMT> w_cur = load_row(r_begin), w_n1 = load_row(r_begin + 1), w_n2 = load_row(r_begin + 2);
 
   // One row step: consumes raw row r, completes blurred row r-3 into N, emits Hessian row r-4
   // from M (row r-5), C (row r-4), N (row r-3).
   auto step = [&](int r, const BlurRow& M, const BlurRow& C, BlurRow& N) {
-    uint32_t wd = w_cur;
+    RawPx<FMT> wd = w_cur;
     w_cur = w_n1;
     w_n1 = w_n2;
     w_n2 = load_row(r + 3);  // three rows ahead
-    if (left_out) wd = (wd & 0xffu) * 0x01010101u;  // replicate pixel 0
-    if (right_out) wd = (wd >> 24) * 0x01010101u;   // replicate pixel w-1
+    if (FMT == AG_L8) {
+      if (left_out) wd.w[0] = (wd.w[0] & 0xffu) * 0x01010101u;  // replicate pixel 0
+      if (right_out) wd.w[0] = (wd.w[0] >> 24) * 0x01010101u;   // replicate pixel w-1
+    }
     // ---- gray conversion + halo exchange: p[0..9] = pixels c0-3 .. c0+6
     float p[10];
-    p[3] = u8_lane(wd, 0); p[4] = u8_lane(wd, 1); p[5] = u8_lane(wd, 2); p[6] = u8_lane(wd, 3);
+    p[3] = raw_luma<FMT>(wd, 0); p[4] = raw_luma<FMT>(wd, 1); p[5] = raw_luma<FMT>(wd, 2);
+    p[6] = raw_luma<FMT>(wd, 3);
+    if (FMT != AG_L8) {  // strips hanging over the image edge replicate the edge pixel
+      if (left_out) p[4] = p[5] = p[6] = p[3];
+      if (right_out) p[3] = p[4] = p[5] = p[6];
+    }
     p[0] = __shfl_up_sync(0xffffffffu, p[4], 1);
     p[1] = __shfl_up_sync(0xffffffffu, p[5], 1);
     p[2] = __shfl_up_sync(0xffffffffu, p[6], 1);
@@ -442,15 +483,22 @@ int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames,
   int launches = 0;
   k_fill_u32<<<(n_frames + 255) / 256, 256, 0, s>>>(frame_min, n_frames, kOrderedFltMax);
   ++launches;
-  const bool can_stream = g.format == AG_L8 && (g.w % 4) == 0 && g.w >= 8 && (g.row_stride % 4) == 0 &&
-                          (g.frame_stride % 4) == 0 && ((uintptr_t)frames % 4) == 0 && variant != 1;
+  const size_t al = g.format == AG_L16 ? 8 : 4;  // alignment of a lane's load
+  const bool can_stream = (g.w % 4) == 0 && g.w >= 8 && (g.row_stride % al) == 0 && (g.frame_stride % al) == 0 &&
+                          ((uintptr_t)frames % al) == 0 && variant != 1;
   if (can_stream) {
     const int strips = (g.w + S_COLS - 1) / S_COLS;
     dim3 grid((strips + S_WARPS - 1) / S_WARPS, (g.h + S_ROWS - 1) / S_ROWS, n_frames);
-    if (write_blur)
-      k_blur_hessian_stream<true><<<grid, S_WARPS * 32, 0, s>>>(frames, g, blur, resp, frame_min);
-    else
-      k_blur_hessian_stream<false><<<grid, S_WARPS * 32, 0, s>>>(frames, g, blur, resp, frame_min);
+    const dim3 block(S_WARPS * 32);
+#define AG_STREAM(FMT)                                                                             \
+    if (write_blur) k_blur_hessian_stream<FMT, true><<<grid, block, 0, s>>>(frames, g, blur, resp, frame_min); \
+    else k_blur_hessian_stream<FMT, false><<<grid, block, 0, s>>>(frames, g, blur, resp, frame_min)
+    switch (g.format) {
+      case AG_L8: AG_STREAM(AG_L8); break;
+      case AG_L16: AG_STREAM(AG_L16); break;
+      default: AG_STREAM(AG_RGB8); break;
+    }
+#undef AG_STREAM
     return launches + 1;
   }
   switch (g.format) {

@@ -124,6 +124,27 @@ def test_streaming_dense_kernel_shapes(detector, oracle, shape):
     assert g["min"] == g2["min"]
 
 
+@pytest.mark.parametrize("fmt", ["l16", "rgb8"])
+@pytest.mark.parametrize("shape", [(5, 8), (17, 120), (9, 124), (130, 244), (140, 364)])
+def test_streaming_dense_kernel_formats(detector, oracle, fmt, shape):
+    """16-bit gray and RGB8 frames whose width is a multiple of 4 take the register-marching K1 too
+    (a lane's 4 pixels are 2 / 3 words): bit-exact with the oracle and with the generic tile kernel."""
+    rng = np.random.default_rng(shape[0] * 77 + shape[1] + len(fmt))
+    if fmt == "l16":
+        img = rng.integers(0, 65536, shape, dtype=np.uint16)
+    else:
+        img = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+    g, o = check_stages(detector, oracle, img, check_board=False)
+    detector.set_option("dense_variant", 1)
+    try:
+        g2 = detector.stages(img)
+    finally:
+        detector.set_option("dense_variant", 0)
+    assert np.array_equal(g["blur"].view(np.uint32), g2["blur"].view(np.uint32))
+    assert np.array_equal(g["resp"].view(np.uint32), g2["resp"].view(np.uint32))
+    assert g["min"] == g2["min"]
+
+
 def test_constant_image_gives_empty_map(detector, oracle):
     for v in (0, 128, 255):
         img = np.full((48, 64), v, np.uint8)
