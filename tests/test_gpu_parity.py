@@ -306,6 +306,28 @@ def test_saddle_tiers_of_the_board_kernel(pkg, oracle):
                 det.close()
 
 
+def test_4k_rgb_dense_board_through_detect_kornia(pkg, oracle):
+    """BASELINE.json configs[3]: 3840 x 2160 RGB8, 24 x 13 tags.  The frame has more refined saddles
+    than the default capacity (flagged and truncated there, exact with a larger `max_saddles`), far
+    more than the on-chip tiers (general board path), more runs than the run-based labeller takes
+    (pixel-list labeller), and the RGB rows go through the streaming K1."""
+    img = synth.render_board_numpy(3840, 2160, cols=24, rows=13, seed=3, tag_px=100.0, ss=2, rgb=True)
+    fe = oracle.front_end(img, want_labels=False)
+    want = oracle.detect(img)
+    assert len(fe["refined"]) > 2048 and len(want) > 290
+    det = pkg.TagDetector(pkg.TagFamily.T36H11)
+    try:
+        tags, status = det.detect_batch(img[None], cap_per_frame=512, return_status=True)
+        assert status[0] & 2  # AG_FRAME_SADDLE_OVERFLOW at the default capacity: reported, not silent
+        det.set_option("max_saddles", 4096)
+        tags, status = det.detect_batch(img[None], cap_per_frame=512, return_status=True)
+        assert status[0] == 0
+        assert_tags_match(tags[0], want)
+        assert_tags_match(det.detect_kornia(img), want)
+    finally:
+        det.close()
+
+
 def test_label_kernel_variants_agree(pkg, oracle, images):
     """K3 run-based (shared-memory union-find over runs) and pixel-list versions: same cluster
     centres, same order, bit for bit, on images, noise (fallback: too many runs) and odd shapes."""
