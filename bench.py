@@ -368,8 +368,8 @@ def main():
         roofline = {"bound": "hbm", "kernel": "k_blur_hessian_stream (K1: gray->blur->Hessian->min)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src,
-                    "traffic": 6.055e9 * frames_per_launch / 512.0,
-                    "traffic_source": "profiles/r1d_ncu_full_summary.txt (ncu --set full, 512-frame launch: "
+                    "traffic": 6.056e9 * frames_per_launch / 512.0,
+                    "traffic_source": "profiles/r1g_ncu_full_summary.txt (ncu --set full, 512-frame launch: "
                                       "0.72 GB read + 5.33 GB written = 6.05 GB vs 6.04 GB algorithmic)",
                     "algorithmic_bytes_per_launch": alg,
                     "avg_launch_ms": k1_alone_ms if k1_alone_ms else k1_avg_s * 1e3,
