@@ -126,6 +126,17 @@ __device__ __noinline__ void grid_build_warp(Frame& F) {
 // scan of the whole window.
 // The frame's fields the neighbour search needs, read once per warp_score_quads call and kept in
 // registers (the Frame itself lives in local memory; the search runs hundreds of times per call).
+// A pointer into the block's dynamic shared memory, re-derived from the shared array itself: the
+// compiler then knows the address space and emits LDS / STS with 32-bit addresses instead of
+// generic loads and stores through 64-bit pointers (the Frame holds generic pointers because the
+// general path may point them at global memory).  Only for pointers known to be in shared memory.
+extern __shared__ __align__(16) uint8_t agb_dyn_smem[];
+template <class T>
+__device__ __forceinline__ T* as_shared(T* p) {
+  const unsigned off = (unsigned)__cvta_generic_to_shared(p) - (unsigned)__cvta_generic_to_shared(agb_dyn_smem);
+  return (T*)(agb_dyn_smem + off);
+}
+
 // The saddle list of a throughput-path frame lives in shared memory (F.fast_on requires it): x, y
 // and theta arrays `stride` bytes apart, read with 32-bit shared addresses.
 struct Pts {
@@ -383,7 +394,10 @@ __device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
   const unsigned full = 0xffffffffu;
   const int grp = F.lane >> 2, jl = F.lane & 3, gshift = grp * 4;
   const unsigned gmask = 0xfu << gshift;
-  uint8_t* gs = F.fx_gstate + grp * kGroupBytes;
+  uint8_t* const gstate = as_shared(F.fx_gstate);
+  const int16_t* const qlist = as_shared(F.fx_qlist);
+  uint16_t* const qscore = as_shared(F.fx_qscore);
+  uint8_t* gs = gstate + grp * kGroupBytes;
   uint8_t* cell = gs + kGOffCell;
   int16_t* quads = (int16_t*)(gs + kGOffQuads);
   uint16_t* stack = (uint16_t*)(gs + kGOffStack);
@@ -413,7 +427,7 @@ __device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
         for (int t = 0; t < 8; ++t) active[jl + 4 * t] = 0xffffffffu;
         __syncwarp(gmask);
         if (jl == 0) {
-          const int16_t* quad = F.fx_qlist + 4 * k;
+          const int16_t* quad = qlist + 4 * k;
           for (int j = 1; j < 4; ++j) {  // quad[0] stays active (board.rs:35-37)
             const int sdl = quad[j];
             active[sdl >> 5] &= ~(1u << (sdl & 31));
@@ -463,7 +477,7 @@ __device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
         break;
       }
       if (result >= 0) {
-        if (jl == 0) F.fx_qscore[k] = (uint16_t)result;
+        if (jl == 0) qscore[k] = (uint16_t)result;
         alive = false;
       }
     }
@@ -477,11 +491,11 @@ __device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
       const unsigned best = __reduce_max_sync(full, key);
       if ((int)(best >> 16) > save_score) {  // warp-uniform
         const int src_lane = __ffs((int)__ballot_sync(full, key == best)) - 1;  // leader of the winning group
-        const uint8_t* src = F.fx_gstate + (src_lane >> 2) * kGroupBytes;
+        const uint8_t* src = gstate + (src_lane >> 2) * kGroupBytes;
         save_score = (int)(best >> 16);
         const int kk = 0xffff - (int)(best & 0xffffu);
         if (F.lane == 0) *(int*)save = save_score;
-        if (F.lane < 4) ((int16_t*)(save + 4))[F.lane] = F.fx_qlist[4 * kk + F.lane];
+        if (F.lane < 4) ((int16_t*)(save + 4))[F.lane] = qlist[4 * kk + F.lane];
         const uint32_t* s32 = (const uint32_t*)src;  // cell window [0, 256) and quads [256, 768)
         uint32_t* d32 = (uint32_t*)(save + 16);
 #pragma unroll
