@@ -611,6 +611,11 @@ struct SeedEnum {
 // by bisection on its bit pattern (d2 >= 0: the IEEE bits are monotone) with one warp reduction
 // per bit, the saddles at or below it are gathered and sorted by a 64-wide bitonic network.
 __device__ __noinline__ int nearest_k_fast(Frame& F, float qx, float qy, int k, unsigned long long* scratch64) {
+  // the throughput path keeps these arrays in shared memory: address them as such (as_shared)
+  int16_t* const nn_idx = as_shared(F.nn_idx);
+  const float* const sx = as_shared(F.sx);
+  const float* const sy = as_shared(F.sy);
+  scratch64 = as_shared(scratch64);
   const int n = F.n;
   const int kk = k < n ? k : n;
   if (kk <= 0) return 0;
@@ -619,7 +624,7 @@ __device__ __noinline__ int nearest_k_fast(Frame& F, float qx, float qy, int k, 
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int i = F.lane + 32 * j;
-    db[j] = i < n ? __float_as_uint(dist2(F, qx, qy, i)) : 0xffffffffu;
+    db[j] = i < n ? __float_as_uint(fadd(fmul(fsub(qx, sx[i]), fsub(qx, sx[i])), fmul(fsub(qy, sy[i]), fsub(qy, sy[i])))) : 0xffffffffu;
   }
   // smallest T with |{d <= T}| >= kk  (NaN / negative patterns cannot occur: d2 = x*x + y*y)
   unsigned T = 0;
@@ -670,38 +675,48 @@ __device__ __noinline__ int nearest_k_fast(Frame& F, float qx, float qy, int k, 
       }
     }
   }
-  if (F.lane < kk) F.nn_idx[F.lane] = (int16_t)(unsigned)v0;
-  if (F.lane + 32 < kk) F.nn_idx[F.lane + 32] = (int16_t)(unsigned)v1;
+  if (F.lane < kk) nn_idx[F.lane] = (int16_t)(unsigned)v0;
+  if (F.lane + 32 < kk) nn_idx[F.lane + 32] = (int16_t)(unsigned)v1;
   __syncwarp();
   return kk;
 }
 
 // 50-NN of the seed, same / diff classification (detector.rs:550-563), per-diff vectors.
 __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
+  // the throughput path keeps these arrays in shared memory: address them as such (as_shared)
+  const float* const sx = as_shared(F.sx);
+  const float* const sy = as_shared(F.sy);
+  const float* const st = as_shared(F.st);
+  int16_t* const nn_idx = as_shared(F.nn_idx);
+  int16_t* const same = as_shared(F.same);
+  int16_t* const diff = as_shared(F.diff);
+  float* const dvx = as_shared(F.fx_dvx);
+  float* const dvy = as_shared(F.fx_dvy);
+  unsigned long long* const tmask = as_shared(F.fx_tmask);
   E.s0 = s0;
   // the 1 KB at fx_dvx (dvx, dvy, tmask) is free until the classification below fills it
-  int n_nn = nearest_k_fast(F, F.sx[s0], F.sy[s0], 50, (unsigned long long*)F.fx_dvx);
-  if (n_nn < 0) n_nn = nearest_k(F, F.sx[s0], F.sy[s0], 50);
-  const float t0 = F.st[s0], x0 = F.sx[s0], y0 = F.sy[s0];
+  int n_nn = nearest_k_fast(F, sx[s0], sy[s0], 50, (unsigned long long*)F.fx_dvx);
+  if (n_nn < 0) n_nn = nearest_k(F, sx[s0], sy[s0], 50);
+  const float t0 = st[s0], x0 = sx[s0], y0 = sy[s0];
   int n_same = 0, n_diff = 0;
   for (int base = 1; base < n_nn; base += 32) {  // nearest[1..]: the first hit is the seed itself
     const int j = base + F.lane;
     int si = 0;
     bool is_same = false, is_diff = false;
     if (j < n_nn) {
-      si = F.nn_idx[j];
-      const float td = theta_distance_degree(t0, F.st[si]);
+      si = nn_idx[j];
+      const float td = theta_distance_degree(t0, st[si]);
       is_same = td < 5.0f;
       is_diff = !is_same && td > 80.0f;
     }
     const unsigned ms = __ballot_sync(0xffffffffu, is_same), md = __ballot_sync(0xffffffffu, is_diff);
     const unsigned lt = (1u << F.lane) - 1u;
-    if (is_same) F.same[n_same + __popc(ms & lt)] = (int16_t)si;
+    if (is_same) same[n_same + __popc(ms & lt)] = (int16_t)si;
     if (is_diff) {
       const int d = n_diff + __popc(md & lt);
-      F.diff[d] = (int16_t)si;
-      F.fx_dvx[d] = fsub(F.sx[si], x0);
-      F.fx_dvy[d] = fsub(F.sy[si], y0);
+      diff[d] = (int16_t)si;
+      dvx[d] = fsub(sx[si], x0);
+      dvy[d] = fsub(sy[si], y0);
     }
     n_same += __popc(ms);
     n_diff += __popc(md);
@@ -714,8 +729,8 @@ __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
     const int a = blk * 32 + F.lane;
     bool ok = false;
     if (a < n_same) {
-      const int s1 = F.same[a];
-      ok = quad_diag_ok_v(x0, y0, t0, F.sx[s1], F.sy[s1]);
+      const int s1 = same[a];
+      ok = quad_diag_ok_v(x0, y0, t0, sx[s1], sy[s1]);
     }
     E.diag_ok[blk & 1] = __ballot_sync(0xffffffffu, ok);
   }
@@ -724,11 +739,11 @@ __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
   for (int base = 0; base < n_diff; base += 32) {
     const int i = base + F.lane;
     if (i < n_diff) {
-      const float ti = F.st[F.diff[i]];
+      const float ti = st[diff[i]];
       unsigned long long m = 0ull;
       for (int j = i + 1; j < n_diff; ++j)
-        if (!(theta_distance_degree(ti, F.st[F.diff[j]]) > 5.0f)) m |= 1ull << j;
-      F.fx_tmask[i] = m;
+        if (!(theta_distance_degree(ti, st[diff[j]]) > 5.0f)) m |= 1ull << j;
+      tmask[i] = m;
     }
   }
   __syncwarp();
@@ -742,8 +757,19 @@ __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
 // Appends valid quads to F.fx_qlist (from *list_n on) until the seed is exhausted (returns true)
 // or the list may not hold another batch (returns false; call again after draining the list).
 __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) {
+  // the throughput path keeps these arrays in shared memory: address them as such (as_shared)
+  const float* const sx = as_shared(F.sx);
+  const float* const sy = as_shared(F.sy);
+  uint32_t* const squeue = as_shared(F.fx_squeue);
+  int16_t* const same = as_shared(F.same);
+  int16_t* const diff = as_shared(F.diff);
+  const float* const st = as_shared(F.st);
+  int16_t* const qlist = as_shared(F.fx_qlist);
+  float* const dvx = as_shared(F.fx_dvx);
+  float* const dvy = as_shared(F.fx_dvy);
+  unsigned long long* const tmask = as_shared(F.fx_tmask);
   const unsigned lt = (1u << F.lane) - 1u;
-  const float x0 = F.sx[E.s0], y0 = F.sy[E.s0];
+  const float x0 = sx[E.s0], y0 = sy[E.s0];
   for (;;) {
     if (E.q_n >= 32 || (E.exhausted && E.q_n > 0)) {
       // expensive gates for up to 32 survivors, in order
@@ -752,18 +778,18 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
       bool valid = false;
       int s1 = 0, d0 = 0, d1 = 0;
       if (F.lane < take) {
-        const unsigned e = F.fx_squeue[(E.q_head + F.lane) & 63];
-        s1 = F.same[e & 0xffu];
-        d0 = F.diff[(e >> 8) & 0xffu];
-        d1 = F.diff[(e >> 16) & 0xffu];
-        valid = quad_rest_ok_v(x0, y0, F.sx[d0], F.sy[d0], F.st[d0], F.sx[s1], F.sy[s1], F.sx[d1], F.sy[d1],
-                               F.st[d1]);
+        const unsigned e = squeue[(E.q_head + F.lane) & 63];
+        s1 = same[e & 0xffu];
+        d0 = diff[(e >> 8) & 0xffu];
+        d1 = diff[(e >> 16) & 0xffu];
+        valid = quad_rest_ok_v(x0, y0, sx[d0], sy[d0], st[d0], sx[s1], sy[s1], sx[d1], sy[d1],
+                               st[d1]);
       }
       const unsigned m = __ballot_sync(0xffffffffu, valid);
       if (valid) {
         // winding (detector.rs:571-583)
-        const float c0 = cross2(fsub(F.sx[d0], x0), fsub(F.sy[d0], y0), fsub(F.sx[s1], x0), fsub(F.sy[s1], y0));
-        int16_t* q = F.fx_qlist + 4 * (*list_n + __popc(m & lt));
+        const float c0 = cross2(fsub(sx[d0], x0), fsub(sy[d0], y0), fsub(sx[s1], x0), fsub(sy[s1], y0));
+        int16_t* q = qlist + 4 * (*list_n + __popc(m & lt));
         q[0] = (int16_t)E.s0;
         q[2] = (int16_t)s1;
         if (c0 > 0.0f) { q[1] = (int16_t)d0; q[3] = (int16_t)d1; }
@@ -785,8 +811,8 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
         E.exhausted = true;
         continue;
       }
-      const int s1 = F.same[a];
-      const float v02x = fsub(F.sx[s1], x0), v02y = fsub(F.sy[s1], y0);
+      const int s1 = same[a];
+      const float v02x = fsub(sx[s1], x0), v02y = fsub(sy[s1], y0);
       // Per diff entry d: c = cross(v0d, v02) (side of the diagonal s0 -> s1) and the dot gate
       // (saddle.rs:55-59).  The side gate (:40-45) rejects a pair iff c0 * c1 < 0 with
       // c0 = cross(v01, v02) = c[i] and c1 = cross(v02, v03) = -c[j] exactly (the products commute,
@@ -798,7 +824,7 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
         const int d = base + F.lane;
         bool e = false, ps = false, ng = false;
         if (d < E.n_diff) {
-          const float vx = F.fx_dvx[d], vy = F.fx_dvy[d];
+          const float vx = dvx[d], vy = dvy[d];
           const float c = cross2(vx, vy, v02x, v02y);
           e = !(dot2(vx, vy, v02x, v02y) < 0.0f);
           ps = c > 1.0e-18f;
@@ -814,7 +840,7 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
         unsigned long long m = 0ull;
         if (i < E.n_diff && ((el >> i) & 1ull)) {
           const unsigned long long same_side = ((pos >> i) & 1ull) ? pos : (((neg >> i) & 1ull) ? neg : 0ull);
-          m = F.fx_tmask[i] & el & ~same_side;
+          m = tmask[i] & el & ~same_side;
         }
         E.cand[h] = m;
       }
@@ -843,7 +869,7 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
         while (m != 0ull && pos_q < space) {
           const int j = __ffsll((long long)m) - 1;
           m &= m - 1ull;
-          F.fx_squeue[(E.q_head + E.q_n + pos_q) & 63] = (unsigned)E.a | ((unsigned)i << 8) | ((unsigned)j << 16);
+          squeue[(E.q_head + E.q_n + pos_q) & 63] = (unsigned)E.a | ((unsigned)i << 8) | ((unsigned)j << 16);
           ++pos_q;
         }
         E.cand[h] = m;
@@ -890,6 +916,12 @@ constexpr int kMaxRanges = 8;  // seeds whose quads may share one list batch of 
 // and are ignored, so the outcome equals the sequential loop.
 __device__ __noinline__ int find_best_board_fast(Frame& F) {
   if (F.n == 0) return -1;
+  // shared-memory arrays of the block, addressed as such (as_shared)
+  uint16_t* const qscore = as_shared(F.fx_qscore);
+  int16_t* const qlist = as_shared(F.fx_qlist);
+  uint16_t* const wscore = as_shared(F.fx_wscore);
+  int16_t* const wquad = as_shared(F.fx_wquad);
+  int* const ctl = as_shared(F.ctl);
   long long t0 = clock64();
   if (F.warp == 0) {
     grid_build_warp(F);
@@ -898,8 +930,8 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
   if (F.lane == 0) *(int*)(F.fx_save0 + (size_t)F.warp * F.fx_save_stride) = 0;  // no board kept yet
   __syncthreads();
   AGB_TM_ADD(1, clock64() - t0);
-  int seeds_left = F.ctl[0];
-  F.g_on = F.ctl[5];
+  int seeds_left = ctl[0];
+  F.g_on = ctl[5];
   if (F.g_on) F.g_start = F.g_base + 1;
   // first wave: two seeds (the first board is usually found by the first or second seed); after the
   // first board the leftovers rarely hold another one and every seed will be visited: all (up to
@@ -914,8 +946,8 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
     nw = nw < 30 - count ? nw : 30 - count;
     // slot t of the wave holds seed F.seeds[seeds_left - 1 - t]
     if (F.warp == 0) {
-      if (F.lane < nw) F.fx_wscore[F.lane] = 0;
-      if (F.lane == 0) F.ctl[kCtlNext] = 0;
+      if (F.lane < nw) wscore[F.lane] = 0;
+      if (F.lane == 0) ctl[kCtlNext] = 0;
     }
     __syncthreads();
     t0 = clock64();
@@ -930,7 +962,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
           if (!begun) {
             if (no_more || n_rng == kMaxRanges) break;
             int t = 0;
-            if (F.lane == 0) t = atomicAdd(&F.ctl[kCtlNext], 1);
+            if (F.lane == 0) t = atomicAdd(&ctl[kCtlNext], 1);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= nw) { no_more = true; break; }
             t_cur = t;
@@ -953,18 +985,18 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
         warp_score_quads(F, list_n);
         __syncwarp();
         bool redo = false;
-        for (int k = F.lane; k < list_n; k += 32) redo |= F.fx_qscore[k] == kScoreRedo;
+        for (int k = F.lane; k < list_n; k += 32) redo |= qscore[k] == kScoreRedo;
         if (__any_sync(0xffffffffu, redo)) {
           // boards too large for a group: the general warp-wide build gives the same score
           general_state_init(F);
           for (int k = 0; k < list_n; ++k) {
-            if (F.fx_qscore[k] != kScoreRedo) continue;  // warp-uniform
+            if (qscore[k] != kScoreRedo) continue;  // warp-uniform
             int quad[4];
-            for (int j = 0; j < 4; ++j) quad[j] = F.fx_qlist[4 * k + j];
+            for (int j = 0; j < 4; ++j) quad[j] = qlist[4 * k + j];
             board_build(F, F.bs, quad);
             const int sc = F.bs.score < kScoreRedo ? F.bs.score : kScoreRedo - 1;
             __syncwarp();
-            if (F.lane == 0) F.fx_qscore[k] = (uint16_t)sc;
+            if (F.lane == 0) qscore[k] = (uint16_t)sc;
             __syncwarp();
           }
           board_reset(F, F.bs);
@@ -976,7 +1008,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
         for (int r = 0; r < n_rng; ++r) {
           int bs = -1, bk = kNone;
           for (int k = rng_lo[r] + F.lane; k < rng_hi[r]; k += 32) {
-            const int sc = F.fx_qscore[k];
+            const int sc = qscore[k];
             if (sc > bs) { bs = sc; bk = k; }
           }
 #pragma unroll
@@ -985,10 +1017,10 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
             if (os > bs || (os == bs && ok < bk)) { bs = os; bk = ok; }
           }
           const int t = rng_slot[r];
-          if (bs > (int)F.fx_wscore[t]) {
+          if (bs > (int)wscore[t]) {
             __syncwarp();
-            if (F.lane == 0) F.fx_wscore[t] = (uint16_t)bs;
-            if (F.lane < 4) F.fx_wquad[4 * t + F.lane] = F.fx_qlist[4 * bk + F.lane];
+            if (F.lane == 0) wscore[t] = (uint16_t)bs;
+            if (F.lane < 4) wquad[4 * t + F.lane] = qlist[4 * bk + F.lane];
           }
           __syncwarp();
         }
@@ -1006,10 +1038,10 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
     AGB_TM_ADD(3, clock64() - t0);
     // ---- merge the wave in seed order
     for (int t = 0; t < nw; ++t) {
-      const int sc = F.fx_wscore[t];
+      const int sc = wscore[t];
       if (sc > best_score) {  // best_board_option = Some(board)
         best_score = sc;
-        for (int j = 0; j < 4; ++j) best_quad[j] = F.fx_wquad[4 * t + j];
+        for (int j = 0; j < 4; ++j) best_quad[j] = wquad[4 * t + j];
       }
       if (best_score >= 36) break;
       ++count;
