@@ -63,7 +63,7 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   L.bytes_per_frame = align_up(L.off_warp0 + L.bytes_per_warp * kBoardWarps, 256);
   // shared memory of the block: frame-wide part, then one part per warp
   L.smem_saddles = smem_saddles <= 512 ? 512 : 1024;  // tier of the throughput path
-  L.grid_cap_cells = 1408;  // 1280x1024 at 32 px buckets = 1280 buckets
+  L.grid_cap_cells = agb::kGridCapCells;  // 1280x1024 at 32 px buckets = 1280 buckets
   size_t sm = 0;
   auto stake = [&](size_t bytes) {
     size_t r = sm;
@@ -71,9 +71,12 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
     return r;
   };
   L.sm_pos = stake(sizeof(float) * 3 * L.smem_saddles);
+  // bucket starts (a fixed size), grid-ordered positions, grid-ordered item indices: the throughput
+  // path derives the addresses of the last two from the first (agb::kGridStartBytes, 8 bytes per
+  // saddle of the tier), so the order and the sizes here are part of its contract
   L.sm_gstart = stake(sizeof(uint16_t) * (L.grid_cap_cells + 2));
-  L.sm_gitem = stake(sizeof(uint16_t) * L.smem_saddles);
   L.sm_gpos = stake(sizeof(float2) * L.smem_saddles);
+  L.sm_gitem = stake(sizeof(uint16_t) * L.smem_saddles);
   L.sm_hist = stake(sizeof(int) * agb::kHistBins);
   L.sm_ctl = stake(sizeof(int) * 16);
   // throughput path (ag_board_fast.cuh): per wave slot best score + quad
@@ -210,7 +213,9 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.fx_wscore = (uint16_t*)(smem + L.sm_wave);
   F.fx_wquad = (int16_t*)(F.fx_wscore + 32);
   // block-uniform: the whole frame takes the throughput path or the general one
-  F.fast_on = (fast && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles) ? 1 : 0;
+  F.fast_on = (fast && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles &&
+               L.sm_gpos - L.sm_gstart == (size_t)agb::kGridStartBytes &&
+               L.sm_gitem - L.sm_gpos == sizeof(float2) * (size_t)L.smem_saddles) ? 1 : 0;
 
   // init: every warp clears its lattice and activates every saddle; warp 0 clears the tag map
   {

@@ -25,6 +25,8 @@
 
 namespace agb {
 
+constexpr int kGridCapCells = 1408;  // buckets of the neighbour grid (BoardWsLayout::grid_cap_cells)
+constexpr int kGridStartBytes = ((kGridCapCells + 2) * 2 + 15) & ~15;  // its bucket-start array, 16-byte padded
 constexpr int kQCacheBits = 11;  // neighbour-search cache: 2^11 entries of 8 bytes per frame (group_query)
 constexpr int kQCacheEntries = 1 << kQCacheBits;
 constexpr int kFastMaxSaddles = 1024;  // saddle list and bucket grid live in shared memory (two
@@ -160,7 +162,13 @@ struct QueryCtx {
   Pts P;
   float g_inv;
   int g_nx, g_ny, g_on, n;
-  unsigned a_start, a_pos, a_item;  // shared-memory addresses of the grid arrays
+  // Shared-memory address of the bucket starts (F.g_start = array base + one entry).  The
+  // grid-ordered positions follow that array and the grid-ordered item indices follow the positions
+  // (BoardWsLayout; checked where F.fast_on is set), so their addresses are a_start plus a constant
+  // / plus two saddle-array strides: nothing else has to stay live across the search loops.
+  unsigned a_start;
+  __device__ __forceinline__ unsigned a_pos() const { return a_start + (unsigned)(kGridStartBytes - 2); }
+  __device__ __forceinline__ unsigned a_item() const { return a_pos() + 2u * P.stride; }
 };
 __device__ __forceinline__ QueryCtx make_query_ctx(const Frame& F) {
   QueryCtx C;
@@ -168,8 +176,6 @@ __device__ __forceinline__ QueryCtx make_query_ctx(const Frame& F) {
   C.P.stride = (unsigned)((const char*)F.sy - (const char*)F.sx);  // F.st = F.sy + the same stride
   C.g_inv = F.g_inv; C.g_nx = F.g_nx; C.g_ny = F.g_ny; C.g_on = F.g_on; C.n = F.n;
   C.a_start = F.g_on ? (unsigned)__cvta_generic_to_shared(F.g_start) : 0u;
-  C.a_pos = (unsigned)__cvta_generic_to_shared(F.g_pos);
-  C.a_item = (unsigned)__cvta_generic_to_shared(F.g_item);
   return C;
 }
 // group_knn: the search proper (the up to three nearest saddles within the radius, unfiltered,
@@ -221,7 +227,7 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a,
     }
     const float bsz = 1.0f / F.g_inv;  // bucket side, a power of two: bucket indices are exact
     // shared-memory addresses of the grid arrays (32-bit, LDS instead of generic loads)
-    const unsigned a_start = F.a_start, a_pos = F.a_pos, a_item = F.a_item;
+    const unsigned a_start = F.a_start, a_pos = F.a_pos(), a_item = F.a_item();
     auto lds_u16 = [](unsigned addr) -> int {
       unsigned short v;
       asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
