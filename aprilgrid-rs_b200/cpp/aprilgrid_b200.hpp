@@ -80,6 +80,26 @@ class TagDetector {
     return res;
   }
 
+  // Streaming form of detect_batch over host frames (option "host_async"): submit() returns once the
+  // batch is enqueued, wait(keep_in_flight) once all but the newest keep_in_flight batches have
+  // delivered; frames and the Batch object must stay alive and untouched until then.
+  struct Batch {
+    std::vector<ag_tag> tags;
+    std::vector<int> counts;
+    int cap_per_frame = 0;
+    TagMap frame(int i) const { return to_map(tags.data() + (size_t)i * cap_per_frame, counts[i]); }
+  };
+  void set_streaming(bool on) const { check(ag_set_option(h_, "host_async", on ? 1 : 0)); }
+  void submit(Batch& b, const void* base, size_t frame_stride, int n_frames, int width, int height,
+              size_t row_stride, int format, int cap_per_frame = 128) const {
+    b.tags.assign((size_t)n_frames * cap_per_frame, ag_tag{});
+    b.counts.assign(n_frames, 0);
+    b.cap_per_frame = cap_per_frame;
+    check(ag_detect_batch(h_, base, frame_stride, n_frames, width, height, row_stride, format, b.tags.data(),
+                          cap_per_frame, b.counts.data(), nullptr));
+  }
+  void wait(int keep_in_flight = 0) const { check(ag_detect_batch_wait(h_, keep_in_flight)); }
+
   std::vector<Saddle> refined_saddle_points(const ImageView& img) const {
     std::vector<ag_saddle> out(16384);
     int n = 0;

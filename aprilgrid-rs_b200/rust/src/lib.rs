@@ -88,8 +88,27 @@ mod ffi {
         pub fn ag_detect_batch(det: *mut AgDetector, frames: *const c_void, frame_stride: usize, n_frames: c_int,
                                width: c_int, height: c_int, row_stride: usize, format: c_int, out: *mut AgTag,
                                cap_per_frame: c_int, n_per_frame: *mut c_int, frame_status: *mut u32) -> c_int;
+        pub fn ag_set_option(det: *mut AgDetector, key: *const c_char, value: std::os::raw::c_long) -> c_int;
+        pub fn ag_detect_batch_wait(det: *mut AgDetector, keep_in_flight: c_int) -> c_int;
         pub fn ag_refined_saddle_points(det: *mut AgDetector, pixels: *const c_void, width: c_int, height: c_int,
                                         row_stride: usize, format: c_int, out: *mut Saddle, cap: c_int, n: *mut c_int) -> c_int;
+    }
+}
+
+/// A batch handed to `TagDetector::submit_batch`; keep it alive (and do not move its vectors'
+/// contents) until `wait_batches` has covered it.
+pub struct PendingBatch {
+    frames: Vec<u8>,
+    out: Vec<AgTag>,
+    counts: Vec<c_int>,
+    cap: usize,
+}
+impl PendingBatch {
+    pub fn maps(&self) -> Vec<HashMap<u32, [(f32, f32); 4]>> {
+        let _ = &self.frames;
+        (0..self.counts.len())
+            .map(|i| self.out[i * self.cap..i * self.cap + self.counts[i] as usize].iter().map(|t| (t.id, corners(t))).collect())
+            .collect()
     }
 }
 
@@ -202,6 +221,39 @@ impl TagDetector {
         (0..imgs.len())
             .map(|i| out[i * CAP..i * CAP + counts[i] as usize].iter().map(|t| (t.id, corners(t))).collect())
             .collect()
+    }
+
+    /// New: a stream of batches over host frames.  `submit` enqueues one batch (option "host_async") and
+    /// returns; the returned `PendingBatch` owns the packed frames and the output arrays, which the
+    /// library reads / fills until `wait` has covered the batch.  `wait(keep)` blocks until all but
+    /// the newest `keep` submitted batches are complete; `PendingBatch::maps` then yields the
+    /// per-frame results.  The uploads of one batch overlap the board searches of the one before.
+    pub fn submit_batch(&self, packed: Vec<u8>, n_frames: usize, w: u32, h: u32, stride: usize, fmt: i32) -> PendingBatch {
+        const CAP: usize = 128;
+        let mut b = PendingBatch {
+            frames: packed,
+            out: vec![AgTag { id: 0, xy: [0.0; 8] }; CAP * n_frames],
+            counts: vec![0 as c_int; n_frames],
+            cap: CAP,
+        };
+        let key = std::ffi::CString::new("host_async").unwrap();
+        let rc = unsafe {
+            ffi::ag_set_option(self.h, key.as_ptr(), 1);
+            ffi::ag_detect_batch(self.h, b.frames.as_ptr() as *const c_void, stride * h as usize, n_frames as c_int,
+                                 w as c_int, h as c_int, stride, fmt as c_int, b.out.as_mut_ptr(), CAP as c_int,
+                                 b.counts.as_mut_ptr(), std::ptr::null_mut())
+        };
+        if rc != 0 {
+            panic!("aprilgrid_b200: ag_detect_batch failed ({rc}): {}", last_error(self.h));
+        }
+        b
+    }
+
+    pub fn wait_batches(&self, keep_in_flight: usize) {
+        let rc = unsafe { ffi::ag_detect_batch_wait(self.h, keep_in_flight as c_int) };
+        if rc != 0 {
+            panic!("aprilgrid_b200: ag_detect_batch_wait failed ({rc}): {}", last_error(self.h));
+        }
     }
 
     pub fn refined_saddle_points(&self, img: &DynamicImage) -> Vec<Saddle> {

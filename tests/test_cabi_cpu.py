@@ -24,6 +24,20 @@ def test_header_declares_the_expected_surface():
         assert must in syms
 
 
+def test_streaming_entry_points_are_declared():
+    syms = declared_symbols()
+    assert "ag_detect_batch_wait" in syms and "ag_detect_batch_device_wait" in syms
+
+
+def test_cpp_mirror_header_compiles(tmp_path):
+    """The C++ host-side mirror of the reference API (cpp/aprilgrid_b200.hpp) is header-only: it must
+    at least compile against the C header."""
+    src = tmp_path / "use.cpp"
+    src.write_text('#include "aprilgrid_b200.hpp"\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-I",
+                           os.path.join(ROOT, "aprilgrid-rs_b200", "cpp"), str(src)])
+
+
 def test_library_exports_every_declared_symbol(pkg):
     lib = C.CDLL(pkg.LIB_PATH)
     for s in declared_symbols():
