@@ -143,7 +143,11 @@ struct ag_detector {
   FrameGeom tap_geom{};
   bool tap_valid = false;
   // optional per-stage timing (ag_set_option "profile"): CUDA events between the kernels
-  long dense_variant = 0;   // 0 = streaming K1 where applicable, 1 = always the generic tile kernel
+  // 0 = auto: the streaming K1 where applicable -- its compact loop inside detect, its six-step
+  // loop in ag_dense_batch_device (no board kernel beside it); 1 = always the generic tile kernel;
+  // 2 / 3 = the streaming K1 with the six-step / the compact loop everywhere
+  long dense_variant = 0;
+  bool dense_only_call = false;  // set by ag_dense_batch_device around its run_dense calls
   long board_lattice = 64;  // side of the tag lattice a board may span (16 / 32 / 64)
   // warps per frame in the board kernel: 0 = automatic (1 when a launch has enough frames to
   // fill the GPU with one-warp blocks, 4 otherwise), or 1 / 2 / 4 / 8
@@ -410,8 +414,9 @@ void prof_mark(ag_detector* det, int stage, cudaStream_t s) {
 int run_dense(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
               bool write_blur, cudaStream_t s) {
   prof_mark(det, -1, s);
-  det->launches += launch_blur_hessian(d_frames, g, n, S.d_blur, S.d_resp, S.d_min, write_blur,
-                                       (int)det->dense_variant, s);
+  const int dv = (int)det->dense_variant;
+  const int variant = dv == 0 ? (det->dense_only_call ? 2 : 0) : (dv == 3 ? 0 : dv);
+  det->launches += launch_blur_hessian(d_frames, g, n, S.d_blur, S.d_resp, S.d_min, write_blur, variant, s);
   prof_mark(det, 0, s);
   det->launches += launch_threshold(S.d_resp, g, n, S.d_min, S.d_mask, s);
   prof_mark(det, 1, s);
@@ -862,7 +867,10 @@ int ag_dense_batch_device(ag_detector* det, const void* d_frames, size_t frame_s
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
     const int n = std::min(chunk, n_frames - f0);
     const uint8_t* in = (const uint8_t*)d_frames + (size_t)f0 * g.frame_stride;
-    if ((rc = run_dense(det, S, in, g, n, true, s))) return rc;
+    det->dense_only_call = true;
+    rc = run_dense(det, S, in, g, n, true, s);
+    det->dense_only_call = false;
+    if (rc) return rc;
   }
   return AG_OK;
 }

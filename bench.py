@@ -285,9 +285,11 @@ def main():
         torch.cuda.synchronize()
         det.stage_times(reset=True)
         det.set_option("profile", 1)
+        det.set_option("dense_variant", 3)  # the same K1 instantiation the detect pipeline launches
         for _ in range(3):
             det.dense_batch_device(frames.data_ptr(), B, W, H, pkg.FMT_L8, stream=sp)
         torch.cuda.synchronize()
+        det.set_option("dense_variant", 0)
         det.set_option("profile", 0)
         st_alone = det.stage_times(reset=True)
         k1_alone_ms = st_alone["blur_hessian_min"][0] / max(st_alone["blur_hessian_min"][1], 1)

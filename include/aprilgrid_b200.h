@@ -107,7 +107,8 @@ AG_API const char* ag_last_error(const ag_detector* det);
 
 /* Tunables.  key: "chunk_frames" (frames per pipeline chunk), "max_clusters",
  * "max_saddles" (per-frame capacities), "profile" (0/1, see ag_stage_times), "device_async"
- * (see ag_detect_batch_device_wait), "host_async" (see ag_detect_batch_wait), "board_warps" (warps per frame in the board search:
+ * (see ag_detect_batch_device_wait), "host_async" (see ag_detect_batch_wait), "dense_variant" (K1: 0 auto, 1 generic tile kernel,
+ * 2 / 3 streaming kernel with six / three row steps per loop trip), "board_warps" (warps per frame in the board search:
  * 0 = automatic, 1/2/4/8), "board_fast" (0 = general board path only), "board_lattice".
  * Capacities must be set before the first detect call that needs them larger. */
 AG_API int ag_set_option(ag_detector* det, const char* key, long value);

@@ -145,6 +145,26 @@ def test_streaming_dense_kernel_formats(detector, oracle, fmt, shape):
     assert g["min"] == g2["min"]
 
 
+@pytest.mark.parametrize("shape", [(5, 8), (17, 120), (130, 244), (300, 364), (1024, 1280)])
+def test_streaming_dense_kernel_six_step_loop(detector, oracle, shape):
+    """The K1 instantiation with six row steps per trip (what ag_dense_batch_device launches) gives the
+    same bits as the compact loop of the detect pipeline, for row counts with every remainder."""
+    rng = np.random.default_rng(shape[0] + 3 * shape[1])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    g = detector.stages(img)
+    detector.set_option("dense_variant", 2)
+    try:
+        g2 = detector.stages(img)
+    finally:
+        detector.set_option("dense_variant", 0)
+    assert np.array_equal(g["blur"].view(np.uint32), g2["blur"].view(np.uint32))
+    assert np.array_equal(g["resp"].view(np.uint32), g2["resp"].view(np.uint32))
+    assert g["min"] == g2["min"] and np.array_equal(g["mask"], g2["mask"])
+    if shape[0] <= 300:
+        o = oracle.front_end(img, want_labels=False)
+        assert np.array_equal(g2["blur"].view(np.uint32), o["blur"].view(np.uint32))
+
+
 def test_constant_image_gives_empty_map(detector, oracle):
     for v in (0, 128, 255):
         img = np.full((48, 64), v, np.uint8)
