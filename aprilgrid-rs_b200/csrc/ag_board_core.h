@@ -336,14 +336,6 @@ AGB_FN bool is_valid_quad(const Frame& F, int s0, int d0, int s1, int d1) {
   // the same verdict as the reference's order (saddle.rs:18-38).
   return quad_diag_ok(F, s0, s1) && quad_rest_ok(F, s0, d0, s1, d1);
 }
-// is_valid_quad on points held through register pointers (throughput path: no call, no reload of
-// the frame's fields)
-AGB_FN bool is_valid_quad_p(const float* sx, const float* sy, const float* st, int s0, int d0, int s1, int d1) {
-  const float x0 = sx[s0], y0 = sy[s0], x1 = sx[s1], y1 = sy[s1];
-  if (!quad_diag_ok_v(x0, y0, st[s0], x1, y1)) return false;
-  return quad_rest_ok_v(x0, y0, sx[d0], sy[d0], st[d0], x1, y1, sx[d1], sy[d1], st[d1]);
-}
-
 // ---- nearest neighbours (kdtree 0.8 `nearest`, restated as exact search) -------------------
 // squared_euclidean: (0 + dx*dx) + dy*dy
 AGB_FN float dist2(const Frame& F, float qx, float qy, int i) {
