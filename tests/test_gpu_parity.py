@@ -204,6 +204,42 @@ def test_synthetic_formats(detector, oracle, kw):
     assert sorted(g["tags"]) == list(range(36))
 
 
+def test_empty_and_single_frame_batches(detector, pkg, oracle):
+    """n_frames = 0 is a valid call that touches nothing (host and device entry points); a batch
+    of one equals detect(); null pointers and negative counts are refused."""
+    import torch
+    frames = synth.fixture_like_frames(1, 640, 480, seed=31, tag_px=42.0)
+    want = oracle.detect(frames[0])
+    assert len(want) > 0
+    assert detector.detect_batch(frames[:0]) == []
+    L = pkg.lib()
+    tags = np.zeros((1, 64), pkg.TAG_DTYPE)
+    cnt = np.full(1, -7, np.int32)
+    vp = lambda a: a.ctypes.data_as(__import__("ctypes").c_void_p)
+    rc = L.ag_detect_batch(detector._h, vp(frames), frames.strides[0], 0, 640, 480, 640, pkg.FMT_L8, vp(tags), 64,
+                           vp(cnt), None)
+    assert rc == pkg.AG_OK and cnt[0] == -7 and not tags["id"].any()
+    rc = L.ag_detect_batch(detector._h, vp(frames), frames.strides[0], -1, 640, 480, 640, pkg.FMT_L8, vp(tags), 64,
+                           vp(cnt), None)
+    assert rc == pkg.AG_ERR_INVALID
+    rc = L.ag_detect_batch(detector._h, None, frames.strides[0], 1, 640, 480, 640, pkg.FMT_L8, vp(tags), 64,
+                           vp(cnt), None)
+    assert rc == pkg.AG_ERR_INVALID
+    d_frames = torch.from_numpy(frames).cuda()
+    d_tags = torch.zeros((1, 64 * 9), dtype=torch.int32, device="cuda")
+    d_cnt = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    detector.detect_batch_device(d_frames.data_ptr(), 0, 640, 480, pkg.FMT_L8, d_tags.data_ptr(), 64, d_cnt.data_ptr())
+    torch.cuda.synchronize()
+    assert int(d_cnt[0]) == -7
+    got = detector.detect_batch(frames)
+    assert len(got) == 1
+    assert_tags_match(got[0], want)
+    assert_tags_match(detector.detect(frames[0]), want)
+    detector.detect_batch_device(d_frames.data_ptr(), 1, 640, 480, pkg.FMT_L8, d_tags.data_ptr(), 64, d_cnt.data_ptr())
+    torch.cuda.synchronize()
+    assert int(d_cnt[0]) == len(want)
+
+
 def test_detect_batch_matches_oracle_per_frame(detector, oracle):
     frames = synth.fixture_like_frames(7, 640, 480, seed=20, tag_px=42.0)
     frames[3] = 77  # one empty frame in the middle of the batch
