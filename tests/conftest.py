@@ -63,3 +63,6 @@ def detector(pkg):
 
 FIXTURE_NAMES = ["iphone", "EuRoC", "TUM_VI", "right", "r45", "top", "two_boards", "top_right",
                  "demo_1520525725372653511"]
+
+# tests/tools/ holds stand-alone checking scripts (they use the oracle, so they live with the tests)
+collect_ignore_glob = ["tools/*"]

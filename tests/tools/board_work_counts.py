@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Work counters of the board-search logic (csrc/ag_board_core.h, host build with
 -DAGB_WORK_COUNTERS) on synthetic 1280x1024 board frames: where K6's time can go.
-usage: python tools/board_work_counts.py [n_frames]"""
+usage: python tests/tools/board_work_counts.py [n_frames]"""
 import ctypes as C
 import os
 import subprocess
@@ -9,7 +9,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle  # noqa: E402

@@ -1,13 +1,13 @@
 #!/usr/bin/env python3
 """Run the device-batch detect path repeatedly on the same frames (streaming calls, all pipeline
 slots in use) and check that every repetition gives bit-identical results, and that they equal the
-CPU oracle on a sample.  usage: python tools/stress_determinism.py [n_frames] [reps] [warps]"""
+CPU oracle on a sample.  usage: python tests/tools/stress_determinism.py [n_frames] [reps] [warps]"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
