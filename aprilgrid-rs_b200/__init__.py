@@ -18,6 +18,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libaprilgrid_b200.so")
+if os.environ.get("AG_LIB"):  # profiling tools only: another build of the same library (tools/build_variant.sh)
+    LIB_PATH = os.path.abspath(os.environ["AG_LIB"])
 
 AG_OK, AG_ERR_INVALID, AG_ERR_NO_DEVICE, AG_ERR_CUDA, AG_ERR_CAPACITY, AG_ERR_UNSUPPORTED = range(6)
 FMT_L8, FMT_L16, FMT_RGB8 = 0, 1, 2

@@ -33,7 +33,8 @@ bool family_info(int family, FamilyInfo* f) {  // src/detector.rs:369-405
   return false;
 }
 
-std::string g_create_error;
+// creation errors have no handle to live in: one message per calling thread
+thread_local std::string g_create_error;
 
 // Pipeline slots.  The device-batch path keeps up to kSlots chunks in flight: the dense + sparse
 // front end of chunk i+1 runs on the caller's stream while the latency-bound board searches of
@@ -111,6 +112,7 @@ struct ag_detector {
   std::mutex mu;
   std::string err;
   Slot slot[kSlots];
+  Slot big;  // one-frame slot with grown capacities: frames that overflowed max_clusters / max_saddles are re-run here
   BoardSlot bslot[kBoardSlots];
   int slot_rr = 0;            // next board slot of the device-batch pipeline (rotates across calls)
   cudaStream_t up_stream = nullptr;  // host-frame path: uploads, ahead of the kernels
@@ -126,18 +128,25 @@ struct ag_detector {
     ag_tag* out = nullptr;
     int* n_per_frame = nullptr;
     uint32_t* status = nullptr;
+    const uint8_t* src = nullptr;  // host frames of the chunk (re-run of overflowed frames)
+    FrameGeom g{};
   } hpend[kBoardSlots];
   uint64_t host_seq = 0;        // number of ag_detect_batch calls issued
   bool host_async = false;      // ag_detect_batch returns without collecting its results
   bool host_truncated = false;  // a collected frame had more tags than its call's cap_per_frame
+  bool host_unresolved = false;  // a collected frame overflowed a capacity that could not be grown
   bool device_path_busy = false;  // device-batch work may still be in flight on slot 0 / the board slots
   bool device_async = false;  // ag_detect_batch_device returns without ordering the results on the
                               // caller's stream; ag_detect_batch_device_wait does that
   uint64_t launches = 0;
   long chunk_frames = 512;
   long host_chunk_frames = 128;  // chunk of the host-buffer path (ag_detect_batch)
-  long max_clusters = 16384;
-  long max_saddles = 2048;
+  // per-frame capacities; 0 = automatic (from the image area, see set_caps).  A frame that still
+  // overflows them is re-run on its own with grown capacities (host entry points), so they bound
+  // memory, not results.
+  long max_clusters = 0;
+  long max_saddles = 0;
+  int cur_clusters = 16384, cur_saddles = 2048;  // capacities in force for the current call
   uint64_t* d_codes = nullptr;  // family table in global memory (renderer)
   // stage-tap state
   FrameGeom tap_geom{};
@@ -219,6 +228,23 @@ int make_geom(ag_detector* det, int w, int h, size_t row_stride, size_t frame_st
   return AG_OK;
 }
 
+// Per-frame capacities in force for a call: the options when set, else sized from the image area
+// (1280 x 1024 -> 16384 clusters, 2048 saddles; a 4K frame -> 103680 / 13056).  Real images stay
+// far below them; a frame that does not is flagged and re-run alone with grown capacities.
+void set_caps(ag_detector* det, const FrameGeom& g) {
+  long ncl = det->max_clusters, nsd = det->max_saddles;
+  if (ncl <= 0) ncl = std::min<long>(std::max<long>(g.n_px / 80, 16384), 1l << 22);
+  if (nsd <= 0) nsd = std::min<long>(std::max<long>(((g.n_px / 640 + 255) / 256) * 256, 2048), 16384);
+  det->cur_clusters = (int)ncl;
+  det->cur_saddles = (int)nsd;
+}
+// Frames per pipeline chunk: the option, bounded so that the dense buffers of a chunk (blur +
+// response, 8 bytes per pixel) stay below 8 GB whatever the image size.
+int chunk_limit(const ag_detector* det, const FrameGeom& g, long want) {
+  const long by_mem = std::max<long>(1, (long)((8ull << 30) / ((unsigned long long)g.n_px * 8ull)));
+  return (int)std::max<long>(1, std::min<long>(want, by_mem));
+}
+
 template <typename T>
 int regrow(ag_detector* det, T** p, size_t count) {
   if (*p) AG_CUDA(det, cudaFree(*p));
@@ -241,7 +267,7 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
     AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_front, cudaEventDisableTiming));
     AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_boards, cudaEventDisableTiming));
   }
-  const int nsd = (int)det->max_saddles;
+  const int nsd = det->cur_saddles;
   const bool realloc = frames > B.cap_frames || nsd != B.cap_saddles || det->board_warps != B.cfg_warps ||
                        det->board_lattice != B.cfg_lattice;
   if (B.pending && (realloc || drain)) {
@@ -317,7 +343,7 @@ void free_board_slot(BoardSlot& B) {
 // Make sure a slot can hold `frames` frames of geometry g with `cap_tags` tags per frame.
 // `own_board` = the slot's own board-search side is needed too (host path, taps).
 int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int cap_tags,
-                bool need_input, bool own_board = true) {
+                bool need_input, bool own_board = true, bool need_parent = false) {
   int rc;
   if (!S.stream) {
     AG_CUDA(det, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
@@ -333,7 +359,9 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     AG_CUDA(det, cudaStreamSynchronize(S.stream));
     if ((rc = regrow(det, &S.d_blur, (size_t)F * px))) return rc;
     if ((rc = regrow(det, &S.d_resp, (size_t)F * px))) return rc;
-    if ((rc = regrow(det, &S.d_parent, (size_t)F * px))) return rc;
+    // per-pixel union-find parents: only the labels tap needs them kept; the labelling kernels
+    // that want per-pixel scratch otherwise use the response buffer, which is dead after K2
+    if (S.d_parent) { AG_CUDA(det, cudaFree(S.d_parent)); S.d_parent = nullptr; }
     if ((rc = regrow(det, &S.d_mask, (size_t)F * words))) return rc;
     // the saddle mask is 1-4 % full; a list of 1/8 of the pixels covers every real image, fuller
     // masks (noise) take the word-oriented labelling path
@@ -342,7 +370,7 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     S.cap_px = px;
     S.cap_words = words;
   }
-  const int ncl = (int)det->max_clusters, nsd = (int)det->max_saddles;
+  const int ncl = det->cur_clusters, nsd = det->cur_saddles;
   if (grow_frames || ncl != S.cap_clusters || nsd != S.cap_saddles) {
     AG_CUDA(det, cudaStreamSynchronize(S.stream));
     if ((rc = regrow(det, &S.d_min, (size_t)F))) return rc;
@@ -368,6 +396,10 @@ int ensure_slot(ag_detector* det, Slot& S, const FrameGeom& g, int frames, int c
     if (S.h_tags) cudaFreeHost(S.h_tags);
     AG_CUDA(det, cudaMallocHost((void**)&S.h_tags, sizeof(ag_tag) * (size_t)F * ct));
     S.cap_tags = ct;
+  }
+  if (need_parent && !S.d_parent) {
+    AG_CUDA(det, cudaStreamSynchronize(S.stream));
+    if ((rc = regrow(det, &S.d_parent, (size_t)F * px))) return rc;
   }
   if (need_input) {
     const size_t in_bytes = (size_t)F * g.frame_stride;
@@ -431,7 +463,10 @@ int run_sparse(ag_detector* det, Slot& S, BoardSlot& B, const FrameGeom& g, int 
   prof_mark(det, -1, s);
   // label_variant 0: run-based (no per-pixel parent array) unless the labels tap needs one
   const int variant = (det->label_variant == 0 && !want_pixel_parents) ? 0 : 1;
-  det->launches += launch_label_clusters(S.d_mask, g, n, S.d_parent, S.cap_clusters, S.d_acc,
+  // per-pixel parents: the kept array when the labels tap asked for one (taps), else the response
+  // buffer as scratch (K2 has consumed it; nothing downstream reads it)
+  int* parent = S.d_parent ? S.d_parent : reinterpret_cast<int*>(S.d_resp);
+  det->launches += launch_label_clusters(S.d_mask, g, n, parent, S.cap_clusters, S.d_acc,
                                          S.d_centers, S.d_ncl, d_status,
                                          det->label_list ? S.d_pixlist : nullptr, S.pix_cap, variant,
                                          S.d_label_fallback, s);
@@ -481,9 +516,15 @@ int run_chunk(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeo
 
 void copy_out_b(const BoardSlot& B, int n, int cap, ag_tag* out, int* n_per_frame, uint32_t* frame_status,
                 int frame0, bool* truncated);
+int rerun_frame_grown(ag_detector* det, const uint8_t* host_px, const FrameGeom& g, uint32_t first_status,
+                      ag_tag* out, int cap, int* n_out, uint32_t* status_out);
+
+constexpr uint32_t kGrowable = AG_FRAME_CLUSTER_OVERFLOW | AG_FRAME_SADDLE_OVERFLOW;
 
 // Host-buffer path: wait for the chunk staged in board slot bi and hand its results to the output
-// arrays of the call that submitted it.
+// arrays of the call that submitted it.  A frame that overflowed max_clusters / max_saddles was
+// truncated by the pipeline: it is run again, alone, with grown capacities, so the caller gets
+// the untruncated result (the reference has no such limits, src/detector.rs:505-540) or an error.
 int collect_host_slot(ag_detector* det, int bi) {
   auto& P = det->hpend[bi];
   if (!P.live) return AG_OK;
@@ -492,6 +533,22 @@ int collect_host_slot(ag_detector* det, int bi) {
   copy_out_b(B, P.n, P.cap, P.out, P.n_per_frame, P.status, P.f0, &det->host_truncated);
   P.live = false;
   B.pending = false;
+  for (int i = 0; i < P.n; ++i) {
+    const uint32_t st = B.h_status[i];
+    if (st & kGrowable) {
+      int cnt = 0;
+      uint32_t st2 = 0;
+      int rc = rerun_frame_grown(det, P.src + (size_t)i * P.g.frame_stride, P.g, st,
+                                 P.out + (size_t)(P.f0 + i) * P.cap, P.cap, &cnt, &st2);
+      if (rc) return rc;
+      P.n_per_frame[P.f0 + i] = cnt;
+      if (P.status) P.status[P.f0 + i] = st2;
+      if (cnt > P.cap) det->host_truncated = true;
+      if (st2 & (kGrowable | AG_FRAME_BOARD_OVERFLOW)) det->host_unresolved = true;
+    } else if (st & AG_FRAME_BOARD_OVERFLOW) {
+      det->host_unresolved = true;
+    }
+  }
   return AG_OK;
 }
 // ... for every chunk of the calls up to sequence number `upto`, oldest first (board slots are
@@ -570,6 +627,73 @@ void copy_out_b(const BoardSlot& B, int n, int cap, ag_tag* out, int* n_per_fram
     memcpy(out + (size_t)(frame0 + i) * cap, B.h_tags + (size_t)i * B.hs_tags, sizeof(ag_tag) * m);
     if (frame_status) frame_status[frame0 + i] = B.h_status[i];
   }
+}
+
+// One frame through the whole pipeline on the detector's one-frame slot, with the capacities the
+// frame overflowed grown until it fits (clusters x16 up to 2^22, saddles up to 16384).  Synchronous;
+// uses its own stream and buffers, so chunks of streaming calls may be in flight meanwhile.
+int rerun_frame_grown(ag_detector* det, const uint8_t* host_px, const FrameGeom& g_in, uint32_t first_status,
+                      ag_tag* out, int cap, int* n_out, uint32_t* status_out) {
+  FrameGeom g = g_in;
+  g.frame_stride = g.row_stride * (size_t)g.h;
+  const int save_cl = det->cur_clusters, save_sd = det->cur_saddles;
+  int ncl = save_cl, nsd = save_sd, rc = AG_OK;
+  uint32_t st = first_status;
+  Slot& S = det->big;
+  for (;;) {
+    bool grew = false;
+    if ((st & AG_FRAME_CLUSTER_OVERFLOW) && ncl < (1 << 22)) { ncl = (int)std::min<long>((long)ncl * 16, 1l << 22); grew = true; }
+    if ((st & AG_FRAME_SADDLE_OVERFLOW) && nsd < 16384) { nsd = 16384; grew = true; }
+    if (!grew) break;  // already at the limits: the flags stay set and the caller reports them
+    det->cur_clusters = ncl;
+    det->cur_saddles = nsd;
+    if (!(rc = ensure_slot(det, S, g, 1, det->fam.n_codes, true))) {
+      const size_t bytes = g.row_stride * (size_t)(g.h - 1) + (size_t)g.w * bytes_per_px(g.format);
+      cudaStream_t s = S.stream;
+      // front end first: the board search only runs once the frame fits
+      if (cudaMemcpyAsync(S.d_in, host_px, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) rc = AG_ERR_CUDA;
+      if (!rc) rc = run_dense(det, S, S.d_in, g, 1, true, s);
+      if (!rc) rc = run_sparse(det, S, S.bb, g, 1, S.d_status, s);
+      if (!rc && (cudaMemcpyAsync(S.h_status, S.d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                  cudaStreamSynchronize(s) != cudaSuccess))
+        rc = AG_ERR_CUDA;
+      if (!rc && !(S.h_status[0] & kGrowable)) {
+        rc = run_boards(det, S.bb, S.d_in, g, 1, S.d_tags, S.cap_tags, S.d_ntags, S.d_status, false, s);
+        if (!rc && (cudaMemcpyAsync(S.h_ntags, S.d_ntags, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                    cudaMemcpyAsync(S.h_status, S.d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                    cudaMemcpyAsync(S.h_tags, S.d_tags, sizeof(ag_tag) * (size_t)S.cap_tags, cudaMemcpyDeviceToHost, s) !=
+                        cudaSuccess ||
+                    cudaStreamSynchronize(s) != cudaSuccess))
+          rc = AG_ERR_CUDA;
+      } else if (!rc) {
+        S.h_ntags[0] = 0;  // still too large: no board search on a truncated saddle list
+      }
+      if (rc == AG_ERR_CUDA && det->err.empty()) det->err = "re-run of an overflowed frame failed";
+    }
+    det->cur_clusters = save_cl;
+    det->cur_saddles = save_sd;
+    if (rc) return rc;
+    st = S.h_status[0];
+    const int cnt = S.h_ntags[0];
+    *n_out = cnt;
+    memcpy(out, S.h_tags, sizeof(ag_tag) * (size_t)std::min(std::min(cnt, cap), S.cap_tags));
+    if (cnt > cap) st |= AG_FRAME_TAG_OVERFLOW;
+    if (!(st & kGrowable)) break;
+  }
+  *status_out = st;
+  return AG_OK;
+}
+
+// What a synchronous host call / a wait reports after its chunks were collected.
+int host_call_verdict(ag_detector* det) {
+  const bool trunc = det->host_truncated, unres = det->host_unresolved;
+  det->host_truncated = det->host_unresolved = false;
+  if (unres)
+    return fail(det, AG_ERR_CAPACITY,
+                "a frame exceeds the detector's limits (clusters > 2^22, saddles > 16384 or a board wider than "
+                "the +-31 tag lattice): its result is truncated, see frame_status");
+  if (trunc) return fail(det, AG_ERR_CAPACITY, "cap_per_frame too small for at least one frame");
+  return AG_OK;
 }
 
 }  // namespace
@@ -671,6 +795,7 @@ void ag_destroy(ag_detector* det) {
   cudaSetDevice(det->device);
   cudaDeviceSynchronize();
   for (auto& S : det->slot) free_slot(S);
+  free_slot(det->big);
   for (auto& B : det->bslot) free_board_slot(B);
   if (det->up_stream) cudaStreamDestroy(det->up_stream);
   if (det->ev_call) cudaEventDestroy(det->ev_call);
@@ -690,10 +815,10 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     if (value < 1 || value > 65535) return fail(det, AG_ERR_INVALID, "host_chunk_frames out of range");
     det->host_chunk_frames = value;
   } else if (!strcmp(key, "max_clusters")) {
-    if (value < 16 || value > (1 << 22)) return fail(det, AG_ERR_INVALID, "max_clusters out of range");
+    if (value != 0 && (value < 16 || value > (1 << 22))) return fail(det, AG_ERR_INVALID, "max_clusters out of range (0 = automatic)");
     det->max_clusters = value;
   } else if (!strcmp(key, "max_saddles")) {
-    if (value < 16 || value > 16384) return fail(det, AG_ERR_INVALID, "max_saddles out of range");
+    if (value != 0 && (value < 16 || value > 16384)) return fail(det, AG_ERR_INVALID, "max_saddles out of range (0 = automatic)");
     det->max_saddles = value;
   } else if (!strcmp(key, "dense_variant")) {
     det->dense_variant = value;
@@ -715,8 +840,10 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
   } else if (!strcmp(key, "dense_streams")) {
     if (value < 1 || value > 2) return fail(det, AG_ERR_INVALID, "dense_streams must be 1 or 2");
     det->dense_streams = value;
+#ifdef AG_EXPERIMENTS  // occupancy experiments only (tools/build_variant.sh); not in the shipped library
   } else if (!strcmp(key, "board_smem_pad")) {
     ag::g_board_smem_pad = (int)value;
+#endif
   } else if (!strcmp(key, "label_variant")) {
     if (value < 0 || value > 1) return fail(det, AG_ERR_INVALID, "label_variant must be 0 or 1");
     det->label_variant = value;
@@ -779,7 +906,11 @@ int ag_detect_batch_device(ag_detector* det, const void* d_frames, size_t frame_
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
-  const int chunk = (int)std::min<long>(det->chunk_frames, std::max(n_frames, 1));
+  // chunks of host-buffer calls still in flight share the dense buffers and the board slots:
+  // hand their results out first (streaming host calls and device calls do not overlap)
+  if ((rc = collect_host(det, det->host_seq))) return rc;
+  set_caps(det, g);
+  const int chunk = chunk_limit(det, g, std::min<long>(det->chunk_frames, std::max(n_frames, 1)));
   // One set of dense buffers (slot 0: K1-K4 of consecutive chunks are serial on stream s anyway),
   // kBoardSlots board-search sides: chunk i's K6 runs on its board slot's own stream, so the
   // searches of up to kBoardSlots chunks (of this call and of earlier calls) overlap each other
@@ -861,7 +992,8 @@ int ag_dense_batch_device(ag_detector* det, const void* d_frames, size_t frame_s
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
   Slot& S = det->slot[0];
-  const int chunk = (int)std::min<long>(det->chunk_frames, std::max(n_frames, 1));
+  set_caps(det, g);
+  const int chunk = chunk_limit(det, g, std::min<long>(det->chunk_frames, std::max(n_frames, 1)));
   if ((rc = ensure_slot(det, S, g, chunk, 1, false, false))) return rc;
   cudaStream_t s = stream ? (cudaStream_t)stream : S.stream;
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
@@ -872,31 +1004,37 @@ int ag_dense_batch_device(ag_detector* det, const void* d_frames, size_t frame_s
     det->dense_only_call = false;
     if (rc) return rc;
   }
+  // later calls on this handle (any stream) order themselves after this one through slot 0's event
+  AG_CUDA(det, cudaEventRecord(S.done, s));
+  det->device_path_busy = true;
   return AG_OK;
 }
 
-int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, int n_frames, int width,
-                    int height, size_t row_stride, int format, ag_tag* out, int cap_per_frame,
-                    int* n_per_frame, uint32_t* frame_status) {
+// ag_detect_batch proper.  async_call: return once the chunks are enqueued (streaming use, option
+// host_async); otherwise the results are in the output arrays when the call returns.
+static int detect_batch_host(ag_detector* det, const void* frames, size_t frame_stride, int n_frames, int width,
+                             int height, size_t row_stride, int format, ag_tag* out, int cap_per_frame,
+                             int* n_per_frame, uint32_t* frame_status, bool async_call) {
   if (!det) return AG_ERR_INVALID;
   if (!frames || !out || !n_per_frame || n_frames < 0 || cap_per_frame < 1)
     return fail(det, AG_ERR_INVALID, "null pointer or bad count");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
-  // streaming calls ("host_async") leave the chunks of earlier calls in flight
-  { int qrc = quiesce_device_path(det, !det->host_async); if (qrc) return qrc; }
-  if (!det->host_async) det->host_truncated = false;
+  // streaming calls leave the chunks of earlier calls in flight; a synchronous call first hands
+  // out everything that is still pending (to the output arrays of the calls that submitted it)
+  { int qrc = quiesce_device_path(det, !async_call); if (qrc) return qrc; }
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, frame_stride, format, &g);
   if (rc) return rc;
   const uint64_t seq = ++det->host_seq;
-  if (n_frames == 0) return AG_OK;
+  if (n_frames == 0) return async_call ? AG_OK : host_call_verdict(det);
+  set_caps(det, g);
   // Host frames go through the same pipeline as device-resident ones: one set of dense buffers,
   // eight board slots.  A chunk is uploaded on the upload stream (ahead of the kernels), K1-K4
   // run on the dense stream, K6 and the download of the results on the board slot's stream, so
   // uploads, front end, board searches and downloads of up to eight chunks overlap.  The staged
   // input of a chunk stays in its board slot until K6 (which samples the tag bits) is done.
-  const int chunk = (int)std::min<long>(std::min<long>(det->chunk_frames, det->host_chunk_frames), n_frames);
+  const int chunk = chunk_limit(det, g, std::min<long>(std::min<long>(det->chunk_frames, det->host_chunk_frames), n_frames));
   Slot& D = det->slot[0];
   if ((rc = ensure_slot(det, D, g, chunk, 1, false, false))) return rc;
   if (!det->up_stream) AG_CUDA(det, cudaStreamCreateWithFlags(&det->up_stream, cudaStreamNonBlocking));
@@ -906,7 +1044,7 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
   // is searched, so a large batch starts and ends with quarter and half chunks.
   auto next_chunk = [&](int f0) {
     const int left = n_frames - f0;
-    if (n_frames < 4 * chunk || det->host_async) return std::min(chunk, left);  // streaming: no fill / drain
+    if (n_frames < 4 * chunk || async_call) return std::min(chunk, left);  // streaming: no fill / drain
     if (f0 == 0) return chunk / 4 > 0 ? chunk / 4 : 1;
     if (f0 < chunk) return std::min(chunk / 2 > 0 ? chunk / 2 : 1, left);
     if (left <= chunk / 4) return left;
@@ -936,6 +1074,9 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
     AG_CUDA(det, cudaStreamWaitEvent(B.bstream, B.ev_front, 0));
     if ((rc = run_boards(det, B, B.d_in, g, n, B.d_tags, B.hs_tags, B.d_ntags, B.d_status, false, B.bstream)))
       return rc;
+    // the same events the device-batch path orders itself by: a later device call (or a quiesce)
+    // sees this chunk's board kernel and front end like one of its own
+    AG_CUDA(det, cudaEventRecord(B.ev_boards, B.bstream));
     AG_CUDA(det, cudaMemcpyAsync(B.h_ntags, B.d_ntags, sizeof(int) * n, cudaMemcpyDeviceToHost, B.bstream));
     AG_CUDA(det, cudaMemcpyAsync(B.h_status, B.d_status, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost,
                                  B.bstream));
@@ -952,14 +1093,22 @@ int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, i
     P.out = out;
     P.n_per_frame = n_per_frame;
     P.status = frame_status;
+    P.src = src;
+    P.g = g;
   }
-  if (det->host_async) return AG_OK;  // results are collected by later calls / ag_detect_batch_wait
+  // (a later device-batch call first collects these chunks -- it blocks until they are done -- so
+  // the host path needs no busy flag of its own; streaming host calls must not drain each other)
+  AG_CUDA(det, cudaEventRecord(D.done, s));
+  if (async_call) return AG_OK;  // results are collected by later calls / ag_detect_batch_wait
   if ((rc = collect_host(det, seq))) return rc;
-  if (det->host_truncated) {
-    det->host_truncated = false;
-    return fail(det, AG_ERR_CAPACITY, "cap_per_frame too small for at least one frame");
-  }
-  return AG_OK;
+  return host_call_verdict(det);
+}
+
+int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride, int n_frames, int width,
+                    int height, size_t row_stride, int format, ag_tag* out, int cap_per_frame,
+                    int* n_per_frame, uint32_t* frame_status) {
+  return detect_batch_host(det, frames, frame_stride, n_frames, width, height, row_stride, format, out,
+                           cap_per_frame, n_per_frame, frame_status, det ? det->host_async : false);
 }
 
 int ag_detect_batch_wait(ag_detector* det, int keep_in_flight) {
@@ -970,18 +1119,18 @@ int ag_detect_batch_wait(ag_detector* det, int keep_in_flight) {
   if ((uint64_t)keep_in_flight >= det->host_seq) return AG_OK;
   int rc = collect_host(det, det->host_seq - (uint64_t)keep_in_flight);
   if (rc) return rc;
-  if (det->host_truncated) {
-    det->host_truncated = false;
-    return fail(det, AG_ERR_CAPACITY, "cap_per_frame too small for at least one frame");
-  }
-  return AG_OK;
+  return host_call_verdict(det);
 }
 
+// TagDetector::detect: ALWAYS synchronous (its output arrays usually live on the caller's stack),
+// whatever the streaming option of the handle says; chunks of streaming calls that are still in
+// flight are handed to their own output arrays first.
 int ag_detect(ag_detector* det, const void* pixels, int width, int height, size_t row_stride,
               int format, ag_tag* out, int cap, int* n) {
   if (!n) return det ? fail(det, AG_ERR_INVALID, "n is null") : AG_ERR_INVALID;
   int cnt = 0;
-  int rc = ag_detect_batch(det, pixels, 0, 1, width, height, row_stride, format, out, cap, &cnt, nullptr);
+  int rc = detect_batch_host(det, pixels, 0, 1, width, height, row_stride, format, out, cap, &cnt, nullptr,
+                             false);
   *n = cnt;
   return rc;
 }
@@ -993,13 +1142,13 @@ int ag_stage_run(ag_detector* det, const void* pixels, int width, int height, si
   if (!pixels) return fail(det, AG_ERR_INVALID, "pixels is null");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
-  { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
   det->tap_valid = false;
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, 0, format, &g);
   if (rc) return rc;
-  Slot& S = det->slot[0];
-  if ((rc = ensure_slot(det, S, g, 1, det->fam.n_codes, true))) return rc;
+  set_caps(det, g);
+  Slot& S = det->big;  // the one-frame slot: independent of the batch pipelines
+  if ((rc = ensure_slot(det, S, g, 1, det->fam.n_codes, true, true, true))) return rc;
   const size_t bytes = g.row_stride * (size_t)(g.h - 1) + (size_t)g.w * bytes_per_px(g.format);
   AG_CUDA(det, cudaMemcpyAsync(S.d_in, pixels, bytes, cudaMemcpyHostToDevice, S.stream));
   if ((rc = run_chunk(det, S, S.d_in, g, 1, S.d_tags, S.cap_tags, S.d_ntags, S.d_status, true, S.stream)))
@@ -1015,7 +1164,7 @@ int ag_stage_run(ag_detector* det, const void* pixels, int width, int height, si
   std::lock_guard<std::mutex> lk(det->mu);                                        \
   if (!det->tap_valid) return fail(det, AG_ERR_INVALID, "call ag_stage_run first"); \
   AG_CUDA(det, cudaSetDevice(det->device));                                       \
-  Slot& S = det->slot[0];                                                         \
+  Slot& S = det->big;                                                             \
   const FrameGeom& g = det->tap_geom;                                             \
   (void)g;
 
@@ -1121,23 +1270,52 @@ int ag_refined_saddle_points(ag_detector* det, const void* pixels, int width, in
   if (!pixels || !out || !n) return fail(det, AG_ERR_INVALID, "null pointer");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
-  { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
   det->tap_valid = false;
   FrameGeom g;
   int rc = make_geom(det, width, height, row_stride, 0, format, &g);
   if (rc) return rc;
-  Slot& S = det->slot[0];
-  if ((rc = ensure_slot(det, S, g, 1, 1, true))) return rc;
+  set_caps(det, g);
+  Slot& S = det->big;  // the one-frame slot: independent of the batch pipelines
+  const int save_cl = det->cur_clusters, save_sd = det->cur_saddles;
   const size_t bytes = g.row_stride * (size_t)(g.h - 1) + (size_t)g.w * bytes_per_px(g.format);
-  AG_CUDA(det, cudaMemcpyAsync(S.d_in, pixels, bytes, cudaMemcpyHostToDevice, S.stream));
-  if ((rc = run_dense(det, S, S.d_in, g, 1, true, S.stream))) return rc;
-  if ((rc = run_sparse(det, S, S.bb, g, 1, S.d_status, S.stream))) return rc;
   int cnt = 0;
-  AG_CUDA(det, cudaMemcpyAsync(&cnt, S.bb.d_nref, sizeof(int), cudaMemcpyDeviceToHost, S.stream));
-  AG_CUDA(det, cudaStreamSynchronize(S.stream));
+  uint32_t st = 0;
+  // a frame that overflows the capacities is run again with grown ones (the reference has no limits)
+  for (;;) {
+    if (!(rc = ensure_slot(det, S, g, 1, det->fam.n_codes, true))) {
+      if (cudaMemcpyAsync(S.d_in, pixels, bytes, cudaMemcpyHostToDevice, S.stream) != cudaSuccess) rc = AG_ERR_CUDA;
+      if (!rc) rc = run_dense(det, S, S.d_in, g, 1, true, S.stream);
+      if (!rc) rc = run_sparse(det, S, S.bb, g, 1, S.d_status, S.stream);
+      if (!rc && (cudaMemcpyAsync(S.h_ntags, S.bb.d_nref, sizeof(int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
+                  cudaMemcpyAsync(S.h_status, S.d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, S.stream) !=
+                      cudaSuccess ||
+                  cudaStreamSynchronize(S.stream) != cudaSuccess))
+        rc = AG_ERR_CUDA;
+    }
+    if (rc) break;
+    cnt = S.h_ntags[0];
+    st = S.h_status[0];
+    bool grew = false;
+    if ((st & AG_FRAME_CLUSTER_OVERFLOW) && det->cur_clusters < (1 << 22)) {
+      det->cur_clusters = (int)std::min<long>((long)det->cur_clusters * 16, 1l << 22);
+      grew = true;
+    }
+    if ((st & AG_FRAME_SADDLE_OVERFLOW) && det->cur_saddles < 16384) {
+      det->cur_saddles = 16384;
+      grew = true;
+    }
+    if (!grew) break;
+  }
+  det->cur_clusters = save_cl;
+  det->cur_saddles = save_sd;
+  if (rc) {
+    if (det->err.empty()) det->err = "refined_saddle_points failed";
+    return rc;
+  }
   *n = cnt;
   int m = std::min(cnt, cap);
   if (m > 0) AG_CUDA(det, cudaMemcpy(out, S.bb.d_refined, sizeof(ag_saddle) * m, cudaMemcpyDeviceToHost));
+  if (st & kGrowable) return fail(det, AG_ERR_CAPACITY, "frame exceeds the detector's limits (clusters > 2^22 or saddles > 16384)");
   return cnt > cap ? fail(det, AG_ERR_CAPACITY, "saddle capacity too small") : AG_OK;
 }
 

@@ -116,6 +116,15 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int f = blockIdx.x;  // one block per frame
+  // A frame whose cluster / saddle list was truncated (flagged by K3 / K4) has no meaningful board:
+  // it reports no tags and keeps its flags; the host entry points re-run it with grown capacities.
+  if (frame_status[f] & (uint32_t)(AG_FRAME_CLUSTER_OVERFLOW | AG_FRAME_SADDLE_OVERFLOW)) {  // block-uniform
+    if (threadIdx.x == 0) {
+      n_out[f] = 0;
+      if (tap_n_quads) tap_n_quads[f] = 0;
+    }
+    return;
+  }
   uint8_t* W = ws + (size_t)f * L.bytes_per_frame;
   uint8_t* WW = W + L.off_warp0 + (size_t)warp * L.bytes_per_warp;
   uint8_t* SW = smem + L.sm_warp0 + (size_t)warp * L.smem_per_warp;

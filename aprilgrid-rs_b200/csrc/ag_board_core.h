@@ -48,6 +48,7 @@ struct float2 { float x, y; };  // host test build: the CUDA vector type is not 
 // Optional work counters for the host build (tools/board_work_counts.py); no-ops otherwise.
 #if defined(AGB_WORK_COUNTERS) && !defined(__CUDA_ARCH__)
 extern "C" long long agb_work_counters[32];
+extern "C" void agb_note_query(int a, int b, int self_is_b, float qx, float qy, float r2);
 #define AGB_COUNT(slot, n) (agb_work_counters[(slot) + 12 * agb_work_counters[31]] += (n))
 #else
 #define AGB_COUNT(slot, n) ((void)0)
@@ -606,6 +607,9 @@ AGB_FN int closest_candidates_single(const Frame& F, const BoardState& B, int a,
   const int self = self_is_b ? b : a;
   float px = fadd(F.sx[self], fmul(v10x, ratio0)), py = fadd(F.sy[self], fmul(v10y, ratio0));
   int nn[3];
+#if defined(AGB_WORK_COUNTERS) && !defined(__CUDA_ARCH__)
+  agb_note_query(a, b, self_is_b ? 1 : 0, px, py, radius_sq);
+#endif
   const int c = nearest3_within_single(F, px, py, radius_sq, nn);
   int k = 0;
   for (int j = 0; j < c; ++j)

@@ -27,7 +27,10 @@ namespace agb {
 
 constexpr int kGridCapCells = 1408;  // buckets of the neighbour grid (BoardWsLayout::grid_cap_cells)
 constexpr int kGridStartBytes = ((kGridCapCells + 2) * 2 + 15) & ~15;  // its bucket-start array, 16-byte padded
-constexpr int kQCacheBits = 11;  // neighbour-search cache: 2^11 entries of 8 bytes per frame (group_query)
+#ifndef AGB_QCACHE_BITS
+#define AGB_QCACHE_BITS 11
+#endif
+constexpr int kQCacheBits = AGB_QCACHE_BITS;  // neighbour-search cache: 2^11 entries of 8 bytes per frame (group_query)
 constexpr int kQCacheEntries = 1 << kQCacheBits;
 constexpr int kFastMaxSaddles = 1024;  // saddle list and bucket grid live in shared memory (two
                                        // layout tiers: 512 and 1024 saddles, see make_board_layout)

@@ -23,7 +23,7 @@ __constant__ float c_taps[kBlurTaps] = {
 // ---- gray conversion (image 0.25: to_luma32f) ------------------------------------------
 // v / 255 and v / 65535 correctly rounded, as two FP ops: with r_hi + r_lo = 1/max split in
 // two floats, fma(v, r_hi, v * r_lo) equals RN(v / max) for every u8 / u16 v (checked
-// exhaustively by tests/test_gpu_dense.py::test_unorm_conversion_exhaustive).
+// exhaustively by tests/test_gpu_parity.py::test_unorm_conversion_exhaustive).
 AG_D float unorm8_to_f32(float v) {
   const float rh = __uint_as_float(0x3b808081u), rl = __uint_as_float(0xaf7efeffu);
   return __fmaf_rn(v, rh, __fmul_rn(v, rl));

@@ -77,7 +77,14 @@ typedef struct ag_saddle {
   float x, y, k, theta, phi;
 } ag_saddle;
 
-/* per-frame status bits written to `frame_status` of the batch calls (0 = clean) */
+/* per-frame status bits written to `frame_status` of the batch calls (0 = clean).
+ * The reference has no per-frame limits (src/detector.rs:505-540).  The HOST entry points
+ * (ag_detect, ag_detect_batch, ag_refined_saddle_points) therefore re-run a frame that overflowed
+ * max_clusters / max_saddles with grown capacities (up to 2^22 clusters, 16384 saddles) and report
+ * the untruncated result; only a frame beyond those hard limits, or a board wider than the
+ * lattice, keeps its bits, and the call then returns AG_ERR_CAPACITY -- never AG_OK with a
+ * truncated map.  The DEVICE entry point cannot re-run (its results stay on the device): a frame
+ * with CLUSTER / SADDLE overflow reports zero tags and its bits; the caller checks them. */
 enum {
   AG_FRAME_CLUSTER_OVERFLOW = 1, /* more saddle clusters than max_clusters            */
   AG_FRAME_SADDLE_OVERFLOW = 2,  /* more refined saddles than max_saddles             */
@@ -106,7 +113,8 @@ AG_API void ag_destroy(ag_detector* det);
 AG_API const char* ag_last_error(const ag_detector* det);
 
 /* Tunables.  key: "chunk_frames" (frames per pipeline chunk), "max_clusters",
- * "max_saddles" (per-frame capacities), "profile" (0/1, see ag_stage_times), "device_async"
+ * "max_saddles" (per-frame capacities of the batch pipeline; 0 = automatic, sized from the image
+ * area -- they bound memory, not results: see the frame status bits), "profile" (0/1, see ag_stage_times), "device_async"
  * (see ag_detect_batch_device_wait), "host_async" (see ag_detect_batch_wait), "dense_variant" (K1: 0 auto, 1 generic tile kernel,
  * 2 / 3 streaming kernel with six / three row steps per loop trip), "board_warps" (warps per frame in the board search:
  * 0 = automatic, 1/2/4/8), "board_fast" (0 = general board path only), "board_lattice".
@@ -114,7 +122,8 @@ AG_API const char* ag_last_error(const ag_detector* det);
 AG_API int ag_set_option(ag_detector* det, const char* key, long value);
 
 /* TagDetector::detect on one host image.  `out` receives up to `cap` tags in ascending id
- * order; *n = number found (may exceed cap => AG_ERR_CAPACITY, first cap written).       */
+ * order; *n = number found (may exceed cap => AG_ERR_CAPACITY, first cap written).
+ * Always synchronous, also on a handle whose streaming option "host_async" is on.        */
 AG_API int ag_detect(ag_detector* det, const void* pixels, int width, int height,
                      size_t row_stride, int format, ag_tag* out, int cap, int* n);
 
@@ -150,7 +159,7 @@ AG_API int ag_detect_batch_device_wait(ag_detector* det, void* stream);
  * `keep_in_flight` calls are complete (0 = every call), so that the uploads of one call overlap
  * the board searches of the one before.  The frames and the output arrays of a call must stay
  * valid and untouched until a wait has covered it.  AG_ERR_CAPACITY is reported by the wait.
- * (detect over an unbounded sequence of host images: src/detector.rs:651 `detect`, batched.)  */
+ * (detect over an unbounded sequence of host images: src/detector.rs:505-540 `detect`, batched.)  */
 AG_API int ag_detect_batch_wait(ag_detector* det, int keep_in_flight);
 
 /* TagDetector::refined_saddle_points: refined saddles of one host image, reference order. */

@@ -17,7 +17,17 @@ extern "C" void agb_note_key(int kind, unsigned long long key) {
   agb_work_counters[24 + kind] += 1;  // total (both rounds)
   if (g_keys[r][kind].insert(key).second) agb_work_counters[27 + kind] += 1;  // distinct
 }
-extern "C" void agb_reset_keys() { for (auto& a : g_keys) for (auto& b : a) b.clear(); }
+static std::vector<float> g_queries;  // per query: round, a, b, self_is_b, qx, qy, r2
+extern "C" void agb_note_query(int a, int b, int self_is_b, float qx, float qy, float r2) {
+  const float rec[7] = {(float)agb_work_counters[31], (float)a, (float)b, (float)self_is_b, qx, qy, r2};
+  g_queries.insert(g_queries.end(), rec, rec + 7);
+}
+extern "C" int agb_get_queries(float* out, int cap) {
+  const int n = (int)(g_queries.size() / 7);
+  for (int i = 0; i < n && i < cap; ++i) memcpy(out + 7 * i, &g_queries[7 * (size_t)i], 28);
+  return n;
+}
+extern "C" void agb_reset_keys() { for (auto& a : g_keys) for (auto& b : a) b.clear(); g_queries.clear(); }
 #endif
 
 extern "C" {

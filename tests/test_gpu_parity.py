@@ -363,23 +363,124 @@ def test_saddle_tiers_of_the_board_kernel(pkg, oracle):
 
 
 def test_4k_rgb_dense_board_through_detect_kornia(pkg, oracle):
-    """BASELINE.json configs[3]: 3840 x 2160 RGB8, 24 x 13 tags.  The frame has more refined saddles
-    than the default capacity (flagged and truncated there, exact with a larger `max_saddles`), far
-    more than the on-chip tiers (general board path), more runs than the run-based labeller takes
-    (pixel-list labeller), and the RGB rows go through the streaming K1."""
+    """BASELINE.json configs[3]: 3840 x 2160 RGB8, 24 x 13 tags, through detect / detect_kornia with
+    DEFAULT options.  The frame has more refined saddles than a 1280 x 1024 frame's capacity (the
+    automatic capacity follows the image area), far more than the on-chip tiers (general board
+    path), more runs than the run-based labeller takes (pixel-list labeller), and the RGB rows go
+    through the streaming K1.  With the capacity forced down to 2048 the host entry points re-run
+    the frame with grown capacities (same result); the device entry point flags it."""
+    import torch
     img = synth.render_board_numpy(3840, 2160, cols=24, rows=13, seed=3, tag_px=100.0, ss=2, rgb=True)
     fe = oracle.front_end(img, want_labels=False)
     want = oracle.detect(img)
     assert len(fe["refined"]) > 2048 and len(want) > 290
     det = pkg.TagDetector(pkg.TagFamily.T36H11)
     try:
-        tags, status = det.detect_batch(img[None], cap_per_frame=512, return_status=True)
-        assert status[0] & 2  # AG_FRAME_SADDLE_OVERFLOW at the default capacity: reported, not silent
-        det.set_option("max_saddles", 4096)
+        assert_tags_match(det.detect_kornia(img), want)
+        assert_tags_match(det.detect(img), want)
         tags, status = det.detect_batch(img[None], cap_per_frame=512, return_status=True)
         assert status[0] == 0
         assert_tags_match(tags[0], want)
-        assert_tags_match(det.detect_kornia(img), want)
+        det.set_option("max_saddles", 2048)  # too small for this frame
+        tags, status = det.detect_batch(img[None], cap_per_frame=512, return_status=True)
+        assert status[0] == 0  # re-run with a grown capacity inside the call
+        assert_tags_match(tags[0], want)
+        assert_tags_match(det.detect(img), want)
+        d_img = torch.from_numpy(img).cuda()
+        d_tags = torch.zeros((1, 512 * 9), dtype=torch.int32, device="cuda")
+        d_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        d_st = torch.zeros(1, dtype=torch.int32, device="cuda")
+        det.detect_batch_device(d_img.data_ptr(), 1, 3840, 2160, pkg.FMT_RGB8, d_tags.data_ptr(), 512,
+                                d_cnt.data_ptr(), d_st.data_ptr())
+        torch.cuda.synchronize()
+        assert int(d_st[0]) & 2  # AG_FRAME_SADDLE_OVERFLOW: device-resident results are flagged, not silent
+    finally:
+        det.close()
+
+
+def test_detect_grows_capacities_instead_of_truncating(pkg, oracle):
+    """The reference has no per-frame limits (detector.rs:505-540).  Frames that overflow the
+    cluster / saddle capacities (iid noise: 65 k clusters, 11 k refined saddles; a fine checkerboard:
+    6.9 k refined saddles) come back from detect / detect_batch / refined_saddle_points exactly as
+    the oracle has them, with default options; a frame beyond the hard limits is an error, never a
+    silently truncated map."""
+    rng = np.random.default_rng(5)
+    H, W = 1024, 1280
+    noise = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    checker = np.where(((yy // 12) + (xx // 12)) % 2 == 0, 40, 200).astype(np.uint8)
+    board = synth.render_board_numpy(W, H, seed=5)
+    det = pkg.TagDetector(pkg.TagFamily.T36H11)
+    try:
+        for img, n_min in ((noise, 8000), (checker, 4000)):
+            fe = oracle.front_end(img, want_labels=False)
+            assert len(fe["refined"]) > n_min
+            assert_saddles_match(det.refined_saddle_points(img, cap=32768), fe["refined"])
+        assert_tags_match(det.detect(noise), oracle.detect(noise))
+        frames = np.stack([board, noise, board, noise[::-1].copy()])
+        want = [oracle.detect(f) for f in frames]
+        assert len(want[0]) == 36
+        tags, status = det.detect_batch(frames, return_status=True)
+        assert not status.any()
+        for t, w in zip(tags, want):
+            assert_tags_match(t, w)
+        # streaming calls: overflowed frames are re-run when their chunk is collected
+        det.set_option("host_async", 1)
+        out = np.zeros((4, 128), pkg.TAG_DTYPE)
+        cnt = np.zeros(4, np.int32)
+        st = np.ones(4, np.uint32)
+        det.detect_batch_into(frames, out, cnt, st)
+        det.detect_batch_wait(0)
+        det.set_option("host_async", 0)
+        assert not st.any() and cnt.tolist() == [len(w) for w in want]
+        # beyond the hard limit of 16384 saddles per frame: an error, not a truncated result
+        dense = np.where(((yy // 5) + (xx // 5)) % 2 == 0, 40, 200).astype(np.uint8)
+        if len(oracle.front_end(dense, want_labels=False)["refined"]) > 16384:
+            with pytest.raises(RuntimeError, match="limits"):
+                det.detect(dense)
+            with pytest.raises(RuntimeError, match="limits"):
+                det.refined_saddle_points(dense, cap=65536)
+    finally:
+        det.close()
+
+
+def test_detect_is_synchronous_on_a_streaming_handle(pkg, oracle):
+    """ag_detect writes into buffers that usually live on the caller's stack: it must return complete
+    results even when the handle's streaming option (host_async) is on, and a device-batch call on
+    the same handle must not overtake host chunks that are still in flight."""
+    import torch
+    det = pkg.TagDetector(pkg.TagFamily.T36H11)
+    try:
+        n, w, h, cap = 24, 640, 480, 64
+        det.set_option("host_chunk_frames", 4)
+        d_frames = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+        det.render_boards_device(d_frames.data_ptr(), n, w, h, 6, 6, 4242)
+        torch.cuda.synchronize()
+        frames = d_frames.cpu().numpy()
+        ref = (np.zeros((n, cap), pkg.TAG_DTYPE), np.zeros(n, np.int32), np.zeros(n, np.uint32))
+        det.detect_batch_into(frames, *ref)
+        img = synth.render_board_numpy(w, h, seed=9, tag_px=44.0)
+        want = oracle.detect(img)
+        assert len(want) == 36
+        det.set_option("host_async", 1)
+        for rep in range(3):
+            o = (np.zeros((n, cap), pkg.TAG_DTYPE), np.zeros(n, np.int32), np.zeros(n, np.uint32))
+            det.detect_batch_into(frames, *o)          # chunks in flight
+            assert_tags_match(det.detect(img), want)   # synchronous nevertheless, and correct
+            assert np.array_equal(o[0], ref[0]) and np.array_equal(o[1], ref[1])  # ... and it delivered them
+            det.detect_batch_wait(0)
+        # device call while host chunks are in flight
+        o = (np.zeros((n, cap), pkg.TAG_DTYPE), np.zeros(n, np.int32), np.zeros(n, np.uint32))
+        det.detect_batch_into(frames, *o)
+        tags = torch.zeros((n, cap * 9), dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+        det.detect_batch_device(d_frames.data_ptr(), n, w, h, pkg.FMT_L8, tags.data_ptr(), cap, cnt.data_ptr())
+        torch.cuda.synchronize()
+        det.detect_batch_wait(0)
+        assert np.array_equal(o[0], ref[0]) and np.array_equal(o[1], ref[1])
+        assert np.array_equal(cnt.cpu().numpy(), ref[1])
+        assert np.array_equal(tags.cpu().numpy().view(pkg.TAG_DTYPE).reshape(n, cap), ref[0])
+        det.set_option("host_async", 0)
     finally:
         det.close()
 
