@@ -167,6 +167,7 @@ struct ag_detector {
   bool label_list = true;  // K3 over a compact pixel list (0 = word-oriented version only)
   bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
   bool board_fast = true;  // four-lane group scoring of candidate boards (0 = general path only)
+  bool board_small = true;  // rounds after the first: one lane per candidate board where the saddles fit
   bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -239,9 +240,9 @@ void set_caps(ag_detector* det, const FrameGeom& g) {
   det->cur_saddles = (int)nsd;
 }
 // Frames per pipeline chunk: the option, bounded so that the dense buffers of a chunk (blur +
-// response, 8 bytes per pixel) stay below 8 GB whatever the image size.
+// response, 8 bytes per pixel) stay below 24 GB whatever the image size.
 int chunk_limit(const ag_detector* det, const FrameGeom& g, long want) {
-  const long by_mem = std::max<long>(1, (long)((8ull << 30) / ((unsigned long long)g.n_px * 8ull)));
+  const long by_mem = std::max<long>(1, (long)((24ull << 30) / ((unsigned long long)g.n_px * 8ull)));
   return (int)std::max<long>(1, std::min<long>(want, by_mem));
 }
 
@@ -496,7 +497,8 @@ int run_boards(ag_detector* det, BoardSlot& S, const uint8_t* d_frames, const Fr
       d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->d_codes, det->fam.n_codes, det->fam.edge,
       det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
       d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout[0].max_quads,
-      det->board_grid ? 1 : 0, det->board_fast ? 1 : 0, det->board_timing ? S.d_board_tm : nullptr, s);
+      det->board_grid ? 1 : 0, det->board_fast ? (det->board_small ? 3 : 1) : 0,
+      det->board_timing ? S.d_board_tm : nullptr, s);
   prof_mark(det, 4, s);
   AG_CUDA(det, cudaGetLastError());
   return AG_OK;
@@ -856,6 +858,8 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     det->board_timing = value != 0;
   } else if (!strcmp(key, "board_fast")) {
     det->board_fast = value != 0;
+  } else if (!strcmp(key, "board_small")) {
+    det->board_small = value != 0;
   } else if (!strcmp(key, "board_grid")) {
     det->board_grid = value != 0;
   } else if (!strcmp(key, "profile")) {

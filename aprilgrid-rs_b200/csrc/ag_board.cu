@@ -173,7 +173,9 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
     F.g_cap_cells = L.grid_cap_cells;
     F.g_cap_items = L.smem_saddles;
     F.g_inv = 1.0f / (float)bucket;
+    F.g_bucket0 = bucket;
     F.g_on = 0;
+    F.g_sat = 0;
   }
   F.hist = (int*)(smem + L.sm_hist);
   F.ctl = (int*)(smem + L.sm_ctl);
@@ -222,7 +224,8 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.fx_wscore = (uint16_t*)(smem + L.sm_wave);
   F.fx_wquad = (int16_t*)(F.fx_wscore + 32);
   // block-uniform: the whole frame takes the throughput path or the general one
-  F.fast_on = (fast && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles &&
+  F.fx_small = (fast >> 1) & 1;
+  F.fast_on = ((fast & 1) && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles &&
                L.sm_gpos - L.sm_gstart == (size_t)agb::kGridStartBytes &&
                L.sm_gitem - L.sm_gpos == sizeof(float2) * (size_t)L.smem_saddles) ? 1 : 0;
 

@@ -14,6 +14,7 @@
 //                          reference: src/detector.rs:194-361 (rochade_refine), :432-445.
 #include "ag_common.cuh"
 #include "ag_kernels.h"
+#include "ag_libm.h"
 
 namespace ag {
 
@@ -560,9 +561,10 @@ int upload_rochade_tables(const float* cone25, const float* pinv150) {
 constexpr int kRefineThreads = 512;
 constexpr int kRefineWarps = kRefineThreads / 32;
 
-// libm-compatible transcendental results for f32 arguments: evaluate in f64 and round once.
-AG_D float acosf_cr(float x) { return (float)acos((double)x); }
-AG_D float atan2f_cr(float y, float x) { return (float)atan2((double)y, (double)x); }
+// f32::acos / f32::atan2 of the reference = the platform's acosf / atan2f: glibc's routines restated
+// operation for operation (ag_libm.h), same bits as the oracle's libm calls.
+AG_D float acosf_cr(float x) { return lm_acosf(x); }
+AG_D float atan2f_cr(float y, float x) { return lm_atan2f(y, x); }
 
 // Rust f32::round (half away from zero) followed by `as i32` (saturating).
 AG_D int round_to_i32(float v) {
