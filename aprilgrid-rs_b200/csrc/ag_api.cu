@@ -61,8 +61,9 @@ struct BoardSlot {
   uint32_t* d_board_tm = nullptr;  // optional per-frame timing of the board kernel ([frames][32])
   int32_t* d_tap_quads = nullptr;
   int* d_tap_nquads = nullptr;
-  BoardWsLayout layout[2]{};        // [tier] sized for the largest warps-per-frame (allocation)
-  BoardWsLayout layout_batch[2]{};  // [tier] layout used when many frames are in flight
+  // [tier]: 0 = 320, 1 = 512, 2 = 1024 saddles on chip in the board kernel
+  BoardWsLayout layout[3]{};        // sized for the largest warps-per-frame (allocation)
+  BoardWsLayout layout_batch[3]{};  // layout used when many frames are in flight
   // host-frame path (ag_detect_batch): staged input of the chunk (K6 samples the tag bits from it,
   // so it lives as long as the slot's board search), device results and pinned result staging
   uint8_t* d_in = nullptr;
@@ -167,7 +168,7 @@ struct ag_detector {
   bool label_list = true;  // K3 over a compact pixel list (0 = word-oriented version only)
   bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
   bool board_fast = true;  // four-lane group scoring of candidate boards (0 = general path only)
-  bool board_small = true;  // rounds after the first: one lane per candidate board where the saddles fit
+  bool board_split = true;  // batches: small frames (<= 320 saddles) searched by their own launch with the small tier
   bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -281,8 +282,8 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
   if ((rc = regrow(det, &B.d_status, (size_t)F))) return rc;
   if ((rc = regrow(det, &B.d_refined, (size_t)F * nsd))) return rc;
   // layouts for both tiers of on-chip saddle capacity (chosen per launch from the image size)
-  for (int tier = 0; tier < 2; ++tier) {
-    const int cap = tier == 0 ? 512 : 1024;
+  for (int tier = 0; tier < 3; ++tier) {
+    const int cap = tier == 0 ? 320 : (tier == 1 ? 512 : 1024);
     B.layout[tier] = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 8, cap);
     B.layout_batch[tier] =
         make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 2, cap);
@@ -486,19 +487,28 @@ int run_boards(ag_detector* det, BoardSlot& S, const uint8_t* d_frames, const Fr
                cudaStream_t s) {
   prof_mark(det, -1, s);
   // automatic warps per frame: throughput (2 warps: most frames resident per SM) once a launch can
-  // fill the GPU, latency (8 warps share one frame's seeds) for a handful of frames
-  // on-chip saddle capacity: 512 up to 1.5 Mpx (more frames per SM), 1024 above (larger images
-  // carry more saddles); frames beyond the tier take the general path inside the kernel
-  const int tier = det->board_saddle_tier >= 0 ? (int)det->board_saddle_tier
-                                               : ((long long)g.w * g.h > 1572864ll ? 1 : 0);
-  const BoardWsLayout& BL =
-      (det->board_warps == 0 && n >= det->board_batch_frames) ? S.layout_batch[tier] : S.layout[tier];
-  det->launches += launch_boards_decode(
-      d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->d_codes, det->fam.n_codes, det->fam.edge,
-      det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
-      d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout[0].max_quads,
-      det->board_grid ? 1 : 0, det->board_fast ? (det->board_small ? 3 : 1) : 0,
-      det->board_timing ? S.d_board_tm : nullptr, s);
+  // fill the GPU, latency (8 warps share one frame's seeds) for a handful of frames.
+  // On-chip saddle capacity (tier): 512 up to 1.5 Mpx, 1024 above (larger images carry more
+  // saddles); frames beyond the tier take the general path inside the kernel.  A batch is searched
+  // by TWO launches: frames of at most 320 saddles (one board) with the small tier -- 32 KB of
+  // shared memory per frame, seven frames per SM -- and the others with the image's tier; a block
+  // whose frame belongs to the other launch exits at once.
+  const int big = det->board_saddle_tier >= 0 ? (int)det->board_saddle_tier + 1
+                                              : ((long long)g.w * g.h > 1572864ll ? 2 : 1);
+  const bool batch = det->board_warps == 0 && n >= det->board_batch_frames;
+  const int n_launch = (batch && det->board_split) ? 2 : 1;
+  for (int pass = 0; pass < n_launch; ++pass) {
+    const int tier = (n_launch == 2 && pass == 0) ? 0 : big;
+    const int n_above = (n_launch == 2 && pass == 1) ? S.layout[0].smem_saddles : -1;
+    const int n_upto = (n_launch == 2 && pass == 0) ? S.layout[0].smem_saddles : 0x7fffffff;
+    const BoardWsLayout& BL = batch ? S.layout_batch[tier] : S.layout[tier];
+    det->launches += launch_boards_decode(
+        d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->d_codes, det->fam.n_codes, det->fam.edge,
+        det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
+        d_status, taps ? S.d_tap_quads : nullptr, taps ? S.d_tap_nquads : nullptr, S.layout[0].max_quads,
+        det->board_grid ? 1 : 0, det->board_fast ? 1 : 0, det->board_timing ? S.d_board_tm : nullptr, n_above,
+        n_upto, s);
+  }
   prof_mark(det, 4, s);
   AG_CUDA(det, cudaGetLastError());
   return AG_OK;
@@ -850,7 +860,7 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     if (value < 0 || value > 1) return fail(det, AG_ERR_INVALID, "label_variant must be 0 or 1");
     det->label_variant = value;
   } else if (!strcmp(key, "board_saddle_tier")) {
-    if (value < -1 || value > 1) return fail(det, AG_ERR_INVALID, "board_saddle_tier must be -1, 0 or 1");
+    if (value < -1 || value > 1) return fail(det, AG_ERR_INVALID, "board_saddle_tier must be -1, 0 (512) or 1 (1024)");
     det->board_saddle_tier = value;
   } else if (!strcmp(key, "label_list")) {
     det->label_list = value != 0;
@@ -858,8 +868,8 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     det->board_timing = value != 0;
   } else if (!strcmp(key, "board_fast")) {
     det->board_fast = value != 0;
-  } else if (!strcmp(key, "board_small")) {
-    det->board_small = value != 0;
+  } else if (!strcmp(key, "board_split")) {
+    det->board_split = value != 0;
   } else if (!strcmp(key, "board_grid")) {
     det->board_grid = value != 0;
   } else if (!strcmp(key, "profile")) {

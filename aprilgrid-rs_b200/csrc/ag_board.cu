@@ -62,7 +62,9 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   L.bytes_per_warp = align_up(w, 64);
   L.bytes_per_frame = align_up(L.off_warp0 + L.bytes_per_warp * kBoardWarps, 256);
   // shared memory of the block: frame-wide part, then one part per warp
-  L.smem_saddles = smem_saddles <= 512 ? 512 : 1024;  // tier of the throughput path
+  // tier of the throughput path: 320 (the usual frame: one board, ~270 saddles; seven frames per SM),
+  // 512 or 1024 saddles on chip
+  L.smem_saddles = smem_saddles <= 320 ? 320 : (smem_saddles <= 512 ? 512 : 1024);
   L.grid_cap_cells = agb::kGridCapCells;  // 1280x1024 at 32 px buckets = 1280 buckets
   size_t sm = 0;
   auto stake = [&](size_t bytes) {
@@ -77,7 +79,6 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   L.sm_gstart = stake(sizeof(uint16_t) * (L.grid_cap_cells + 2));
   L.sm_gpos = stake(sizeof(float2) * L.smem_saddles);
   L.sm_gitem = stake(sizeof(uint16_t) * L.smem_saddles);
-  L.sm_hist = stake(sizeof(int) * agb::kHistBins);
   L.sm_ctl = stake(sizeof(int) * 16);
   // throughput path (ag_board_fast.cuh): per wave slot best score + quad
   L.sm_wave = stake(32 * (sizeof(uint16_t) + 4 * sizeof(int16_t)));
@@ -96,8 +97,11 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   L.smw_qlist = swtake(sizeof(int16_t) * 4 * agb::kQListCap);
   L.smw_qscore = swtake(sizeof(uint16_t) * agb::kQListCap);
   L.smw_fvec = swtake(sizeof(float) * 64 * 4);
-  L.smw_elig = swtake(64);
   L.smw_squeue = swtake(sizeof(uint32_t) * 64);
+  // the theta histogram of select_seeds (warp 0, before any seed is enumerated) borrows warp 0's
+  // enumeration scratch
+  static_assert(sizeof(int) * agb::kHistBins <= sizeof(float) * 64 * 4, "histogram must fit the enumeration scratch");
+  L.sm_hist = L.sm_warp0 + L.smw_fvec;
   L.smem_per_warp = sw;
   L.smem_per_block = L.sm_warp0 + sw * kBoardWarps;
   return L;
@@ -111,11 +115,17 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
                 int hamming, int max_boards, ag_tag* __restrict__ out, int cap,
                 int* __restrict__ n_out, uint32_t* __restrict__ frame_status,
                 int32_t* __restrict__ tap_quads, int* __restrict__ tap_n_quads, int tap_cap,
-                int use_grid, int fast, uint32_t* __restrict__ timing) {
+                int use_grid, int fast, uint32_t* __restrict__ timing, int n_above, int n_upto) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int f = blockIdx.x;  // one block per frame
+  // A chunk is searched by two launches with different shared-memory tiers (small frames: more
+  // blocks per SM); a block whose frame belongs to the other launch leaves at once.
+  {
+    const int nf = n_refined[f];
+    if (nf <= n_above || nf > n_upto) return;  // block-uniform
+  }
   // A frame whose cluster / saddle list was truncated (flagged by K3 / K4) has no meaningful board:
   // it reports no tags and keeps its flags; the host entry points re-run it with grown capacities.
   if (frame_status[f] & (uint32_t)(AG_FRAME_CLUSTER_OVERFLOW | AG_FRAME_SADDLE_OVERFLOW)) {  // block-uniform
@@ -173,9 +183,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
     F.g_cap_cells = L.grid_cap_cells;
     F.g_cap_items = L.smem_saddles;
     F.g_inv = 1.0f / (float)bucket;
-    F.g_bucket0 = bucket;
     F.g_on = 0;
-    F.g_sat = 0;
   }
   F.hist = (int*)(smem + L.sm_hist);
   F.ctl = (int*)(smem + L.sm_ctl);
@@ -224,8 +232,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.fx_wscore = (uint16_t*)(smem + L.sm_wave);
   F.fx_wquad = (int16_t*)(F.fx_wscore + 32);
   // block-uniform: the whole frame takes the throughput path or the general one
-  F.fx_small = (fast >> 1) & 1;
-  F.fast_on = ((fast & 1) && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles &&
+  F.fast_on = (fast && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles &&
                L.sm_gpos - L.sm_gstart == (size_t)agb::kGridStartBytes &&
                L.sm_gitem - L.sm_gpos == sizeof(float2) * (size_t)L.smem_saddles) ? 1 : 0;
 
@@ -298,7 +305,7 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
                          int hamming,
                          int max_boards, ag_tag* out, int cap, int* n_out, uint32_t* frame_status,
                          int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid, int fast,
-                         uint32_t* timing, cudaStream_t s) {
+                         uint32_t* timing, int n_above, int n_upto, cudaStream_t s) {
   const int blocks = n_frames;
   if (blocks == 0) return 0;
   const size_t smem = L.smem_per_block + (size_t)g_board_smem_pad;
@@ -310,7 +317,7 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
     return 0;
   k_boards_decode<<<blocks, L.warps * 32, smem, s>>>(
       frames, g, n_frames, refined, n_refined, ws, L, d_codes, n_codes, edge, border, hamming, max_boards,
-      out, cap, n_out, frame_status, tap_quads, tap_n_quads, tap_cap, use_grid, fast, timing);
+      out, cap, n_out, frame_status, tap_quads, tap_n_quads, tap_cap, use_grid, fast, timing, n_above, n_upto);
   return 1;
 }
 

@@ -51,6 +51,7 @@ struct float2 { float x, y; };  // host test build: the CUDA vector type is not 
 #if defined(AGB_WORK_COUNTERS) && !defined(__CUDA_ARCH__)
 extern "C" long long agb_work_counters[32];
 extern "C" void agb_note_query(int a, int b, int self_is_b, float qx, float qy, float r2);
+extern "C" void agb_note_query(int a, int b, int self_is_b, float qx, float qy, float r2);
 #define AGB_COUNT(slot, n) (agb_work_counters[(slot) + 12 * agb_work_counters[31]] += (n))
 #else
 #define AGB_COUNT(slot, n) ((void)0)
@@ -102,8 +103,6 @@ struct Frame {
   uint16_t* g_start;  // [g_nx * g_ny + 1] first entry of each bucket in g_item
   uint16_t* g_item;   // [n] saddle indices sorted by bucket
   int g_nx, g_ny, g_cap_cells, g_cap_items;
-  int g_bucket0;      // smallest bucket side (px) whose grid fits g_cap_cells; rounds may use a multiple
-  int g_sat;          // 1 = the grid array holds a summed-area table of bucket counts (throughput path), see grid_row_start
   int g_on;           // 1 = the grid holds the current round's saddles (block-uniform)
   float g_inv;        // 1 / bucket size in pixels
   int16_t* stack;   // [2 * (max_quads + 1)] DFS stack: cell index, next direction
@@ -133,7 +132,6 @@ struct Frame {
   int lane;  // 0 on host
   // throughput path (device only, ag_board_fast.cuh); unused when fast_on == 0
   int fast_on;
-  int fx_small;          // later rounds: one lane per board (warp_score_small) when the saddles fit
   int round;             // board round being searched (0 = first board)
   uint16_t* g_base;      // unshifted bucket-grid array ([cells + 2])
   float2* g_pos;         // [n] saddle positions in g_item order (one load per scanned candidate)
@@ -374,23 +372,8 @@ AGB_FN int grid_bucket(const Frame& F, float x, float y) {
   by = by < 0 ? 0 : (by >= F.g_ny ? F.g_ny - 1 : by);
   return by * F.g_nx + bx;
 }
-// First entry (in g_item order) of bucket (x, y); x may be g_nx: the end of row y.  Two layouts of
-// the grid array: bucket starts in row-major order (grid_build), or -- throughput path -- the
-// summed-area table S[y][x] = saddles in bucket rows < y and columns < x ((g_ny + 1) x (g_nx + 1)
-// entries), from which a start is (saddles in the rows above) + (saddles left of x in row y).
-AGB_FN int grid_row_start(const Frame& F, int y, int x) {
-#if AGB_DEVICE
-  if (F.g_sat) {
-    const uint16_t* S = F.g_base;
-    const int w1 = F.g_nx + 1;
-    return (int)S[y * w1 + F.g_nx] + (int)S[(y + 1) * w1 + x] - (int)S[y * w1 + x];
-  }
-#endif
-  return F.g_start[y * F.g_nx + x];
-}
 AGB_NOINLINE void grid_build(Frame& F) {
   F.g_on = 0;
-  F.g_sat = 0;
   if (!F.g_start) return;
   const int nc = F.g_nx * F.g_ny;
   // too large for the on-chip grid: queries fall back to the exhaustive scan
@@ -454,7 +437,8 @@ AGB_NOINLINE int nearest3_within(const Frame& F, float qx, float qy, float r2, i
     if (bw > 0 && bh > 0) {
       // rows of buckets are contiguous in g_item: one (start, end) range per bucket row
       for (int row = F.lane; row < bh; row += AGB_LANES) {
-        const int e0 = grid_row_start(F, y0 + row, x0), e1 = grid_row_start(F, y0 + row, x0 + bw);
+        const int b0 = (y0 + row) * F.g_nx + x0;
+        const int e0 = F.g_start[b0], e1 = F.g_start[b0 + bw];
         for (int e = e0; e < e1; ++e) consider(F.g_item[e]);
       }
     }
@@ -509,8 +493,9 @@ AGB_FN int nearest3_within_single(const Frame& F, float qx, float qy, float r2, 
     const int bw = x1 - x0 + 1;
     if (bw > 0)
       for (int by = y0; by <= y1; ++by) {
-        const int e1 = grid_row_start(F, by, x0 + bw);
-        for (int e = grid_row_start(F, by, x0); e < e1; ++e) consider(F.g_item[e]);
+        const int b0 = by * F.g_nx + x0;
+        const int e1 = F.g_start[b0 + bw];
+        for (int e = F.g_start[b0]; e < e1; ++e) consider(F.g_item[e]);
       }
   } else {
     for (int i = 0; i < F.n; ++i) consider(i);
@@ -676,8 +661,9 @@ __device__ __forceinline__ void expand_queries_warp(const Frame& F, const BoardS
     const int bw = x1 - x0 + 1;
     if (bw > 0)
       for (int yy = y0 + sub; yy <= y1; yy += 8) {
-        const int e1 = grid_row_start(F, yy, x0 + bw);
-        for (int e = grid_row_start(F, yy, x0); e < e1; ++e) consider(F.g_item[e]);
+        const int b0 = yy * F.g_nx + x0;
+        const int e1 = F.g_start[b0 + bw];
+        for (int e = F.g_start[b0]; e < e1; ++e) consider(F.g_item[e]);
       }
   } else {
     for (int i = sub; i < F.n; i += 8) consider(i);

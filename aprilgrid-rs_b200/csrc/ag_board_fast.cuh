@@ -54,115 +54,61 @@ constexpr int kDiffCap = 52;        // `diff` / `same` entries of a seed: at mos
 namespace agb {
 
 // ---- bucket grid, built by the whole warp ------------------------------------------------------
-// Saddles counting-sorted by bucket (row-major); the grid array holds the SUMMED-AREA TABLE of the
-// bucket counts, S[y][x] = saddles in bucket rows < y and columns < x, (g_ny + 1) x (g_nx + 1)
-// entries.  One table answers both questions a neighbour search asks:
-//   * where does a row segment of buckets start / end in the sorted arrays (grid_row_start), and
-//   * how many saddles does a whole query window hold (four entries) -- so a search knows before it
-//     starts that its window is empty, and stops as soon as it has seen every saddle of the window.
+// Layout: G[0] = 0, G[b + 1] = first entry of bucket b, G[nc + 1] = n; F.g_start = G + 1.
 // Order inside a bucket is arbitrary: every query selects by the total order (d2, index).
-//
-// Bucket side of a round (a power of two, >= 32 px, also the smallest side whose grid fits the
-// bucket-start array): doubled while the saddles' bounding box holds fewer than about 0.4 saddles
-// per bucket.  A neighbour search walks bucket ROWS, so in the sparse later rounds (the leftovers
-// of a found board: ~130 saddles, query radii of ~100 px) larger buckets halve the rows per search
-// at the same number of candidates.  Any side gives the same search results.
-__device__ __forceinline__ void grid_choose_bucket(Frame& F) {
-  int bucket = F.g_bucket0;
-#ifndef AGB_FIXED_BUCKET
-  float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
-  for (int i = F.lane; i < F.n; i += 32) {
-    const float x = F.sx[i], y = F.sy[i];
-    x0 = fminf(x0, x); x1 = fmaxf(x1, x); y0 = fminf(y0, y); y1 = fmaxf(y1, y);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-    y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-  }
-  const float area = fmaxf(x1 - x0, 1.0f) * fmaxf(y1 - y0, 1.0f);
-  while (bucket < 256 && F.n > 0 && (float)F.n * (float)bucket * (float)bucket < 0.4f * area) bucket *= 2;
-#endif
-  // the table has one row and one column more than the grid has buckets
-  while (((F.w + bucket - 1) / bucket + 1) * ((F.h + bucket - 1) / bucket + 1) > F.g_cap_cells + 2) bucket *= 2;
-  F.g_nx = (F.w + bucket - 1) / bucket;
-  F.g_ny = (F.h + bucket - 1) / bucket;
-  F.g_inv = 1.0f / (float)bucket;
-  if (F.lane == 0) F.ctl[7] = bucket;
-}
-// The other warps of the block adopt the grid geometry warp 0 chose (after a block barrier).
-__device__ __forceinline__ void grid_adopt_bucket(Frame& F) {
-  const int bucket = F.ctl[7];
-  if (bucket <= 0) return;  // no grid this round
-  F.g_nx = (F.w + bucket - 1) / bucket;
-  F.g_ny = (F.h + bucket - 1) / bucket;
-  F.g_inv = 1.0f / (float)bucket;
-  F.g_sat = 1;
-}
-
-// `cursor`: scratch of one u16 per bucket (the caller's lattice / group-state region, free here).
-__device__ __noinline__ void grid_build_warp(Frame& F, uint16_t* cursor) {
+__device__ __noinline__ void grid_build_warp(Frame& F) {
   F.g_on = 0;
-  F.g_sat = 0;
-  if (F.lane == 0) F.ctl[7] = 0;
   if (!F.g_base) return;
-  grid_choose_bucket(F);
-  const int nx = F.g_nx, ny = F.g_ny, nc = nx * ny, w1 = nx + 1;
-  if (F.n > F.g_cap_items || nc > F.g_cap_cells || F.n > 65535) {
-    if (F.lane == 0) F.ctl[7] = 0;
-    return;
-  }
+  const int nc = F.g_nx * F.g_ny;
+  if (F.n > F.g_cap_items || nc > F.g_cap_cells || F.n > 65535) return;
   F.g_on = 1;
-  F.g_sat = 1;
-  uint16_t* S = F.g_base;
-  for (int c = F.lane; c < (ny + 1) * w1; c += 32) S[c] = 0;
-  for (int c = F.lane; c < nc; c += 32) cursor[c] = 0;
+  uint16_t* G = F.g_base;
+  for (int c = F.lane; c <= nc + 1; c += 32) G[c] = 0;
   __syncwarp();
-  // bucket counts into S[y + 1][x + 1]
+  // counts into G[b + 1]
   for (int base = 0; base < F.n; base += 32) {
     const int i = base + F.lane;
     const int b = i < F.n ? grid_bucket(F, F.sx[i], F.sy[i]) : (0x10000 + F.lane);
     const unsigned peers = __match_any_sync(0xffffffffu, b);
-    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) {
-      const int by = b / nx, bx = b - by * nx;
-      S[(by + 1) * w1 + bx + 1] = (uint16_t)(S[(by + 1) * w1 + bx + 1] + __popc(peers));
-    }
+    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) G[b + 1] = (uint16_t)(G[b + 1] + __popc(peers));
     __syncwarp();
   }
-  // prefix sums along x (one lane per table row), then along y (one lane per table column)
-  for (int y = 1 + F.lane; y <= ny; y += 32) {
-    unsigned run = 0;
-    for (int x = 1; x <= nx; ++x) {
-      run += S[y * w1 + x];
-      S[y * w1 + x] = (uint16_t)run;
+  // inclusive scan of G[1 .. nc]: afterwards G[b + 1] = end of bucket b
+  {
+    const int per = (nc + 31) / 32;
+    const int c0 = 1 + F.lane * per, c1 = min(c0 + per, nc + 1);
+    unsigned sum = 0;
+    for (int c = c0; c < c1; ++c) sum += G[c];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (F.lane >= o) incl += v;
+    }
+    unsigned run = incl - sum;
+    for (int c = c0; c < c1; ++c) {
+      run += G[c];
+      G[c] = (uint16_t)run;
     }
   }
   __syncwarp();
-  for (int x = 1 + F.lane; x <= nx; x += 32) {
-    unsigned run = 0;
-    for (int y = 1; y <= ny; ++y) {
-      run += S[y * w1 + x];
-      S[y * w1 + x] = (uint16_t)run;
-    }
-  }
-  __syncwarp();
-  // fill: entry = start of the bucket + saddles of the bucket placed by earlier batches + rank in this batch
+  // fill from the back of every bucket: G[b + 1] walks down from end(b) to start(b)
   for (int base = 0; base < F.n; base += 32) {
     const int i = base + F.lane;
     const int b = i < F.n ? grid_bucket(F, F.sx[i], F.sy[i]) : (0x10000 + F.lane);
     const unsigned peers = __match_any_sync(0xffffffffu, b);
     if (i < F.n) {
-      const int by = b / nx, bx = b - by * nx;
-      const int e = (int)S[by * w1 + nx] + (int)S[(by + 1) * w1 + bx] - (int)S[by * w1 + bx] + (int)cursor[b] +
-                    __popc(peers & ((1u << F.lane) - 1u));
-      F.g_item[e] = (uint16_t)i;
-      F.g_pos[e] = make_float2(F.sx[i], F.sy[i]);
+      const int rank = __popc(peers & ((1u << F.lane) - 1u));
+      const int e = G[b + 1];
+      F.g_item[e - 1 - rank] = (uint16_t)i;
+      F.g_pos[e - 1 - rank] = make_float2(F.sx[i], F.sy[i]);
     }
     __syncwarp();
-    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) cursor[b] = (uint16_t)(cursor[b] + __popc(peers));
+    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) G[b + 1] = (uint16_t)(G[b + 1] - __popc(peers));
     __syncwarp();
   }
-  F.g_start = S;
+  if (F.lane == 0) G[nc + 1] = (uint16_t)F.n;
+  F.g_start = G + 1;
   __syncwarp();
 }
 
@@ -219,12 +165,12 @@ struct QueryCtx {
   Pts P;
   float g_inv;
   int g_nx, g_ny, g_on, n;
-  // Shared-memory address of the grid's summed-area table.  The grid-ordered positions follow that
-  // array and the grid-ordered item indices follow the positions (BoardWsLayout; checked where
-  // F.fast_on is set), so their addresses are a_sat plus a constant / plus two saddle-array
-  // strides: nothing else has to stay live across the search loops.
-  unsigned a_sat;
-  __device__ __forceinline__ unsigned a_pos() const { return a_sat + (unsigned)kGridStartBytes; }
+  // Shared-memory address of the bucket starts (F.g_start = array base + one entry).  The
+  // grid-ordered positions follow that array and the grid-ordered item indices follow the positions
+  // (BoardWsLayout; checked where F.fast_on is set), so their addresses are a_start plus a constant
+  // / plus two saddle-array strides: nothing else has to stay live across the search loops.
+  unsigned a_start;
+  __device__ __forceinline__ unsigned a_pos() const { return a_start + (unsigned)(kGridStartBytes - 2); }
   __device__ __forceinline__ unsigned a_item() const { return a_pos() + 2u * P.stride; }
 };
 __device__ __forceinline__ QueryCtx make_query_ctx(const Frame& F) {
@@ -232,63 +178,14 @@ __device__ __forceinline__ QueryCtx make_query_ctx(const Frame& F) {
   C.P.base = (unsigned)__cvta_generic_to_shared(F.sx);
   C.P.stride = (unsigned)((const char*)F.sy - (const char*)F.sx);  // F.st = F.sy + the same stride
   C.g_inv = F.g_inv; C.g_nx = F.g_nx; C.g_ny = F.g_ny; C.g_on = F.g_on; C.n = F.n;
-  C.a_sat = F.g_on ? (unsigned)__cvta_generic_to_shared(F.g_base) : 0u;
+  C.a_start = F.g_on ? (unsigned)__cvta_generic_to_shared(F.g_start) : 0u;
   return C;
-}
-__device__ __forceinline__ int lds_u16(unsigned addr) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-  return (int)v;
-}
-// One neighbour search, prepared: query point, squared radius, the bucket window of the radius and
-// the number of saddles the window holds (from the summed-area table: four loads).
-struct Prep {
-  float qx, qy, r2, r;
-  int x0, x1, y0, y1;
-  int total;      // saddles in the window (all saddles when there is no window: degenerate radius / no grid)
-  bool windowed;
-};
-__device__ __forceinline__ Prep query_prepare(const QueryCtx& F, bool on, int a, int b, int self) {
-  Prep Q;
-  Q.qx = Q.qy = Q.r = 0.0f;
-  Q.r2 = -1.0f;
-  Q.x0 = Q.y0 = 0;
-  Q.x1 = Q.y1 = -1;
-  Q.total = 0;
-  Q.windowed = false;
-  if (!on) return Q;
-  const float ratio0 = fadd(1.0f, 0.3f);  // 1.0 + spacing_ratio; detector.rs:621 passes 0.3
-  const float ax = F.P.x(a), ay = F.P.y(a), bx = F.P.x(b), by = F.P.y(b);
-  const float dx = fsub(ax, bx), dy = fsub(ay, by);
-  Q.r2 = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
-  const float v10x = fsub(bx, ax), v10y = fsub(by, ay);
-  const float sfx = self == a ? ax : bx, sfy = self == a ? ay : by;
-  Q.qx = fadd(sfx, fmul(v10x, ratio0));
-  Q.qy = fadd(sfy, fmul(v10y, ratio0));
-  Q.total = F.n;
-  if (F.g_on && Q.r2 >= 0.0f && Q.r2 < 1.0e12f) {
-    Q.windowed = true;
-    Q.total = 0;
-    Q.r = sqrtf(Q.r2) * 1.0001f + 0.01f;  // conservative: the window contains every saddle within the radius
-    int x0 = (int)floorf((Q.qx - Q.r) * F.g_inv), x1 = (int)floorf((Q.qx + Q.r) * F.g_inv);
-    int y0 = (int)floorf((Q.qy - Q.r) * F.g_inv), y1 = (int)floorf((Q.qy + Q.r) * F.g_inv);
-    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
-    x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
-    Q.x0 = x0; Q.x1 = x1; Q.y0 = y0; Q.y1 = y1;
-    if (x0 <= x1 && y0 <= y1) {
-      const unsigned w1 = (unsigned)F.g_nx + 1u;
-      const unsigned top = F.a_sat + 2u * ((unsigned)y0 * w1), bot = F.a_sat + 2u * ((unsigned)(y1 + 1) * w1);
-      Q.total = lds_u16(bot + 2u * (unsigned)(x1 + 1)) - lds_u16(top + 2u * (unsigned)(x1 + 1)) -
-                lds_u16(bot + 2u * (unsigned)x0) + lds_u16(top + 2u * (unsigned)x0);
-    }
-  }
-  return Q;
 }
 // group_knn: the search proper (the up to three nearest saddles within the radius, unfiltered,
 // packed as above).  It depends on (a, b, self == b) and the frame's saddle list only -- not on the
 // board being grown -- so its result is shared by every board of the frame through a cache
 // (group_query below).
-__device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, const Prep& Q, uint32_t* tm = nullptr) {
+__device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a, int b, int self, uint32_t* tm = nullptr) {
   const unsigned full = 0xffffffffu;
   // key = squared distance bits << 32 | index; "none" carries distance +inf, so the distance of the
   // third-best candidate is the high word of k2 whether or not three are known
@@ -305,21 +202,40 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, const 
       d3f = __uint_as_float((unsigned)(k2 >> 32));
     }
   };
-  const float qx = Q.qx, qy = Q.qy, r2 = Q.r2, r = Q.r;
+  float qx = 0.0f, qy = 0.0f, r2 = -1.0f, r = 0.0f;
+  if (on) {
+    const float ratio0 = fadd(1.0f, 0.3f);  // 1.0 + spacing_ratio; detector.rs:621 passes 0.3
+    const float ax = F.P.x(a), ay = F.P.y(a), bx = F.P.x(b), by = F.P.y(b);
+    const float dx = fsub(ax, bx), dy = fsub(ay, by);
+    r2 = fmul(0.5f, fadd(fmul(dx, dx), fmul(dy, dy)));
+    const float v10x = fsub(bx, ax), v10y = fsub(by, ay);
+    const float sfx = self == a ? ax : bx, sfy = self == a ? ay : by;
+    qx = fadd(sfx, fmul(v10x, ratio0));
+    qy = fadd(sfy, fmul(v10y, ratio0));
+  }
   if (F.g_on) {  // block-uniform
-    const bool windowed = on && Q.windowed;
-    const int x0 = Q.x0, x1 = Q.x1, y0 = Q.y0, y1 = Q.y1;
-    int cy = 0, t = 0, t_end = 0;
-    int left = Q.total;  // saddles of the window not visited yet: at 0 the search is complete
-    if (windowed && left > 0) {
-      cy = (int)floorf(qy * F.g_inv);
-      cy = cy < y0 ? y0 : (cy > y1 ? y1 : cy);
-      t_end = 2 * max(cy - y0, y1 - cy) + 1;  // rows are visited at offsets 0, -1, +1, -2, ...
+    const bool windowed = on && r2 >= 0.0f && r2 < 1.0e12f;
+    int x0 = 0, x1 = -1, y0 = 0, y1 = -1, cy = 0, t = 0, t_end = 0;
+    if (windowed) {
+      r = sqrtf(r2) * 1.0001f + 0.01f;
+      x0 = (int)floorf((qx - r) * F.g_inv); x1 = (int)floorf((qx + r) * F.g_inv);
+      y0 = (int)floorf((qy - r) * F.g_inv); y1 = (int)floorf((qy + r) * F.g_inv);
+      x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
+      x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+      if (x0 <= x1 && y0 <= y1) {
+        cy = (int)floorf(qy * F.g_inv);
+        cy = cy < y0 ? y0 : (cy > y1 ? y1 : cy);
+        t_end = 2 * max(cy - y0, y1 - cy) + 1;  // rows are visited at offsets 0, -1, +1, -2, ...
+      }
     }
     const float bsz = 1.0f / F.g_inv;  // bucket side, a power of two: bucket indices are exact
     // shared-memory addresses of the grid arrays (32-bit, LDS instead of generic loads)
-    const unsigned a_sat = F.a_sat, a_pos = F.a_pos(), a_item = F.a_item();
-    const unsigned w1 = (unsigned)F.g_nx + 1u;
+    const unsigned a_start = F.a_start, a_pos = F.a_pos(), a_item = F.a_item();
+    auto lds_u16 = [](unsigned addr) -> int {
+      unsigned short v;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+      return (int)v;
+    };
     // Outer loop: row offset t is the same for every lane (each lane's rows are counted from its own
     // query row), so the row set-up is executed once per t for the whole warp; it is issued one
     // row AHEAD (its shared-memory loads overlap the candidate loop of the current row; the bounds
@@ -349,11 +265,9 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, const 
       if (lb * lb * 0.9999f > stop_d3) {                   // ... and so are the remaining rows
         t_end = 0;
       } else if (bx0 <= bx1) {
-        // start of bucket (yy, x) = saddles in the rows above + saddles left of x in row yy
-        const unsigned ra = a_sat + 2u * ((unsigned)yy * w1), rb = ra + 2u * w1;
-        const int above = lds_u16(ra + 2u * (w1 - 1u));
-        re = above + lds_u16(rb + 2u * (unsigned)bx0) - lds_u16(ra + 2u * (unsigned)bx0);
-        re1 = above + lds_u16(rb + 2u * (unsigned)(bx1 + 1)) - lds_u16(ra + 2u * (unsigned)(bx1 + 1));
+        const int b0 = yy * F.g_nx;
+        re = lds_u16(a_start + 2u * (unsigned)(b0 + bx0));
+        re1 = lds_u16(a_start + 2u * (unsigned)(b0 + bx1 + 1));
       }
     };
     int e = 0, e1 = 0;
@@ -383,17 +297,12 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, const 
           if (da <= r2) insert(da, lds_u16(a_item + 2u * (unsigned)e));
           if (two && db <= r2) insert(db, lds_u16(a_item + 2u * (unsigned)(e + 1)));
           e += 2;
-          left -= two ? 2 : 1;
         }
       }
       e = ne;
       e1 = ne1;
-      if (left <= 0) {  // every saddle of the window has been seen
-        e = e1 = 0;
-        t_end = 0;
-      }
     }
-    if (on && !Q.windowed)  // degenerate radius (NaN / huge): exhaustive
+    if (on && !windowed)  // degenerate radius (NaN / huge): exhaustive
       for (int i = 0; i < F.n; ++i) {
         const float ddx = fsub(qx, F.P.x(i)), ddy = fsub(qy, F.P.y(i));
         const float d = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
@@ -419,14 +328,8 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, const 
 // warp are repeats.  An entry is written and read with single 64-bit accesses; a reader sees
 // the old or the new entry, both are complete, and a hit returns exactly what the search
 // would, so races between the warps of a frame do not change the result.
-//
-// gshift: first lane of the caller's four-lane group (the four searches of one try_expand_one).
-// An expansion with an EMPTY candidate list fails whatever the other three lists hold (the tuple
-// loops of board.rs:160-175 never run), so a group with a list known to be empty -- from the cache,
-// or because the query window holds no saddle at all -- skips its remaining searches and every one
-// of its lanes reports an empty list.
 __device__ __forceinline__ unsigned group_query(const QueryCtx& F, unsigned long long* qcache, unsigned round_tag,
-                                                const uint32_t* active, bool on, int a, int b, int self, int gshift,
+                                                const uint32_t* active, bool on, int a, int b, int self,
                                                 uint32_t* tm) {
   unsigned knn = 0, tag = 0;
   unsigned long long* slot = nullptr;
@@ -441,25 +344,12 @@ __device__ __forceinline__ unsigned group_query(const QueryCtx& F, unsigned long
       search = false;
     }
   }
-  const Prep Q = query_prepare(F, search, a, b, self);
-  bool empty = on && !search && (knn & 3u) == 0u;
-  if (search && Q.total == 0) {  // nothing in the window: the (empty) result is known without a search
-    if (slot) __stcg(slot, (unsigned long long)tag << 32);
-    search = false;
-    empty = true;
-  }
-#ifndef AGB_NO_GROUP_ABORT
-  const bool dead = ((__ballot_sync(0xffffffffu, empty) >> gshift) & 0xfu) != 0u;
-#else
-  const bool dead = false;
-#endif
-  if (dead) search = false;
   if (tm) {
     const unsigned ms = __ballot_sync(0xffffffffu, search), mo = __ballot_sync(0xffffffffu, on);
     if ((threadIdx.x & 31) == 0) { tm[20] += __popc(mo); tm[21] += __popc(ms); tm[22] += ms != 0u; }
   }
   if (__any_sync(0xffffffffu, search)) {
-    const unsigned r = group_knn(F, search, Q, tm);
+    const unsigned r = group_knn(F, search, a, b, self, tm);
     if (search) {
       knn = r;
       if (slot) __stcg(slot, ((unsigned long long)tag << 32) | r);
@@ -467,7 +357,7 @@ __device__ __forceinline__ unsigned group_query(const QueryCtx& F, unsigned long
   }
   // active mask of the board and theta gate (board.rs:218-231), order kept
   unsigned packed = 0, cnt = 0;
-  if (on && !dead) {
+  if (on) {
     const float ts = F.P.t(self);
     const int n = (int)(knn & 3u);
     for (int t = 0; t < 3; ++t) {
@@ -646,7 +536,7 @@ __device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
       qself = (jl == 1 || jl == 2) ? qb : qa;
     }
     __syncwarp();
-    const unsigned mine = group_query(QC, qcache, round_tag, active, need, qa, qb, qself, gshift, (TM && F.warp == 0) ? F.tm : nullptr);  // whole warp, convergent
+    const unsigned mine = group_query(QC, qcache, round_tag, active, need, qa, qb, qself, (TM && F.warp == 0) ? F.tm : nullptr);  // whole warp, convergent
     if (tmon) { const long long tc = clock64(); F.tm[18] += (uint32_t)(tc - tc0); tc0 = tc; }
     const unsigned p0 = __shfl_sync(full, mine, 0, 4), p1 = __shfl_sync(full, mine, 1, 4);
     const unsigned p2 = __shfl_sync(full, mine, 2, 4), p3 = __shfl_sync(full, mine, 3, 4);
@@ -714,228 +604,6 @@ __device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
 __device__ __forceinline__ void warp_score_quads(const Frame& F, int nq) {
   if (F.tm) warp_score_quads_t<true>(F, nq);
   else warp_score_quads_t<false>(F, nq);
-}
-
-// ---- small boards: one LANE per board, 32 boards per warp ------------------------------------------
-// The boards of the later rounds -- grown from the leftovers of a found board -- are tiny (two
-// quads on average, a handful at most) but there are hundreds of them per frame.  Four lanes per
-// board leave most of the warp idle there, so these rounds give every board ONE lane: 32 boards
-// advance in lockstep, each lane runs the four neighbour searches of its try_expand_one one after
-// the other (all 32 lanes search together, and a lane whose list came back empty skips the rest:
-// the expansion has failed, board.rs:160-175) and then walks its candidate tuples in the
-// reference's order.  State per board: an 8 x 8 tag window, 16 quads, 256 saddles -- 64 words,
-// interleaved by lane in the warp's 8 KB group-state region (word w of lane l at [w * 32 + l], so
-// lanes touching the same field hit different banks).  A board that outgrows this is marked
-// kScoreRedo and scored again by the four-lane groups (and, beyond those, by the general path).
-constexpr int kSWin = 8;            // tag window per lane board: x, y in [-4, 3]
-constexpr int kSQuads = 16;         // quads per lane board
-constexpr int kSMaxSaddles = 256;   // saddle indices of a lane board's active mask
-constexpr int kSOffCell = 0;        // 16 words: u8 [64]  0 unvisited, 0xff None, q + 1 Some(q)
-constexpr int kSOffQuads = 16;      // 32 words: quad q = (q0 | q1 << 16), (q2 | q3 << 16)
-constexpr int kSOffStack = 48;      // 8 words: u16 [16]  cell | next direction << 8
-constexpr int kSOffActive = 56;     // 8 words: 256 bits
-static_assert(kSOffActive * 4 + kSMaxSaddles / 8 == 256 && 32 * 256 <= kGroupsPerWarp * kGroupBytes, "lane-board state");
-
-// One neighbour search of a lane board (see group_query): cache, window count, search, then the
-// board's active mask and the theta gate.  Every lane of the warp calls it (`on` = this lane asks).
-__device__ __forceinline__ unsigned lane_query(const QueryCtx& F, unsigned long long* qcache, unsigned round_tag,
-                                               const uint32_t* S, bool on, int a, int b, int self) {
-  unsigned knn = 0, tag = 0;
-  unsigned long long* slot = nullptr;
-  bool search = on;
-  if (on && qcache) {
-    const unsigned key = ((unsigned)a << 11) | ((unsigned)b << 1) | (self == a ? 0u : 1u);
-    tag = round_tag | key;
-    slot = qcache + ((key * 0x9E3779B1u) >> (32 - kQCacheBits));
-    const unsigned long long e = __ldcg(slot);
-    if ((unsigned)(e >> 32) == tag) {
-      knn = (unsigned)e;
-      search = false;
-    }
-  }
-  const Prep Q = query_prepare(F, search, a, b, self);
-  if (search && Q.total == 0) {  // nothing in the window: the (empty) result is known without a search
-    if (slot) __stcg(slot, (unsigned long long)tag << 32);
-    search = false;
-  }
-  if (__any_sync(0xffffffffu, search)) {
-    const unsigned r = group_knn(F, search, Q);
-    if (search) {
-      knn = r;
-      if (slot) __stcg(slot, ((unsigned long long)tag << 32) | r);
-    }
-  }
-  unsigned packed = 0, cnt = 0;
-  if (on) {
-    const float ts = F.P.t(self);
-    const int n = (int)(knn & 3u);
-    for (int t = 0; t < 3; ++t) {
-      if (t >= n) break;
-      const int i = (int)((knn >> (2 + 10 * t)) & 0x3ffu);
-      if (((S[(kSOffActive + (i >> 5)) * 32] >> (i & 31)) & 1u) && theta_distance_degree(ts, F.P.t(i)) < 5.0f) {
-        packed |= (unsigned)i << (2 + 10 * cnt);
-        ++cnt;
-      }
-    }
-  }
-  return packed | cnt;
-}
-
-// Board::new + try_expand (board.rs:27-48, :114-176) for the quads qlist[0 .. nq) (any memory),
-// scores to qscore[]; F.n <= kSMaxSaddles.
-__device__ __noinline__ void warp_score_small(const Frame& F, const int16_t* qlist, uint16_t* qscore, int nq) {
-  const QueryCtx QC = make_query_ctx(F);
-  const int max_quads = F.max_quads;
-  unsigned long long* const qcache = F.round < 127 ? F.fx_qcache : nullptr;
-  const unsigned round_tag = 0x80000000u | ((unsigned)F.round << 24);
-  const unsigned full = 0xffffffffu;
-  uint32_t* const S = (uint32_t*)as_shared(F.fx_gstate) + F.lane;  // this lane's word w is S[w * 32]
-  auto cell_ld = [&](int c) -> int { return (int)((S[(kSOffCell + (c >> 2)) * 32] >> (8 * (c & 3))) & 0xffu); };
-  auto cell_st = [&](int c, unsigned v) {
-    uint32_t& w = S[(kSOffCell + (c >> 2)) * 32];
-    w = (w & ~(0xffu << (8 * (c & 3)))) | (v << (8 * (c & 3)));
-  };
-  const int c_origin = 4 * kSWin + 4;
-  bool alive = false, list_empty = nq <= 0;
-  int k = 0, n_quads = 0, depth = 0, cur_ci = 0, cur_i = 0;
-  int next = 0;  // list cursor (warp-uniform)
-  for (;;) {
-    // (0) idle lanes take the next quads of the list
-    const unsigned idle = __ballot_sync(full, !alive);
-    if (idle != 0u && !list_empty) {
-      const int cnt = __popc(idle);
-      const int kk = next + __popc(idle & ((1u << F.lane) - 1u));
-      next += cnt;
-      if (next >= nq) list_empty = true;
-      if (!alive && kk < nq) {
-        k = kk;
-        alive = true;
-#pragma unroll
-        for (int t = 0; t < 16; ++t) S[(kSOffCell + t) * 32] = 0u;            // window empty
-#pragma unroll
-        for (int t = 0; t < 8; ++t) S[(kSOffActive + t) * 32] = 0xffffffffu;  // every saddle active
-        const int q0 = qlist[4 * k], q1 = qlist[4 * k + 1], q2 = qlist[4 * k + 2], q3 = qlist[4 * k + 3];
-        S[(kSOffActive + (q1 >> 5)) * 32] &= ~(1u << (q1 & 31));  // quad[0] stays active (board.rs:35-37)
-        S[(kSOffActive + (q2 >> 5)) * 32] &= ~(1u << (q2 & 31));
-        S[(kSOffActive + (q3 >> 5)) * 32] &= ~(1u << (q3 & 31));
-        S[kSOffQuads * 32] = (unsigned)q0 | ((unsigned)q1 << 16);
-        S[(kSOffQuads + 1) * 32] = (unsigned)q2 | ((unsigned)q3 << 16);
-        cell_st(c_origin, 1u);
-        n_quads = 1;
-        depth = 1;
-        cur_ci = c_origin;
-        cur_i = 0;
-      }
-    }
-    if (!__any_sync(full, alive)) break;
-    // (1) every running board advances to its next expansion attempt (or finishes)
-    bool need = false;
-    int dir = 0, nci = 0;
-    if (alive) {
-      int result = -1;
-      for (;;) {
-        if (cur_i == 4) {  // all four directions of this cell done: return to the parent
-          if (--depth == 0) { result = n_quads; break; }
-          const unsigned e = (S[(kSOffStack + ((depth - 1) >> 1)) * 32] >> (16 * ((depth - 1) & 1))) & 0xffffu;
-          cur_ci = (int)(e & 0xffu);
-          cur_i = (int)(e >> 8);
-          continue;
-        }
-        dir = cur_i++;
-        const int bx = (cur_ci >> 3) - 4, by = (cur_ci & 7) - 4;
-        int nx = bx, ny = by;
-        if (dir == 0) nx = bx + 1;
-        else if (dir == 1) ny = by - 1;
-        else if (dir == 2) nx = bx - 1;
-        else ny = by + 1;
-        if (nx < -4 || nx > 3 || ny < -4 || ny > 3) { result = kScoreRedo; break; }
-        nci = (nx + 4) * kSWin + (ny + 4);
-        const int cur = cell_ld(nci);
-        if (cur != 0 && cur != 0xff) continue;  // already Some (board.rs:131-135)
-        if (n_quads >= max_quads) {             // no room: the attempt fails, the cell becomes None
-          cell_st(nci, 0xffu);
-          continue;
-        }
-        if (n_quads >= kSQuads) { result = kScoreRedo; break; }
-        need = true;
-        break;
-      }
-      if (result >= 0) {
-        qscore[k] = (uint16_t)result;
-        alive = false;
-      }
-    }
-    if (!__any_sync(full, need)) continue;
-    // (2) the four neighbour searches of try_expand_one, one after the other; a lane whose list came
-    //     back empty has lost its expansion and sits the remaining searches out
-    int qs0 = 0, qs1 = 0, qs2 = 0, qs3 = 0;
-    if (need) {
-      const int qi = cell_ld(cur_ci) - 1;
-      const unsigned w0 = S[(kSOffQuads + 2 * qi) * 32], w1 = S[(kSOffQuads + 2 * qi + 1) * 32];
-      const int qq[4] = {(int)(w0 & 0xffffu), (int)(w0 >> 16), (int)(w1 & 0xffffu), (int)(w1 >> 16)};
-      // rotate_left(dir): qs[j] = quad[(j + dir) & 3]
-      qs0 = dir == 0 ? qq[0] : (dir == 1 ? qq[1] : (dir == 2 ? qq[2] : qq[3]));
-      qs1 = dir == 0 ? qq[1] : (dir == 1 ? qq[2] : (dir == 2 ? qq[3] : qq[0]));
-      qs2 = dir == 0 ? qq[2] : (dir == 1 ? qq[3] : (dir == 2 ? qq[0] : qq[1]));
-      qs3 = dir == 0 ? qq[3] : (dir == 1 ? qq[0] : (dir == 2 ? qq[1] : qq[2]));
-    }
-    bool going = need;
-    // new_s0s: edge qs0 -> qs1 seen from qs0; new_s1s: same edge from qs1; new_s2s: edge qs3 -> qs2 from
-    // qs2; new_s3s: same edge from qs3 (board.rs:154-159)
-    const unsigned p0 = lane_query(QC, qcache, round_tag, S, going, qs0, qs1, qs0);
-    going = going && (p0 & 3u) != 0u;
-    const unsigned p1 = lane_query(QC, qcache, round_tag, S, going, qs0, qs1, qs1);
-    going = going && (p1 & 3u) != 0u;
-    const unsigned p2 = lane_query(QC, qcache, round_tag, S, going, qs3, qs2, qs2);
-    going = going && (p2 & 3u) != 0u;
-    const unsigned p3 = lane_query(QC, qcache, round_tag, S, going, qs3, qs2, qs3);
-    going = going && (p3 & 3u) != 0u;
-    // (3) candidate 4-tuples in the reference's nested-loop order (i0 outermost), first valid one wins
-    const int n1 = packed_count(p1), n2 = packed_count(p2), n3 = packed_count(p3);
-    const int total = going ? packed_count(p0) * n1 * n2 * n3 : 0;
-    bool ok = false;
-    int nq0 = 0, nq1 = 0, nq2 = 0, nq3 = 0;
-    for (int t = 0; __any_sync(full, !ok && t < total); ++t) {
-      if (!ok && t < total) {
-        int r = t;
-        const int i3 = r % n3; r /= n3;
-        const int i2 = r % n2; r /= n2;
-        const int i1 = r % n1; r /= n1;
-        const int c0 = packed_cand(p0, r), c1 = packed_cand(p1, i1), c2 = packed_cand(p2, i2), c3 = packed_cand(p3, i3);
-        if (is_valid_quad_s(QC.P, c0, c1, c2, c3)) {
-          ok = true;
-          nq0 = c0; nq1 = c1; nq2 = c2; nq3 = c3;
-        }
-      }
-    }
-    // (4) update the board
-    if (need) {
-      if (ok) {
-        // rotate_right(dir): v[(j + dir) & 3] = nq[j], i.e. v[i] = nq[(i - dir) & 3]
-        const int v[4] = {dir == 0 ? nq0 : (dir == 1 ? nq3 : (dir == 2 ? nq2 : nq1)),
-                          dir == 0 ? nq1 : (dir == 1 ? nq0 : (dir == 2 ? nq3 : nq2)),
-                          dir == 0 ? nq2 : (dir == 1 ? nq1 : (dir == 2 ? nq0 : nq3)),
-                          dir == 0 ? nq3 : (dir == 1 ? nq2 : (dir == 2 ? nq1 : nq0))};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) S[(kSOffActive + (v[j] >> 5)) * 32] &= ~(1u << (v[j] & 31));
-        S[(kSOffQuads + 2 * n_quads) * 32] = (unsigned)v[0] | ((unsigned)v[1] << 16);
-        S[(kSOffQuads + 2 * n_quads + 1) * 32] = (unsigned)v[2] | ((unsigned)v[3] << 16);
-        cell_st(nci, (unsigned)(n_quads + 1));
-        {
-          uint32_t& w = S[(kSOffStack + ((depth - 1) >> 1)) * 32];
-          const int sh = 16 * ((depth - 1) & 1);
-          w = (w & ~(0xffffu << sh)) | ((unsigned)(cur_ci | (cur_i << 8)) << sh);
-        }
-        ++n_quads;
-        ++depth;
-        cur_ci = nci;
-        cur_i = 0;
-      } else {
-        cell_st(nci, 0xffu);
-      }
-    }
-  }
-  __syncwarp();
 }
 
 // ---- init_quads, enumerated by one warp ----------------------------------------------------------
@@ -1100,10 +768,9 @@ __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
   E.exhausted = n_diff < 2;
 }
 
-// Appends valid quads to qlist (capacity qcap quads, from *list_n on) until the seed is exhausted
-// (returns true) or the list may not hold another batch (returns false; call again after draining
-// the list).
-__device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int16_t* qlist, int qcap, int* list_n) {
+// Appends valid quads to F.fx_qlist (from *list_n on) until the seed is exhausted (returns true)
+// or the list may not hold another batch (returns false; call again after draining the list).
+__device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) {
   // the throughput path keeps these arrays in shared memory: address them as such (as_shared)
   const float* const sx = as_shared(F.sx);
   const float* const sy = as_shared(F.sy);
@@ -1111,6 +778,7 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int16_t* qlis
   int16_t* const same = as_shared(F.same);
   int16_t* const diff = as_shared(F.diff);
   const float* const st = as_shared(F.st);
+  int16_t* const qlist = as_shared(F.fx_qlist);
   float* const dvx = as_shared(F.fx_dvx);
   float* const dvy = as_shared(F.fx_dvy);
   unsigned long long* const tmask = as_shared(F.fx_tmask);
@@ -1119,7 +787,7 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int16_t* qlis
   for (;;) {
     if (E.q_n >= 32 || (E.exhausted && E.q_n > 0)) {
       // expensive gates for up to 32 survivors, in order
-      if (*list_n + 32 > qcap) return false;
+      if (*list_n + 32 > kQListCap) return false;
       const int take = E.q_n < 32 ? E.q_n : 32;
       bool valid = false;
       int s1 = 0, d0 = 0, d1 = 0;
@@ -1263,30 +931,14 @@ constexpr int kMaxRanges = 8;  // seeds whose quads may share one list batch of 
 __device__ __noinline__ int find_best_board_fast(Frame& F) {
   if (F.n == 0) return -1;
   // shared-memory arrays of the block, addressed as such (as_shared)
-  // Candidate quads between enumeration and scoring.  First round: 64 quads in shared memory,
-  // scored by the four-lane groups (real boards: few, large).  Later rounds, when the leftover
-  // saddles fit a lane board's active mask: one lane per board (warp_score_small), fed from a long
-  // list in this warp's global scratch (the seed-best arrays, free during the search), so that
-  // every seed this warp claims in the wave is enumerated before the 32 lanes start scoring.
-  uint16_t* const qscore_s = as_shared(F.fx_qscore);
-  int16_t* const qlist_s = as_shared(F.fx_qlist);
-  const bool small = F.fx_small != 0 && F.round > 0 && F.n <= kSMaxSaddles;
-  uint16_t* const qscore = small ? (uint16_t*)F.seedbest.vals : qscore_s;
-  int16_t* const qlist = small ? F.seedbest.quads : qlist_s;
-  int qcap = kQListCap;
-  if (small) {
-    qcap = F.max_quads < F.lat * F.lat ? F.max_quads : F.lat * F.lat;  // entries of the two scratch arrays
-    qcap = (qcap < 512 ? qcap : 512) & ~31;
-    if (qcap < kQListCap) qcap = 0;  // (tiny max_saddles option) no room: keep the shared-memory list
-  }
-  const bool use_small = small && qcap > 0;
-  if (!use_small) qcap = kQListCap;
+  uint16_t* const qscore = as_shared(F.fx_qscore);
+  int16_t* const qlist = as_shared(F.fx_qlist);
   uint16_t* const wscore = as_shared(F.fx_wscore);
   int16_t* const wquad = as_shared(F.fx_wquad);
   int* const ctl = as_shared(F.ctl);
   long long t0 = clock64();
   if (F.warp == 0) {
-    grid_build_warp(F, (uint16_t*)as_shared(F.fx_gstate));
+    grid_build_warp(F);
     select_seeds(F);
   }
   if (F.lane == 0) *(int*)(F.fx_save0 + (size_t)F.warp * F.fx_save_stride) = 0;  // no board kept yet
@@ -1294,11 +946,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
   AGB_TM_ADD(1, clock64() - t0);
   int seeds_left = ctl[0];
   F.g_on = ctl[5];
-  F.g_sat = 0;
-  if (F.g_on) {
-    F.g_start = F.g_base;
-    grid_adopt_bucket(F);
-  }
+  if (F.g_on) F.g_start = F.g_base + 1;
   // first wave: two seeds (the first board is usually found by the first or second seed); after the
   // first board the leftovers rarely hold another one and every seed will be visited: all (up to
   // 30) seeds form ONE wave, so the warps of the block meet at a barrier once instead of once per
@@ -1339,7 +987,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
             rng_lo[n_rng] = rng_hi[n_rng] = list_n;
             ++n_rng;
           }
-          const bool seed_done = seed_enum_fill(F, E, use_small ? qlist : qlist_s, qcap, &list_n);
+          const bool seed_done = seed_enum_fill(F, E, &list_n);
           rng_hi[n_rng - 1] = list_n;
           if (!seed_done) break;  // list full: score it, then continue with this seed
           begun = false;
@@ -1348,42 +996,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
         AGB_TM_ADD(9, list_n);
         // ---- score the listed quads: eight boards side by side, four lanes each
         const long long ts = clock64();
-        if (use_small) {
-          warp_score_small(F, qlist, qscore, list_n);
-          // boards that outgrew a lane: the four-lane groups score them, 64 at a time through the
-          // shared-memory list (what those leave as kScoreRedo goes to the general path below)
-          for (int base = 0; base < list_n;) {
-            int n_re = 0;
-            int k = base;
-            for (; k < list_n && n_re < kQListCap; k += 32) {  // gather up to 64 overflowed entries, in list order
-              const int kk = k + F.lane;
-              const bool re = kk < list_n && qscore[kk] == kScoreRedo;
-              const unsigned m = __ballot_sync(0xffffffffu, re);
-              if (n_re + __popc(m) > kQListCap) break;
-              if (re) {
-                const int dst = n_re + __popc(m & ((1u << F.lane) - 1u));
-                for (int j = 0; j < 4; ++j) qlist_s[4 * dst + j] = qlist[4 * kk + j];
-                qscore_s[dst] = (uint16_t)kk;  // remember where the entry came from (overwritten by its score)
-              }
-              n_re += __popc(m);
-            }
-            const int k_end = k;
-            if (n_re > 0) {
-              __syncwarp();
-              // the origin of each entry, kept in registers across the scoring call (two per lane)
-              const int o0 = F.lane < n_re ? qscore_s[F.lane] : -1, o1 = F.lane + 32 < n_re ? qscore_s[F.lane + 32] : -1;
-              __syncwarp();
-              warp_score_quads(F, n_re);
-              __syncwarp();
-              if (o0 >= 0) qscore[o0] = qscore_s[F.lane];
-              if (o1 >= 0) qscore[o1] = qscore_s[F.lane + 32];
-              __syncwarp();
-            }
-            base = k_end;
-          }
-        } else {
-          warp_score_quads(F, list_n);
-        }
+        warp_score_quads(F, list_n);
         __syncwarp();
         bool redo = false;
         for (int k = F.lane; k < list_n; k += 32) redo |= qscore[k] == kScoreRedo;

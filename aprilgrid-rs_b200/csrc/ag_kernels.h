@@ -21,7 +21,7 @@ struct BoardWsLayout {
   int smem_saddles, grid_cap_cells;
   size_t sm_pos, sm_gstart, sm_gitem, sm_hist, sm_ctl, sm_warp0;
   size_t sm_wave, sm_gpos;
-  size_t smw_cell, smw_active, smw_small, smw_qlist, smw_qscore, smw_fvec, smw_elig, smw_squeue;
+  size_t smw_cell, smw_active, smw_small, smw_qlist, smw_qscore, smw_fvec, smw_squeue;
   size_t smem_per_warp, smem_per_block;
 };
 BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles);
@@ -58,7 +58,7 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
                          int hamming,
                          int max_boards, ag_tag* out, int cap, int* n_out, uint32_t* frame_status,
                          int32_t* tap_quads, int* tap_n_quads, int tap_cap, int use_grid, int fast,
-                         uint32_t* timing, cudaStream_t s);
+                         uint32_t* timing, int n_above, int n_upto, cudaStream_t s);
 
 // ag_render.cu
 int launch_render_boards(uint8_t* frames, int n_frames, int w, int h, int cols, int rows,

@@ -51,11 +51,18 @@ def run(label, max_boards=2, pad=0, warps=0, chunk=None, reps=3, opts=()):
 
 which = os.environ.get("K6_PROBE", "all")
 run("default (2 boards, n=%d)" % n)
+if which == "rounds":
+    run("1 board", max_boards=1)
+if which == "split":
+    run("board_split = 0", opts=(("board_split", 0),))
+    run("default, n=1024 (chunk 1024)", chunk=1024)
+    run("board_split = 0, chunk 1024", chunk=1024, opts=(("board_split", 0),))
 if which == "all":
     run("1 board", max_boards=1)
     # 37.1 KB per block -> 6 blocks per SM; pads chosen so that 5, 4, 3, 2 blocks fit in 227 KB
-    for blocks, pad in ((5, 8 * 1024), (4, 19 * 1024), (3, 38 * 1024), (2, 76 * 1024)):
-        run("%d blocks / SM" % blocks, pad=pad)
+    if os.environ.get("AG_LIB"):  # board_smem_pad exists in experiment builds only
+        for blocks, pad in ((5, 8 * 1024), (4, 19 * 1024), (3, 38 * 1024), (2, 76 * 1024)):
+            run("%d blocks / SM" % blocks, pad=pad)
     run("4 warps / frame", warps=4)
     for c in (296, 444, 888, 1024):
         run("chunk %d (sync calls)" % c, chunk=c)
