@@ -495,8 +495,9 @@ int run_boards(ag_detector* det, BoardSlot& S, const uint8_t* d_frames, const Fr
   // whose frame belongs to the other launch exits at once.
   const int big = det->board_saddle_tier >= 0 ? (int)det->board_saddle_tier + 1
                                               : ((long long)g.w * g.h > 1572864ll ? 2 : 1);
-  const bool batch = det->board_warps == 0 && n >= det->board_batch_frames;
-  const int n_launch = (batch && det->board_split) ? 2 : 1;
+  const bool many = n >= det->board_batch_frames;
+  const bool batch = det->board_warps == 0 && many;
+  const int n_launch = (many && det->board_split) ? 2 : 1;
   for (int pass = 0; pass < n_launch; ++pass) {
     const int tier = (n_launch == 2 && pass == 0) ? 0 : big;
     const int n_above = (n_launch == 2 && pass == 1) ? S.layout[0].smem_saddles : -1;

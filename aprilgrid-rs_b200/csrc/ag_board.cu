@@ -169,6 +169,8 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.best.vals = (int16_t*)(W + L.off_best_vals);
   F.best.n_quads = F.best.n_touched = F.best.score = 0;
   F.stack = (int16_t*)(WW + L.woff_stack);
+  F.dec_qlist = (int16_t*)(W + L.off_warp0 + L.woff_sb_quads);  // warp 0's seed-best arrays: free while decoding
+  F.dec_qbits = (unsigned long long*)(W + L.off_warp0 + L.woff_sb_vals);
   F.seeds = (int16_t*)(W + L.off_seeds);
   // bucket grid: 32 px buckets, doubled until the grid fits its shared-memory budget
   {

@@ -148,6 +148,8 @@ struct Frame {
   size_t fx_save_stride; //   fx_save0 + w * fx_save_stride
   unsigned long long* fx_qcache;  // global: the frame's neighbour-search cache (kQCacheEntries entries)
   uint32_t* tm;          // optional per-frame timing / work counters ([16], may be null)
+  int16_t* dec_qlist;    // decoding: the found board's quads in visiting order (warp 0's seed-best quads)
+  unsigned long long* dec_qbits;  // ... and their bit patterns / decoded (id, rotation)
 };
 
 // ---- warp plumbing ---------------------------------------------------------------------
@@ -1240,6 +1242,82 @@ __device__ __noinline__ int best_tag_warp(const Frame& F, uint64_t bits, int* ro
   }
   return id;
 }
+
+// Decoding of the found board (detector.rs:512-536) by the whole block.  Warp 0 lists the board's
+// quads in visiting order; every thread of the block then takes quads for the bit patterns (one
+// lane per quad: decode_positions, affine fit, 36 samples) and every warp takes quads for the
+// code-table search (one warp per pattern); finally warp 0 enters the results into the map in
+// visiting order, 32 at a time -- a repeated id overwrites, as HashMap::insert -- and marks the
+// saddles of decoded quads for removal.  Returns the number of listed quads (tap).
+__device__ __noinline__ int decode_board_block(Frame& F, int round) {
+  int16_t* const qlist = F.dec_qlist;
+  unsigned long long* const qbits = F.dec_qbits;
+  if (F.warp == 0) {
+    BoardState& B = F.bs;
+    for (int i = F.lane; i < F.n; i += 32) F.remove[i] = 0;
+    const int n_cells = F.lat * F.lat;
+    int n_list = 0;
+    for (int base = 0; base < n_cells; base += 32) {  // all_tag_indexes in ascending (x, y) order
+      const int cv = B.cell[base + F.lane];
+      const unsigned m = __ballot_sync(0xffffffffu, cv > 0);
+      if (cv > 0) {
+        const int dst = n_list + __popc(m & ((1u << F.lane) - 1u));
+        for (int j = 0; j < 4; ++j) qlist[4 * dst + j] = B.quads[(cv - 1) * 4 + j];
+      }
+      n_list += __popc(m);
+    }
+    if (round == 0 && F.tap_quads)
+      for (int i = F.lane; i < n_list && i < F.tap_cap; i += 32)
+        for (int j = 0; j < 4; ++j) F.tap_quads[i * 4 + j] = qlist[4 * i + j];
+    if (F.lane == 0) F.ctl[6] = n_list;
+  }
+  __syncthreads();
+  const int n_list = F.ctl[6];
+  // bit patterns: one lane per quad
+  for (int i = (int)threadIdx.x; i < n_list; i += (int)blockDim.x)
+    qbits[i] = decode_bits_lane(F, qlist[4 * i], qlist[4 * i + 1], qlist[4 * i + 2], qlist[4 * i + 3]);
+  __syncthreads();
+  // code-table search: one warp per pattern; the entry becomes valid << 63 | id << 8 | rotation
+  for (int i = F.warp; i < n_list; i += F.n_warps) {
+    const unsigned long long b = qbits[i];
+    unsigned long long res = 0ull;
+    if (b >> 63) {  // warp-uniform
+      int rot = 0;
+      const int id = best_tag_warp(F, b & ~(1ull << 63), &rot);
+      if (id >= 0) res = (1ull << 63) | ((unsigned long long)id << 8) | (unsigned long long)rot;
+    }
+    __syncwarp();
+    if (F.lane == 0) qbits[i] = res;
+  }
+  __syncthreads();
+  if (F.warp == 0) {
+    for (int base = 0; base < n_list; base += 32) {
+      const int i = base + F.lane;
+      const unsigned long long res = i < n_list ? qbits[i] : 0ull;
+      const bool ok = (res >> 63) != 0ull;
+      const int id = ok ? (int)((res >> 8) & 0xffffffull) : -1 - F.lane;
+      const int rot = (int)(res & 3ull);
+      // of the quads of this batch that decoded to the same id the last one wins (insert overwrites)
+      const unsigned peers = __match_any_sync(0xffffffffu, id);
+      if (ok) {
+        if ((31 - __clz((int)peers)) == F.lane) {
+          TagRec t;
+          t.id = (uint32_t)id;
+          for (int j = 0; j < 4; ++j) {  // rotate_left(rot) then reverse() (:467-469)
+            const int sq = qlist[4 * i + (((3 - j) + rot) & 3)];
+            t.xy[2 * j] = F.sx[sq];
+            t.xy[2 * j + 1] = F.sy[sq];
+          }
+          F.tag_by_id[t.id] = t;
+          F.tag_valid[t.id] = 1;
+        }
+        for (int j = 0; j < 4; ++j) F.remove[qlist[4 * i + j]] = 1;
+      }
+      __syncwarp();
+    }
+  }
+  return n_list;
+}
 #endif
 AGB_FN void detect_boards(Frame& F, int max_boards) {
   for (int round = 0; round < max_boards; ++round) {
@@ -1256,62 +1334,21 @@ AGB_FN void detect_boards(Frame& F, int max_boards) {
 #if AGB_DEVICE
     const long long t_dec = clock64();
 #endif
+#if AGB_DEVICE
+    const int n_tap_dev = decode_board_block(F, round);  // every warp of the block
+#endif
     if (F.warp == 0) {
       BoardState& B = F.bs;
-      for (int i = F.lane; i < F.n; i += AGB_LANES) F.remove[i] = 0;
-      AGB_SYNC();
       int n_tap = 0;
       // all_tag_indexes in ascending (x, y) order
       const int n_cells = F.lat * F.lat;
 #if AGB_DEVICE
-      // (1) the board's quads in visiting order -> list (the seed-best arrays are free here)
-      int16_t* qlist = F.seedbest.quads;
-      uint64_t* qbits = (uint64_t*)F.seedbest.vals;
-      int n_list = 0;
-      for (int base = 0; base < n_cells; base += 32) {
-        const int cv = F.bs.cell[base + F.lane];
-        const unsigned m = __ballot_sync(0xffffffffu, cv > 0);
-        if (cv > 0) {
-          const int dst = n_list + __popc(m & ((1u << F.lane) - 1u));
-          for (int j = 0; j < 4; ++j) qlist[4 * dst + j] = B.quads[(cv - 1) * 4 + j];
-        }
-        n_list += __popc(m);
-      }
-      __syncwarp();
-      if (round == 0 && F.tap_quads) {
-        for (int i = F.lane; i < n_list && i < F.tap_cap; i += 32)
-          for (int j = 0; j < 4; ++j) F.tap_quads[i * 4 + j] = qlist[4 * i + j];
-        n_tap = n_list;
-      }
-      // (2) one lane per quad: positions, affine fit, samples, bit pattern
-      for (int base = 0; base < n_list; base += 32) {
-        const int i = base + F.lane;
-        if (i < n_list) qbits[i] = decode_bits_lane(F, qlist[4 * i], qlist[4 * i + 1], qlist[4 * i + 2], qlist[4 * i + 3]);
-      }
-      __syncwarp();
-      // (3) in visiting order: code-table search on the whole warp, result map (a repeated id overwrites)
-      for (int i = 0; i < n_list; ++i) {
-        const uint64_t b = qbits[i];
-        if (!(b >> 63)) continue;  // warp-uniform
-        int rot = 0;
-        const int id = best_tag_warp(F, b & ~(1ull << 63), &rot);
-        if (id < 0) continue;
-        if (F.lane == 0) {
-          TagRec t;
-          t.id = (uint32_t)id;
-          for (int j = 0; j < 4; ++j) {  // rotate_left(rot) then reverse() (:467-469)
-            const int sq = qlist[4 * i + (((3 - j) + rot) & 3)];
-            t.xy[2 * j] = F.sx[sq];
-            t.xy[2 * j + 1] = F.sy[sq];
-          }
-          F.tag_by_id[t.id] = t;
-          F.tag_valid[t.id] = 1;
-          for (int j = 0; j < 4; ++j) F.remove[qlist[4 * i + j]] = 1;
-        }
-        __syncwarp();
-      }
+      (void)B;
+      (void)n_cells;
+      n_tap = (round == 0 && F.tap_quads) ? n_tap_dev : 0;
 #else
       // host test build (one lane): quad after quad through decode_quad
+      for (int i = F.lane; i < F.n; i += AGB_LANES) F.remove[i] = 0;
       for (int base = 0; base < n_cells; base += AGB_LANES) {
         const int ci = base + F.lane;
         unsigned m = agb_ballot(B.cell[ci] > 0);

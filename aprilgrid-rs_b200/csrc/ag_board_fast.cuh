@@ -375,7 +375,7 @@ __device__ __forceinline__ int packed_count(unsigned p) { return (int)(p & 3u); 
 __device__ __forceinline__ int packed_cand(unsigned p, int k) { return (int)((p >> (2 + 10 * k)) & 0x3ffu); }
 
 // ---- Board::new + try_expand (board.rs:27-48, :114-176), eight boards per warp --------------------
-// Scores the quads F.fx_qlist[0 .. nq): score = number of quads of the grown board, or kScoreRedo
+// Scores the quads qlist[0 .. nq) into qscore[]: score = number of quads of the grown board, or kScoreRedo
 // when the board leaves the group window / quad capacity.  A group of four lanes grows one board;
 // the eight groups of the warp advance in LOCKSTEP, one expansion attempt per iteration (cheap
 // bookkeeping steps -- returning to a parent cell, neighbours that already hold a tag -- are
@@ -392,7 +392,7 @@ constexpr int kSaveMin = 12;
 constexpr int kSaveBytes = 16 + 256 + 512;
 // TM: the instantiation with the timing taps (option board_timing); the production one carries none.
 template <bool TM>
-__device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
+__device__ __noinline__ void warp_score_quads_t(const Frame& F, const int16_t* qlist, uint16_t* qscore, int nq) {
   const QueryCtx QC = make_query_ctx(F);
   const int max_quads = F.max_quads;
   // searches are cached per (round, a, b, self); the 7-bit round tag bounds the rounds that may use it
@@ -404,8 +404,6 @@ __device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
   const int grp = F.lane >> 2, jl = F.lane & 3, gshift = grp * 4;
   const unsigned gmask = 0xfu << gshift;
   uint8_t* const gstate = as_shared(F.fx_gstate);
-  const int16_t* const qlist = as_shared(F.fx_qlist);
-  uint16_t* const qscore = as_shared(F.fx_qscore);
   uint8_t* gs = gstate + grp * kGroupBytes;
   uint8_t* cell = gs + kGOffCell;
   int16_t* quads = (int16_t*)(gs + kGOffQuads);
@@ -601,9 +599,9 @@ __device__ __noinline__ void warp_score_quads_t(const Frame& F, int nq) {
   }
 }
 
-__device__ __forceinline__ void warp_score_quads(const Frame& F, int nq) {
-  if (F.tm) warp_score_quads_t<true>(F, nq);
-  else warp_score_quads_t<false>(F, nq);
+__device__ __forceinline__ void warp_score_quads(const Frame& F, const int16_t* qlist, uint16_t* qscore, int nq) {
+  if (F.tm) warp_score_quads_t<true>(F, qlist, qscore, nq);
+  else warp_score_quads_t<false>(F, qlist, qscore, nq);
 }
 
 // ---- init_quads, enumerated by one warp ----------------------------------------------------------
@@ -768,9 +766,10 @@ __device__ __noinline__ void seed_enum_begin(Frame& F, SeedEnum& E, int s0) {
   E.exhausted = n_diff < 2;
 }
 
-// Appends valid quads to F.fx_qlist (from *list_n on) until the seed is exhausted (returns true)
-// or the list may not hold another batch (returns false; call again after draining the list).
-__device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) {
+// Appends valid quads to qlist (capacity qcap quads, from *list_n on) until the seed is exhausted
+// (returns true) or the list may not hold another batch (returns false; call again after draining
+// the list).
+__device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int16_t* qlist, int qcap, int* list_n) {
   // the throughput path keeps these arrays in shared memory: address them as such (as_shared)
   const float* const sx = as_shared(F.sx);
   const float* const sy = as_shared(F.sy);
@@ -778,7 +777,6 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
   int16_t* const same = as_shared(F.same);
   int16_t* const diff = as_shared(F.diff);
   const float* const st = as_shared(F.st);
-  int16_t* const qlist = as_shared(F.fx_qlist);
   float* const dvx = as_shared(F.fx_dvx);
   float* const dvy = as_shared(F.fx_dvy);
   unsigned long long* const tmask = as_shared(F.fx_tmask);
@@ -787,7 +785,7 @@ __device__ __noinline__ bool seed_enum_fill(Frame& F, SeedEnum& E, int* list_n) 
   for (;;) {
     if (E.q_n >= 32 || (E.exhausted && E.q_n > 0)) {
       // expensive gates for up to 32 survivors, in order
-      if (*list_n + 32 > kQListCap) return false;
+      if (*list_n + 32 > qcap) return false;
       const int take = E.q_n < 32 ? E.q_n : 32;
       bool valid = false;
       int s1 = 0, d0 = 0, d1 = 0;
@@ -916,7 +914,7 @@ __device__ __forceinline__ void general_state_init(Frame& F) {
 #define AGB_TM_ADD(slot, v) do { if (F.tm && F.warp == 0 && F.lane == 0) F.tm[slot] += (uint32_t)(v); } while (0)
 
 constexpr int kWaveMax = 16;  // seeds whose quads may be scored side by side
-constexpr int kMaxRanges = 8;  // seeds whose quads may share one list batch of a warp
+constexpr int kMaxRanges = 32;  // seeds whose quads may share one list batch of a warp (a wave has at most 30)
 
 // try_find_best_board (detector.rs:588-639).  Every warp of the block calls it.  Returns 1 with
 // the best board (after try_fix_missing) live in warp 0's F.bs, or -1 for None.
@@ -931,8 +929,23 @@ constexpr int kMaxRanges = 8;  // seeds whose quads may share one list batch of 
 __device__ __noinline__ int find_best_board_fast(Frame& F) {
   if (F.n == 0) return -1;
   // shared-memory arrays of the block, addressed as such (as_shared)
-  uint16_t* const qscore = as_shared(F.fx_qscore);
-  int16_t* const qlist = as_shared(F.fx_qlist);
+  // Candidate quads between enumeration and scoring.  First round: 64 quads in shared memory (one
+  // or two seeds per warp).  Later rounds visit every seed, each with a dozen short-lived boards:
+  // the list moves to this warp's global scratch (the seed-best arrays, free during the search) and
+  // holds the quads of ALL the seeds the warp claims in the wave, so the eight lane groups run dry
+  // once per wave instead of once per 64 quads.
+  uint16_t* qscore = as_shared(F.fx_qscore);
+  int16_t* qlist = as_shared(F.fx_qlist);
+  int qcap = kQListCap;
+  if (F.round > 0) {
+    int cap = F.max_quads < F.lat * F.lat ? F.max_quads : F.lat * F.lat;  // entries of the two scratch arrays
+    cap = (cap < 512 ? cap : 512) & ~31;
+    if (cap > kQListCap) {
+      qcap = cap;
+      qlist = F.seedbest.quads;
+      qscore = (uint16_t*)F.seedbest.vals;
+    }
+  }
   uint16_t* const wscore = as_shared(F.fx_wscore);
   int16_t* const wquad = as_shared(F.fx_wquad);
   int* const ctl = as_shared(F.ctl);
@@ -987,7 +1000,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
             rng_lo[n_rng] = rng_hi[n_rng] = list_n;
             ++n_rng;
           }
-          const bool seed_done = seed_enum_fill(F, E, &list_n);
+          const bool seed_done = seed_enum_fill(F, E, qlist, qcap, &list_n);
           rng_hi[n_rng - 1] = list_n;
           if (!seed_done) break;  // list full: score it, then continue with this seed
           begun = false;
@@ -996,7 +1009,7 @@ __device__ __noinline__ int find_best_board_fast(Frame& F) {
         AGB_TM_ADD(9, list_n);
         // ---- score the listed quads: eight boards side by side, four lanes each
         const long long ts = clock64();
-        warp_score_quads(F, list_n);
+        warp_score_quads(F, qlist, qscore, list_n);
         __syncwarp();
         bool redo = false;
         for (int k = F.lane; k < list_n; k += 32) redo |= qscore[k] == kScoreRedo;

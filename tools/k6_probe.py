@@ -55,8 +55,8 @@ if which == "rounds":
     run("1 board", max_boards=1)
 if which == "split":
     run("board_split = 0", opts=(("board_split", 0),))
-    run("default, n=1024 (chunk 1024)", chunk=1024)
-    run("board_split = 0, chunk 1024", chunk=1024, opts=(("board_split", 0),))
+    run("4 warps / frame", warps=4)
+    run("1 board", max_boards=1)
 if which == "all":
     run("1 board", max_boards=1)
     # 37.1 KB per block -> 6 blocks per SM; pads chosen so that 5, 4, 3, 2 blocks fit in 227 KB
