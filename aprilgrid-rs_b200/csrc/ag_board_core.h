@@ -1123,46 +1123,64 @@ AGB_NOINLINE uint64_t decode_bits_lane(const Frame& F, int q0, int q1, int q2, i
   const double h0d = axx / sxx, h1d = axy / syy, h3d = ayx / sxx, h4d = ayy / syy;
   const float h0 = (float)h0d, h1 = (float)h1d, h2 = (float)(mcx - h0d * mx - h1d * my);
   const float h3 = (float)h3d, h4 = (float)h4d, h5 = (float)(mcy - h3d * mx - h4d * my);
-  // bit_code :80-122; sample s = (x - border) * edge + (y - border), x outer.  All (up to 36)
-  // samples are loaded first, with no use in between, so their memory latencies overlap.
-  const int ns = F.edge * F.edge;
-  int v[36];
-  bool oob = false;
-  {
-    int ix = 0, iy = 0;
+  // bit_code :80-122; sample s = (x - border) * edge + (y - border), x outer.  Two passes over the
+  // sample grid, one grid row (<= 6 samples, loaded together so their latencies overlap) per trip of
+  // a ROLLED loop: first the brightness range, then the bits -- the second pass reads the same few
+  // bytes again (cache hits).  Rolled on purpose: fully unrolled, this function was a third of the
+  // board kernel's code and its instruction-cache footprint hurt the search loops of the other
+  // frames on the SM.
+  const int edge = F.edge, ns = edge * edge;
+  auto sample_row = [&](int ix, int v[6]) -> bool {  // false: a sample outside the image
+    bool inside = true;
+    const float fx = (float)(F.border + ix);
 AGB_UNROLL
-    for (int sidx = 0; sidx < 36; ++sidx) {
-      v[sidx] = 0;
-      if (sidx < ns) {
-        const float fx = (float)(F.border + ix), fy = (float)(F.border + iy);
+    for (int iy = 0; iy < 6; ++iy) {
+      v[iy] = 0;
+      if (iy < edge) {
+        const float fy = (float)(F.border + iy);
         const float px = fadd(fadd(fmul(h0, fx), fmul(h1, fy)), h2);
         const float py = fadd(fadd(fmul(h3, fx), fmul(h4, fy)), h5);
         const uint32_t x = sat_u32(roundf(px)), y = sat_u32(roundf(py));
-        if (x < (uint32_t)F.w && y < (uint32_t)F.h) v[sidx] = luma8_at(F, x, y);
-        else oob = true;  // a sample outside the image
-        if (++iy == F.edge) { iy = 0; ++ix; }
+        if (x < (uint32_t)F.w && y < (uint32_t)F.h) v[iy] = luma8_at(F, x, y);
+        else inside = false;
       }
     }
-  }
-  if (oob) return 0ull;
+    return inside;
+  };
   int min_b = 255, max_b = 0;
+  bool oob = false;
+#if AGB_DEVICE
+#pragma unroll 1
+#endif
+  for (int ix = 0; ix < edge; ++ix) {
+    int v[6];
+    if (!sample_row(ix, v)) oob = true;
 AGB_UNROLL
-  for (int sidx = 0; sidx < 36; ++sidx)
-    if (sidx < ns) {
-      min_b = v[sidx] < min_b ? v[sidx] : min_b;
-      max_b = v[sidx] > max_b ? v[sidx] : max_b;
-    }
+    for (int iy = 0; iy < 6; ++iy)
+      if (iy < edge) {
+        min_b = v[iy] < min_b ? v[iy] : min_b;
+        max_b = v[iy] > max_b ? v[iy] : max_b;
+      }
+  }
+  if (oob) return 0ull;  // a sample outside the image
   if (max_b - min_b < 50) return 0ull;  // :97
   const int mid_b = (int)sat_u32(roundf(fdiv(fadd((float)min_b, (float)max_b), 2.0f)));
   uint64_t bits = 0;
   int invalid = 0;
+#if AGB_DEVICE
+#pragma unroll 1
+#endif
+  for (int ix = 0; ix < edge; ++ix) {
+    int v[6];
+    sample_row(ix, v);
 AGB_UNROLL
-  for (int sidx = 0; sidx < 36; ++sidx)
-    if (sidx < ns) {
-      const int dlt = mid_b - v[sidx];
-      if ((dlt < 0 ? -dlt : dlt) < 10) ++invalid;
-      if (v[sidx] > mid_b) bits |= 1ull << (ns - 1 - sidx);  // the first sample is the most significant bit
-    }
+    for (int iy = 0; iy < 6; ++iy)
+      if (iy < edge) {
+        const int dlt = mid_b - v[iy];
+        if ((dlt < 0 ? -dlt : dlt) < 10) ++invalid;
+        if (v[iy] > mid_b) bits |= 1ull << (ns - 1 - (ix * edge + iy));  // the first sample is the most significant bit
+      }
+  }
   if (invalid > 3) return 0ull;
   return bits | (1ull << 63);
 }

@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--e2e-sync", action="store_true",
                     help="e2e with synchronous ag_detect_batch calls (default: streaming, two calls in flight)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="extra ag_set_option settings (experiments), e.g. --opt dense_variant=2")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -208,6 +210,9 @@ def main():
         det.set_option("board_lattice", args.lattice)
     if args.board_warps >= 0:
         det.set_option("board_warps", args.board_warps)
+    for kv in args.opt:
+        key, _, val = kv.partition("=")
+        det.set_option(key, int(val))
     B = args.batch or (1024 if args.workload == "detect" else 256)
     cap = 64
     stream = torch.cuda.Stream()  # a real (non-default) stream: the kernels and the events share it
