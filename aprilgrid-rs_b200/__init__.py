@@ -112,6 +112,13 @@ def lib():
         L.ag_launch_count.argtypes = [vp]
         L.ag_stage_times.argtypes = [vp, vp, vp, ci]
         L.ag_render_boards_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, C.c_uint64, vp]
+        L.ag_multi_create.argtypes = [ci, vp, vp, ci, vp]
+        L.ag_multi_destroy.argtypes = [vp]
+        L.ag_multi_device_count.argtypes = [vp]
+        L.ag_multi_last_error.restype = C.c_char_p
+        L.ag_multi_last_error.argtypes = [vp]
+        L.ag_multi_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+        L.ag_multi_detect_batch.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp, ci, vp, vp]
         L.ag_test_unorm_tables.argtypes = [vp, vp, vp, vp, vp]
         L.ag_test_board_times.argtypes = [vp, ci, vp, ci]
         _lib = L
@@ -344,6 +351,57 @@ class TagDetector:
         r8, r16 = np.zeros(256, np.float32), np.zeros(65536, np.float32)
         self._check(lib().ag_test_unorm_tables(self._h, _p(o8), _p(o16), _p(r8), _p(r16)))
         return o8, o16, r8, r16
+
+
+class MultiTagDetector:
+    """detect_batch over several GPUs of one box (ag_multi_*): the batch is cut into contiguous
+    frame ranges, one per device; results come back in frame order, byte-identical to one device."""
+
+    def __init__(self, tag_family=TagFamily.T36H11, optional_detector_params=None, devices=None):
+        self._h = C.c_void_p(None)
+        params = optional_detector_params or DetectorParams.default_params()
+        cp = params._c()
+        devs = np.asarray(devices if devices is not None else [], np.int32)
+        rc = lib().ag_multi_create(int(tag_family), C.byref(cp), _p(devs) if len(devs) else None, len(devs),
+                                   C.byref(self._h))
+        if rc != AG_OK:
+            self._h = C.c_void_p(None)
+            raise RuntimeError("ag_multi_create failed (%d): %s" % (rc, lib().ag_multi_last_error(None).decode()))
+        self.n_devices = int(lib().ag_multi_device_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().ag_multi_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        if lib().ag_multi_set_option(self._h, key.encode(), int(value)) != AG_OK:
+            raise RuntimeError("aprilgrid_b200: %s" % lib().ag_multi_last_error(self._h).decode())
+
+    def detect_batch_into(self, frames, out, cnt, status=None):
+        n = frames.shape[0]
+        fmt, w, h, st = image_format(frames[0])
+        rc = lib().ag_multi_detect_batch(self._h, _p(frames), frames.strides[0], n, w, h, st, fmt, _p(out),
+                                         out.shape[1], _p(cnt), _p(status))
+        if rc != AG_OK:
+            raise RuntimeError("aprilgrid_b200 error %d: %s" % (rc, lib().ag_multi_last_error(self._h).decode()))
+        return rc
+
+    def detect_batch(self, frames, cap_per_frame=128):
+        frames = np.ascontiguousarray(frames)
+        n = frames.shape[0]
+        out = np.zeros((n, cap_per_frame), TAG_DTYPE)
+        cnt = np.zeros(n, np.int32)
+        status = np.zeros(n, np.uint32)
+        if n:
+            self.detect_batch_into(frames, out, cnt, status)
+        return [_tags_to_dict(out[i, :cnt[i]]) for i in range(n)]
 
 
 def saddles_as_array(s):

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ag_codebook.h"
@@ -1459,6 +1460,98 @@ AG_API int ag_test_unorm_tables(ag_detector* det, float* out8, float* out16, flo
   AG_CUDA(det, cudaMemcpy(ref16, r16, 65536 * 4, cudaMemcpyDeviceToHost));
   cudaFree(d);
   return AG_OK;
+}
+
+// ---- one detector over several GPUs ------------------------------------------------------------
+// Frames are independent (TagDetector::detect is stateless, src/detector.rs:505-540): a batch is
+// cut into contiguous frame ranges [g * B / G, (g + 1) * B / G), one per device, each range goes
+// through that device's own pipeline on its own host thread, and every device writes its results
+// straight into the caller's arrays at its frames' positions -- the "gather" is the placement.
+struct ag_multi {
+  std::vector<ag_detector*> dets;
+  std::string err;
+};
+
+int ag_multi_create(int family, const ag_params* params, const int* devices, int n_devices, ag_multi** out) {
+  if (!out) return AG_ERR_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) {
+    g_create_error = "no CUDA device (this library has no CPU path)";
+    return AG_ERR_NO_DEVICE;
+  }
+  std::vector<int> devs;
+  if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+  else for (int d = 0; d < n_dev; ++d) devs.push_back(d);  // NULL / 0: every visible device
+  ag_multi* m = new ag_multi();
+  for (int d : devs) {
+    ag_detector* det = nullptr;
+    const int rc = ag_create(family, params, d, &det);
+    if (rc != AG_OK) {
+      for (auto* p : m->dets) ag_destroy(p);
+      delete m;
+      return rc;  // g_create_error holds the reason
+    }
+    m->dets.push_back(det);
+  }
+  *out = m;
+  return AG_OK;
+}
+
+void ag_multi_destroy(ag_multi* m) {
+  if (!m) return;
+  for (auto* d : m->dets) ag_destroy(d);
+  delete m;
+}
+
+int ag_multi_device_count(const ag_multi* m) { return m ? (int)m->dets.size() : 0; }
+
+const char* ag_multi_last_error(const ag_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+int ag_multi_set_option(ag_multi* m, const char* key, long value) {
+  if (!m) return AG_ERR_INVALID;
+  for (auto* d : m->dets) {
+    const int rc = ag_set_option(d, key, value);
+    if (rc != AG_OK) {
+      m->err = ag_last_error(d);
+      return rc;
+    }
+  }
+  return AG_OK;
+}
+
+int ag_multi_detect_batch(ag_multi* m, const void* frames, size_t frame_stride, int n_frames, int width,
+                          int height, size_t row_stride, int format, ag_tag* out, int cap_per_frame,
+                          int* n_per_frame, uint32_t* frame_status) {
+  if (!m || m->dets.empty()) return AG_ERR_INVALID;
+  if (!frames || !out || !n_per_frame || n_frames < 0 || cap_per_frame < 1) {
+    m->err = "null pointer or bad count";
+    return AG_ERR_INVALID;
+  }
+  // the strides every shard's offsets are computed with (0 = tightly packed, as in ag_detect_batch)
+  const size_t bpp = format == AG_L8 ? 1 : (format == AG_L16 ? 2 : 3);
+  const size_t rs = row_stride ? row_stride : (size_t)(width > 0 ? width : 0) * bpp;
+  const size_t fs = frame_stride ? frame_stride : rs * (size_t)(height > 0 ? height : 0);
+  const int G = (int)m->dets.size();
+  std::vector<int> rcs(G, AG_OK);
+  auto work = [&](int g) {
+    const long long lo = (long long)n_frames * g / G, hi = (long long)n_frames * (g + 1) / G;
+    if (hi <= lo) return;
+    rcs[g] = ag_detect_batch(m->dets[g], (const uint8_t*)frames + (size_t)lo * fs, fs, (int)(hi - lo), width, height,
+                             rs, format, out + (size_t)lo * cap_per_frame, cap_per_frame, n_per_frame + lo,
+                             frame_status ? frame_status + lo : nullptr);
+  };
+  std::vector<std::thread> th;
+  for (int g = 1; g < G; ++g) th.emplace_back(work, g);
+  work(0);
+  for (auto& t : th) t.join();
+  int worst = AG_OK;
+  for (int g = 0; g < G; ++g)
+    if (rcs[g] != AG_OK && (worst == AG_OK || rcs[g] != AG_ERR_CAPACITY)) {  // a hard error outranks a capacity notice
+      worst = rcs[g];
+      m->err = std::string("device ") + std::to_string(m->dets[g]->device) + ": " + ag_last_error(m->dets[g]);
+    }
+  return worst;
 }
 
 }  // extern "C"

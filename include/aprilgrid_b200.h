@@ -217,6 +217,24 @@ AG_API int ag_stage_times(ag_detector* det, double* ms_out, uint64_t* n_out, int
 AG_API int ag_render_boards_device(ag_detector* det, void* d_frames, int n_frames, int width,
                                    int height, int cols, int rows, uint64_t seed, void* stream);
 
+/* ---- one detector over several GPUs of one box ---------------------------------------------
+ * detect_batch for a multi-GPU host: frames are independent (src/detector.rs:505-540), so the
+ * batch is cut into contiguous frame ranges [g*B/G, (g+1)*B/G), one per device, each handled by
+ * that device's own pipeline on its own host thread; every device writes its results into the
+ * caller's arrays at its frames' positions (no collective on the data path).  devices = NULL or
+ * n_devices = 0: every visible device.  Same arguments, results and error behaviour as
+ * ag_detect_batch (always synchronous); byte-identical to one device processing the batch.   */
+typedef struct ag_multi ag_multi;
+AG_API int ag_multi_create(int family, const ag_params* params, const int* devices, int n_devices,
+                           ag_multi** out);
+AG_API void ag_multi_destroy(ag_multi* m);
+AG_API int ag_multi_device_count(const ag_multi* m);
+AG_API const char* ag_multi_last_error(const ag_multi* m);
+AG_API int ag_multi_set_option(ag_multi* m, const char* key, long value); /* applied to every device */
+AG_API int ag_multi_detect_batch(ag_multi* m, const void* frames, size_t frame_stride, int n_frames,
+                                 int width, int height, size_t row_stride, int format, ag_tag* out,
+                                 int cap_per_frame, int* n_per_frame, uint32_t* frame_status);
+
 AG_API const char* ag_version(void);
 
 #ifdef __cplusplus

@@ -73,6 +73,24 @@ def lib():
     return _lib
 
 
+def stage_times(reset=True):
+    """{stage: ms per frame} of detect() since the last reset (wall time summed over threads)."""
+    ms = np.zeros(4, np.float64)
+    n = C.c_longlong(0)
+    L = lib()
+    L.orc_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_stage_times(ms.ctypes.data_as(C.c_void_p), C.byref(n), 1 if reset else 0)
+    k = max(1, n.value)
+    return {"frames": int(n.value), "dense_ms": ms[0] / k, "clusters_refine_ms": ms[1] / k,
+            "board_search_ms": ms[2] / k, "decode_ms": ms[3] / k}
+
+
+def selftest_point_index(n, n_queries, k, mode, seed):
+    L = lib()
+    L.orc_selftest_point_index.argtypes = [C.c_int] * 4 + [C.c_uint]
+    return int(L.orc_selftest_point_index(n, n_queries, k, mode, seed))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 

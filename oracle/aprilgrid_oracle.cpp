@@ -30,6 +30,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <array>
 #include <map>
 #include <thread>
@@ -450,9 +452,24 @@ struct FrontEnd {
   std::vector<Saddle> raw, refined;
 };
 
+// Wall time per stage, summed over all calling threads (benchmark bookkeeping only; bench.py prints
+// it so the CPU number can be checked against the reference's own bench, benches/bench_detection.rs).
+// 0 gray + blur + Hessian + min, 1 clusters + refinement + filter, 2 board search, 3 decode + map
+std::atomic<long long> g_stage_ns[4];
+std::atomic<long long> g_stage_frames;
+struct StageTimer {
+  int stage;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageTimer(int s) : stage(s), t0(std::chrono::steady_clock::now()) {}
+  ~StageTimer() {
+    g_stage_ns[stage] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+
 void refined_saddle_points(const void* pixels, int w, int h, size_t stride, int fmt,
                            const Params& prm, FrontEnd* fe, bool keep_resp) {  // detector.rs:408
   size_t n = (size_t)w * h;
+  StageTimer* tm = new StageTimer(0);
   fe->luma.resize(n);
   fe->blur.resize(n);
   fe->resp.resize(n);
@@ -461,6 +478,8 @@ void refined_saddle_points(const void* pixels, int w, int h, size_t stride, int 
   hessian_response(fe->blur.data(), w, h, fe->resp.data());
   fe->min_resp = min_response(fe->resp.data(), n);
   fe->thr = fe->min_resp * 0.05f;
+  delete tm;
+  StageTimer tm1(1);
   fe->clusters.clear();
   if (keep_resp) {
     std::vector<float> work(fe->resp);
@@ -513,24 +532,102 @@ struct Neighbour {
   float d2;
   int idx;
 };
+// The reference answers these queries with a k-d tree in O(log n); a linear scan per query would
+// make the CPU baseline slower than the crate it stands for.  PointIndex therefore keeps the
+// points in a uniform bucket grid and visits buckets in rings around the query until the k-th
+// best distance is covered -- the SAME result as the linear scan (`nearest_scan`, kept as the
+// definition; tests/test_oracle_pins.py compares the two on random and degenerate point sets).
 struct PointIndex {
   const std::vector<Saddle>* pts;
-  void nearest(float qx, float qy, int k, std::vector<Neighbour>* out) const {
+  float x_min = 0, y_min = 0, inv = 0, side = 32.0f;
+  int nx = 0, ny = 0;
+  std::vector<int> start, item;
+
+  explicit PointIndex(const std::vector<Saddle>* p) : pts(p) { build(); }
+
+  static bool less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+  static void insert(float d2, int i, int k, std::vector<Neighbour>* out) {
+    if ((int)out->size() == k && !less(d2, i, out->back().d2, out->back().idx)) return;
+    int pos = (int)out->size();
+    if ((int)out->size() < k) out->push_back({d2, i});
+    else pos = k - 1;
+    while (pos > 0 && less(d2, i, (*out)[pos - 1].d2, (*out)[pos - 1].idx)) {
+      (*out)[pos] = (*out)[pos - 1];
+      --pos;
+    }
+    (*out)[pos] = {d2, i};
+  }
+  // the definition: every point, ascending (d2, idx)
+  void nearest_scan(float qx, float qy, int k, std::vector<Neighbour>* out) const {
     const auto& P = *pts;
     out->clear();
     for (int i = 0; i < (int)P.size(); ++i) {
       float dx = qx - P[i].x, dy = qy - P[i].y;
-      float d2 = dx * dx + dy * dy;
-      if ((int)out->size() == k && !(d2 < out->back().d2)) continue;
-      // insertion keeps ascending (d2, idx); i ascends so equal d2 goes after earlier ones
-      int pos = (int)out->size();
-      if ((int)out->size() < k) out->push_back({d2, i});
-      else pos = k - 1;
-      while (pos > 0 && (*out)[pos - 1].d2 > d2) {
-        (*out)[pos] = (*out)[pos - 1];
-        --pos;
+      insert(dx * dx + dy * dy, i, k, out);
+    }
+  }
+  void build() {
+    const auto& P = *pts;
+    const int n = (int)P.size();
+    bool finite = n > 0;
+    float x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    for (int i = 0; i < n && finite; ++i) {
+      if (!(fabsf(P[i].x) < 1.0e7f) || !(fabsf(P[i].y) < 1.0e7f)) finite = false;
+      if (i == 0) { x0 = x1 = P[i].x; y0 = y1 = P[i].y; }
+      x0 = std::min(x0, P[i].x); x1 = std::max(x1, P[i].x);
+      y0 = std::min(y0, P[i].y); y1 = std::max(y1, P[i].y);
+    }
+    nx = ny = 0;
+    if (!finite || n < 16 || getenv("ORACLE_LINEAR_SCAN")) return;  // tiny or odd sets (or asked to): the scan
+    // about two points per bucket, at most 256 x 256 buckets
+    side = std::max(8.0f, sqrtf(2.0f * std::max(1.0f, (x1 - x0) * (y1 - y0)) / (float)n));
+    side = std::max(side, std::max(x1 - x0, y1 - y0) / 256.0f + 1.0e-3f);
+    inv = 1.0f / side;
+    x_min = x0;
+    y_min = y0;
+    nx = (int)((x1 - x0) * inv) + 1;
+    ny = (int)((y1 - y0) * inv) + 1;
+    start.assign((size_t)nx * ny + 1, 0);
+    item.resize(n);
+    std::vector<int> cell(n);
+    for (int i = 0; i < n; ++i) {
+      int bx = std::min(nx - 1, std::max(0, (int)((P[i].x - x_min) * inv)));
+      int by = std::min(ny - 1, std::max(0, (int)((P[i].y - y_min) * inv)));
+      cell[i] = by * nx + bx;
+      ++start[cell[i] + 1];
+    }
+    for (size_t c = 1; c < start.size(); ++c) start[c] += start[c - 1];
+    std::vector<int> cur(start.begin(), start.end() - 1);
+    for (int i = 0; i < n; ++i) item[cur[cell[i]]++] = i;
+  }
+  void nearest(float qx, float qy, int k, std::vector<Neighbour>* out) const {
+    if (nx == 0 || !(fabsf(qx) < 1.0e7f) || !(fabsf(qy) < 1.0e7f)) return nearest_scan(qx, qy, k, out);
+    const auto& P = *pts;
+    out->clear();
+    const int cx = std::min(nx - 1, std::max(0, (int)floorf((qx - x_min) * inv)));
+    const int cy = std::min(ny - 1, std::max(0, (int)floorf((qy - y_min) * inv)));
+    const int rings = std::max(std::max(cx, nx - 1 - cx), std::max(cy, ny - 1 - cy));
+    auto bucket = [&](int bx, int by) {
+      if (bx < 0 || by < 0 || bx >= nx || by >= ny) return;
+      const int c = by * nx + bx;
+      for (int e = start[c]; e < start[c + 1]; ++e) {
+        const int i = item[e];
+        float dx = qx - P[i].x, dy = qy - P[i].y;
+        insert(dx * dx + dy * dy, i, k, out);
       }
-      (*out)[pos] = {d2, i};
+    };
+    for (int ring = 0; ring <= rings; ++ring) {
+      if (ring == 0) {
+        bucket(cx, cy);
+      } else {
+        for (int bx = cx - ring; bx <= cx + ring; ++bx) { bucket(bx, cy - ring); bucket(bx, cy + ring); }
+        for (int by = cy - ring + 1; by <= cy + ring - 1; ++by) { bucket(cx - ring, by); bucket(cx + ring, by); }
+      }
+      // every point not visited yet is farther than ring * side from the query (the visited
+      // buckets cover that distance around it, with a safety factor for the rounding of the bucket
+      // coordinates): once the k-th best is closer, it stays
+      const float covered = (float)ring * side * 0.999f;
+      if ((int)out->size() == k && out->back().d2 < covered * covered) break;
     }
   }
 };
@@ -715,7 +812,7 @@ void init_quads(const std::vector<Saddle>& refined, int s0_idx, const PointIndex
 bool try_find_best_board(const std::vector<Saddle>& refined, std::vector<Quad>* tags) {
   tags->clear();
   if (refined.empty()) return false;
-  PointIndex tree{&refined};
+  PointIndex tree(&refined);
   std::vector<char> active_mask(refined.size(), 1);
   std::map<int, std::vector<int>> hm;
   for (int i = 0; i < (int)refined.size(); ++i) hm[sat_i32(roundf(refined[i].theta))].push_back(i);
@@ -890,14 +987,22 @@ bool try_decode_quad(const Family& fam, const uint8_t* grey, uint32_t w, uint32_
 int detect(const Family& fam, const Params& prm, const void* pixels, int w, int h, size_t stride,
            int fmt, TagOut* out, int cap) {
   std::vector<uint8_t> grey((size_t)w * h);
-  to_luma_u8(pixels, w, h, stride, fmt, grey.data());
+  {
+    StageTimer tm(0);
+    to_luma_u8(pixels, w, h, stride, fmt, grey.data());
+  }
+  ++g_stage_frames;
   FrontEnd fe;
   refined_saddle_points(pixels, w, h, stride, fmt, prm, &fe, false);
   std::vector<Saddle> refined = fe.refined;
   std::map<uint32_t, TagOut> detected;
   std::vector<Quad> quads;
   for (int b = 0; b < prm.max_num_of_boards; ++b) {
-    if (!try_find_best_board(refined, &quads)) continue;
+    {
+      StageTimer tm(2);
+      if (!try_find_best_board(refined, &quads)) continue;
+    }
+    StageTimer tm(3);
     std::vector<char> remove(refined.size(), 0);
     for (auto& q : quads) {
       float qx[4], qy[4];
@@ -930,6 +1035,36 @@ int detect(const Family& fam, const Params& prm, const void* pixels, int w, int 
 // C entry points for the Python test harness (ctypes).  Names are orc_*.
 // =====================================================================================
 extern "C" {
+
+// Test hook: the bucket-grid index against the linear scan for n points / queries drawn from a
+// seeded generator (mode 0 uniform, 1 clustered with exact duplicates, 2 collinear).  Returns the
+// number of queries whose (d2, idx) lists differ.
+int orc_selftest_point_index(int n, int n_queries, int k, int mode, unsigned seed) {
+  std::vector<Saddle> pts(n);
+  unsigned s = seed * 2654435761u + 12345u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)(s >> 8) / 16777216.0f; };
+  for (int i = 0; i < n; ++i) {
+    Saddle p{};
+    if (mode == 1) { int c = (int)(rnd() * 7.0f); p.x = 100.0f + 150.0f * c + floorf(rnd() * 12.0f); p.y = 300.0f + floorf(rnd() * 12.0f) * 3.0f; }
+    else if (mode == 2) { p.x = floorf(rnd() * 900.0f); p.y = 77.0f; }
+    else { p.x = rnd() * 1280.0f; p.y = rnd() * 1024.0f; }
+    pts[i] = p;
+  }
+  PointIndex idx(&pts);
+  std::vector<Neighbour> a, b;
+  int bad = 0;
+  for (int q = 0; q < n_queries; ++q) {
+    float qx = rnd() * 1600.0f - 160.0f, qy = rnd() * 1300.0f - 130.0f;
+    if (q % 5 == 0 && n > 0) { qx = pts[q % n].x; qy = pts[q % n].y; }  // on a point: exact ties
+    idx.nearest(qx, qy, k, &a);
+    idx.nearest_scan(qx, qy, k, &b);
+    bool same = a.size() == b.size();
+    for (size_t i = 0; same && i < a.size(); ++i) same = a[i].idx == b[i].idx && a[i].d2 == b[i].d2;
+    if (!same) ++bad;
+  }
+  return bad;
+}
+
 
 void orc_to_luma_f32(const void* px, int w, int h, size_t stride, int fmt, float* out) {
   to_luma_f32(px, w, h, stride, fmt, out);
@@ -1068,7 +1203,7 @@ int orc_try_find_best_board(const float* saddles, int n, int32_t* quads_out, int
 int orc_init_quads(const float* saddles, int n, int s0_idx, int32_t* quads_out, int cap) {
   std::vector<Saddle> s(n);
   if (n) memcpy(s.data(), saddles, (size_t)n * 20);
-  PointIndex tree{&s};
+  PointIndex tree(&s);
   std::vector<Quad> q;
   init_quads(s, s0_idx, tree, &q);
   for (int i = 0; i < (int)q.size() && i < cap; ++i)
@@ -1129,6 +1264,16 @@ int orc_family_info(int family, int* edge, int* border, int* hamming, int* n_cod
   *edge = f.edge; *border = f.border; *hamming = f.hamming; *n_codes = f.n_codes;
   if (codes) *codes = f.codes;
   return 1;
+}
+
+// Per-stage wall time (ms, summed over threads) and frames since the last reset.
+void orc_stage_times(double* ms_out, long long* frames_out, int reset) {
+  for (int i = 0; i < 4; ++i) {
+    ms_out[i] = (double)g_stage_ns[i].load() * 1.0e-6;
+    if (reset) g_stage_ns[i] = 0;
+  }
+  *frames_out = g_stage_frames.load();
+  if (reset) g_stage_frames = 0;
 }
 
 // TagDetector::detect.  Returns the number of tags (may exceed cap; only cap are written).

@@ -644,3 +644,36 @@ def test_label_kernel_row_limit_fallback(detector, oracle):
     img[3::17] = 230
     img = (img.astype(np.int32) + rng.integers(-3, 4, img.shape)).clip(0, 255).astype(np.uint8)
     check_stages(detector, oracle, img, check_board=False)
+
+
+def test_multi_gpu_detect_batch_equals_single_gpu(pkg):
+    """ag_multi_detect_batch: the batch is sharded image-wise over the GPUs of the box, one host thread
+    per device; records come back in frame order, byte-identical to one GPU doing the whole batch.
+    With one visible GPU the same device is used twice (two handles, two shards)."""
+    import torch
+    n_gpu = torch.cuda.device_count()
+    devices = list(range(n_gpu)) if n_gpu >= 2 else [0, 0]
+    single = pkg.TagDetector(pkg.TagFamily.T36H11, None, device=0)
+    multi = pkg.MultiTagDetector(pkg.TagFamily.T36H11, None, devices=devices)
+    try:
+        assert multi.n_devices == len(devices)
+        n, w, h, cap = 37, 640, 480, 64  # 37: ragged shards
+        d_frames = torch.empty((n, h, w), dtype=torch.uint8, device="cuda:0")
+        single.render_boards_device(d_frames.data_ptr(), n, w, h, 6, 6, 9001)
+        torch.cuda.synchronize()
+        frames = d_frames.cpu().numpy()
+        ref = (np.zeros((n, cap), pkg.TAG_DTYPE), np.zeros(n, np.int32), np.zeros(n, np.uint32))
+        single.detect_batch_into(frames, *ref)
+        got = (np.zeros((n, cap), pkg.TAG_DTYPE), np.zeros(n, np.int32), np.ones(n, np.uint32))
+        multi.set_option("host_chunk_frames", 5)
+        multi.detect_batch_into(frames, *got)
+        assert ref[1].sum() > 30 * n
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2])
+        assert len(multi.detect_batch(frames[:3])) == 3 and multi.detect_batch(frames[:0]) == []
+        small = (np.zeros((n, 2), pkg.TAG_DTYPE), np.zeros(n, np.int32), np.zeros(n, np.uint32))
+        with pytest.raises(RuntimeError, match="cap_per_frame"):
+            multi.detect_batch_into(frames, *small)
+        assert np.array_equal(small[1], ref[1])
+    finally:
+        multi.close()
+        single.close()
