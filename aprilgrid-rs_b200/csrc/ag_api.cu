@@ -1,6 +1,9 @@
 // C ABI of the aprilgrid B200 library: handle, workspaces, chunked multi-stream pipeline.
 // See include/aprilgrid_b200.h for the contract of every entry point.
 #include <math.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <stdio.h>
 #include <string.h>
 
@@ -69,6 +72,8 @@ struct BoardSlot {
   // so it lives as long as the slot's board search), device results and pinned result staging
   uint8_t* d_in = nullptr;
   size_t cap_in_bytes = 0;
+  uint8_t* h_in = nullptr;  // pinned staging for frames that arrive in pageable host memory
+  size_t cap_h_in = 0;
   int hs_frames = 0, hs_tags = 0;
   ag_tag* d_tags = nullptr;
   int* d_ntags = nullptr;
@@ -330,6 +335,7 @@ int ensure_host_stage(ag_detector* det, BoardSlot& B, size_t in_bytes, int frame
 
 void free_board_slot(BoardSlot& B) {
   cudaFree(B.d_in); cudaFree(B.d_tags); cudaFree(B.d_ntags);
+  if (B.h_in) cudaFreeHost(B.h_in);
   if (B.h_tags) cudaFreeHost(B.h_tags);
   if (B.h_ntags) cudaFreeHost(B.h_ntags);
   if (B.h_status) cudaFreeHost(B.h_status);
@@ -428,6 +434,59 @@ void free_slot(Slot& S) {
   if (S.done) cudaEventDestroy(S.done);
   if (S.stream) cudaStreamDestroy(S.stream);
   S = Slot();
+}
+
+// Frames in ordinary (pageable) host memory -- a Vec<u8> packed from DynamicImages, a numpy array --
+// cannot be read by the copy engine directly: cudaMemcpyAsync would stage them through the
+// driver's small bounce buffer, synchronously and at a fraction of the link rate.  They are copied
+// into the slot's own pinned staging buffer by several host threads instead (memcpy at memory
+// bandwidth), from where the usual asynchronous upload takes them.
+bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+// One thread's share: streaming (non-temporal) stores, so the destination lines are not read
+// first -- the staging buffer is written once and then read by the copy engine, never by the CPU.
+void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+#if defined(__x86_64__) && defined(__SSE2__)
+  if (n >= 4096 && ((uintptr_t)dst & 15) == 0) {
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+      const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+      const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32)), d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+      _mm_stream_si128((__m128i*)(dst + i), a);
+      _mm_stream_si128((__m128i*)(dst + i + 16), b);
+      _mm_stream_si128((__m128i*)(dst + i + 32), c);
+      _mm_stream_si128((__m128i*)(dst + i + 48), d);
+    }
+    _mm_sfence();
+    memcpy(dst + i, src + i, n - i);
+    return;
+  }
+#endif
+  memcpy(dst, src, n);
+}
+void parallel_copy(uint8_t* dst, const uint8_t* src, size_t bytes) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = std::min<size_t>(std::max<unsigned>(hw, 1), 24);
+  nt = std::min(nt, std::max<size_t>(bytes >> 22, 1));  // at least 4 MB per thread
+  if (nt <= 1) {
+    stream_copy(dst, src, bytes);
+    return;
+  }
+  const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < nt; ++t) {
+    const size_t lo = t * per;
+    if (lo >= bytes) break;
+    th.emplace_back([=] { stream_copy(dst + lo, src + lo, std::min(per, bytes - lo)); });
+  }
+  stream_copy(dst, src, std::min(per, bytes));
+  for (auto& t : th) t.join();
 }
 
 // Stage ids for the optional timing: 0 K1 blur+hessian+min, 1 K2 threshold, 2 K3 label+centroid,
@@ -1056,6 +1115,7 @@ static int detect_batch_host(ag_detector* det, const void* frames, size_t frame_
   if (!det->up_stream) AG_CUDA(det, cudaStreamCreateWithFlags(&det->up_stream, cudaStreamNonBlocking));
   cudaStream_t s = D.stream, up = det->up_stream;
   const size_t chunk_bytes = (size_t)chunk * g.frame_stride;
+  const bool pageable = is_pageable(frames);
   // Chunk schedule: the pipeline fills while the first chunk uploads and drains while the last one
   // is searched, so a large batch starts and ends with quarter and half chunks.
   auto next_chunk = [&](int f0) {
@@ -1081,7 +1141,19 @@ static int detect_batch_host(ag_detector* det, const void* frames, size_t frame_
     const uint8_t* src = (const uint8_t*)frames + (size_t)f0 * g.frame_stride;
     const size_t bytes = (size_t)(n - 1) * g.frame_stride + g.row_stride * (size_t)(g.h - 1) +
                          (size_t)g.w * bytes_per_px(g.format);
-    AG_CUDA(det, cudaMemcpyAsync(B.d_in, src, bytes, cudaMemcpyHostToDevice, up));
+    const uint8_t* up_src = src;
+    if (pageable) {  // (the slot's previous upload is long done: its chunk has been collected)
+      if (chunk_bytes > B.cap_h_in) {
+        if (B.h_in) cudaFreeHost(B.h_in);
+        B.h_in = nullptr;
+        B.cap_h_in = 0;
+        AG_CUDA(det, cudaMallocHost((void**)&B.h_in, chunk_bytes));
+        B.cap_h_in = chunk_bytes;
+      }
+      parallel_copy(B.h_in, src, bytes);
+      up_src = B.h_in;
+    }
+    AG_CUDA(det, cudaMemcpyAsync(B.d_in, up_src, bytes, cudaMemcpyHostToDevice, up));
     AG_CUDA(det, cudaEventRecord(B.ev_up, up));
     AG_CUDA(det, cudaStreamWaitEvent(s, B.ev_up, 0));
     if ((rc = run_dense(det, D, B.d_in, g, n, true, s))) return rc;
