@@ -112,6 +112,9 @@ def lib():
         L.ag_launch_count.argtypes = [vp]
         L.ag_stage_times.argtypes = [vp, vp, vp, ci]
         L.ag_render_boards_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, C.c_uint64, vp]
+        L.ag_host_alloc.restype = vp
+        L.ag_host_alloc.argtypes = [sz]
+        L.ag_host_free.argtypes = [vp]
         L.ag_multi_create.argtypes = [ci, vp, vp, ci, vp]
         L.ag_multi_destroy.argtypes = [vp]
         L.ag_multi_device_count.argtypes = [vp]
@@ -351,6 +354,29 @@ class TagDetector:
         r8, r16 = np.zeros(256, np.float32), np.zeros(65536, np.float32)
         self._check(lib().ag_test_unorm_tables(self._h, _p(o8), _p(o16), _p(r8), _p(r16)))
         return o8, o16, r8, r16
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array in page-locked host memory (ag_host_alloc); keep the returned array alive while in use
+    and release it with pinned_free(arr)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib().ag_host_alloc(max(n, 1))
+    if not ptr:
+        raise MemoryError("ag_host_alloc(%d) failed" % n)
+    buf = (C.c_uint8 * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = ptr
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr):
+    ptr = _PINNED.pop(arr.__array_interface__["data"][0], None)
+    if ptr:
+        lib().ag_host_free(ptr)
 
 
 class MultiTagDetector:

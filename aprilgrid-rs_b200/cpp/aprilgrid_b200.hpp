@@ -125,4 +125,42 @@ class TagDetector {
   ag_detector* h_ = nullptr;
 };
 
+// detect_batch over every GPU of the box (ag_multi_*): frames sharded image-wise, results in frame order.
+class MultiTagDetector {
+ public:
+  explicit MultiTagDetector(TagFamily family, std::optional<DetectorParams> params = std::nullopt,
+                            const std::vector<int>& devices = {}) {
+    DetectorParams p = params.value_or(DetectorParams::default_params());
+    ag_params cp{p.tag_spacing_ratio, p.min_saddle_angle, p.max_saddle_angle, p.max_num_of_boards};
+    if (ag_multi_create(static_cast<int>(family), &cp, devices.empty() ? nullptr : devices.data(), (int)devices.size(),
+                        &m_) != AG_OK)
+      throw std::runtime_error(std::string("aprilgrid_b200: ") + ag_multi_last_error(nullptr));
+  }
+  ~MultiTagDetector() { ag_multi_destroy(m_); }
+  MultiTagDetector(const MultiTagDetector&) = delete;
+  MultiTagDetector& operator=(const MultiTagDetector&) = delete;
+  int device_count() const { return ag_multi_device_count(m_); }
+
+  std::vector<TagMap> detect_batch(const void* base, size_t frame_stride, int n_frames, int width, int height,
+                                   size_t row_stride, int format, int cap_per_frame = 128) const {
+    std::vector<ag_tag> out((size_t)n_frames * cap_per_frame);
+    std::vector<int> cnt(n_frames);
+    if (ag_multi_detect_batch(m_, base, frame_stride, n_frames, width, height, row_stride, format, out.data(),
+                              cap_per_frame, cnt.data(), nullptr) != AG_OK)
+      throw std::runtime_error(std::string("aprilgrid_b200: ") + ag_multi_last_error(m_));
+    std::vector<TagMap> res(n_frames);
+    for (int i = 0; i < n_frames; ++i) {
+      TagMap m;
+      const ag_tag* t = out.data() + (size_t)i * cap_per_frame;
+      for (int k = 0; k < cnt[i] && k < cap_per_frame; ++k)
+        m[t[k].id] = {{{t[k].xy[0], t[k].xy[1]}, {t[k].xy[2], t[k].xy[3]}, {t[k].xy[4], t[k].xy[5]}, {t[k].xy[6], t[k].xy[7]}}};
+      res[i] = std::move(m);
+    }
+    return res;
+  }
+
+ private:
+  ag_multi* m_ = nullptr;
+};
+
 }  // namespace aprilgrid

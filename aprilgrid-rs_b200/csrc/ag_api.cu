@@ -1534,6 +1534,21 @@ AG_API int ag_test_unorm_tables(ag_detector* det, float* out8, float* out16, flo
   return AG_OK;
 }
 
+// Page-locked host memory for callers that assemble batches themselves (a shim packing
+// DynamicImages, a capture loop): frames written here are uploaded by the copy engine directly, at
+// the link rate, without the staging copy ordinary (pageable) memory needs.
+void* ag_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void ag_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 // ---- one detector over several GPUs ------------------------------------------------------------
 // Frames are independent (TagDetector::detect is stateless, src/detector.rs:505-540): a batch is
 // cut into contiguous frame ranges [g * B / G, (g + 1) * B / G), one per device, each range goes

@@ -217,6 +217,13 @@ AG_API int ag_stage_times(ag_detector* det, double* ms_out, uint64_t* n_out, int
 AG_API int ag_render_boards_device(ag_detector* det, void* d_frames, int n_frames, int width,
                                    int height, int cols, int rows, uint64_t seed, void* stream);
 
+/* Page-locked host memory for batches the caller assembles itself (the Rust shim packs its
+ * DynamicImages into it): uploaded at the link rate without a staging copy.  Frames in ordinary
+ * (pageable) memory are accepted everywhere too -- the library then stages them through its own
+ * pinned buffers with several host threads, at memory-copy speed.  NULL on failure.            */
+AG_API void* ag_host_alloc(size_t bytes);
+AG_API void ag_host_free(void* p);
+
 /* ---- one detector over several GPUs of one box ---------------------------------------------
  * detect_batch for a multi-GPU host: frames are independent (src/detector.rs:505-540), so the
  * batch is cut into contiguous frame ranges [g*B/G, (g+1)*B/G), one per device, each handled by

@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): blurred image, response, threshold mask, component labels and
 tag ids bit-exact; refined corner coordinates within 1e-3 px (they come out bit-identical too;
 the tolerance is written where it is used)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -677,3 +679,26 @@ def test_multi_gpu_detect_batch_equals_single_gpu(pkg):
     finally:
         multi.close()
         single.close()
+
+
+def test_cpp_mirror_end_to_end(pkg, oracle, tmp_path):
+    """The C++ mirror of the reference API (cpp/aprilgrid_b200.hpp), compiled and run: detect,
+    detect_batch and MultiTagDetector give the oracle's tags."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cpp_mirror_demo")
+    libdir = os.path.join(root, "aprilgrid-rs_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "aprilgrid-rs_b200", "cpp"), "-o", exe,
+                           os.path.join(root, "tests", "cpp_mirror_demo.cpp"), "-L" + libdir, "-laprilgrid_b200",
+                           "-Wl,-rpath," + libdir])
+    img = synth.render_board_numpy(640, 480, seed=12, tag_px=44.0)
+    raw = tmp_path / "frame.raw"
+    raw.write_bytes(img.tobytes())
+    out = subprocess.check_output([exe, str(raw), "640", "480"], text=True).strip().splitlines()
+    want = oracle.detect(img)
+    assert out[-1].startswith("batch same")
+    got = {}
+    for ln in out[:-1]:
+        f = ln.split()
+        got[int(f[0])] = np.array([float(v) for v in f[1:]], np.float32).reshape(4, 2)
+    assert_tags_match(got, want)
