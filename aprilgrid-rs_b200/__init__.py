@@ -124,6 +124,8 @@ def lib():
         L.ag_multi_detect_batch.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp, ci, vp, vp]
         L.ag_test_unorm_tables.argtypes = [vp, vp, vp, vp, vp]
         L.ag_test_board_times.argtypes = [vp, ci, vp, ci]
+        L.ag_test_render_pose.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, C.c_uint64]
+        L.ag_test_boards_from_saddles.argtypes = [vp, vp, ci, vp, ci, ci, sz, ci, vp, ci, vp, vp, ci, vp]
         _lib = L
     return _lib
 
@@ -342,6 +344,25 @@ class TagDetector:
         self._check(L.ag_stage_tags(self._h, _p(tags), 1024, C.byref(n)))
         return dict(blur=blur, resp=resp, min=float(mt[0]), thr=float(mt[1]), mask=mask, labels=labels,
                     centers=centers, raw=raw, refined=ref, quads=quads, tags=_tags_to_dict(tags[:n.value]))
+
+    def _boards_from_saddles(self, saddles, img):
+        """Test hook: board search + decode on a given saddle list (N x 5 float32: x, y, k, theta, phi).
+        Returns (quads of the first best board [M x 4 int32], {id: corners})."""
+        sd = np.ascontiguousarray(saddles, np.float32).reshape(-1, 5)
+        img = np.ascontiguousarray(img)
+        fmt, w, h, st = image_format(img)
+        quads = np.zeros((4096, 4), np.int32)
+        tags = np.zeros(1024, TAG_DTYPE)
+        nq, nt = C.c_int(0), C.c_int(0)
+        self._check(lib().ag_test_boards_from_saddles(self._h, _p(sd), len(sd), _p(img), w, h, st, fmt, _p(quads), 4096,
+                                                      C.byref(nq), _p(tags), 1024, C.byref(nt)))
+        return quads[:nq.value].copy(), _tags_to_dict(tags[:nt.value])
+
+    def _render_pose(self, d_frame_ptr, width, height, cols, rows, hinv, noise=False, seed=0):
+        """Test hook: one frame of the device renderer under a given image -> page homography."""
+        h = np.ascontiguousarray(hinv, np.float32).reshape(9)
+        self._check(lib().ag_test_render_pose(self._h, C.c_void_p(d_frame_ptr), width, height, cols, rows, _p(h),
+                                              1 if noise else 0, seed))
 
     def _board_times(self, slot, n_frames):
         """Profiling hook: n_frames x 32 u32 timing taps of the last board-kernel launch of a slot."""

@@ -1496,10 +1496,67 @@ int ag_render_boards_device(ag_detector* det, void* d_frames, int n_frames, int 
     int n = std::min(32768, n_frames - f0);
     det->launches += launch_render_boards((uint8_t*)d_frames + (size_t)f0 * width * height, n, width,
                                           height, cols, rows, det->d_codes, det->fam.edge,
-                                          det->fam.border, seed + (uint64_t)f0 * 0x51ed27ull,
+                                          det->fam.border, seed + (uint64_t)f0 * 0x51ed27ull, nullptr, 1,
                                           (cudaStream_t)stream);
   }
   AG_CUDA(det, cudaGetLastError());
+  return AG_OK;
+}
+
+// Test hook (not in the public header): ONE frame of the renderer under a GIVEN pose -- hinv maps
+// image (x, y, 1) to page coordinates in tag sides (row-major 3x3, host pointer) -- with or without
+// the noise, so that tests can pin the renderer's geometry (id <-> lattice position, corner
+// positions) against tests/synth.py and scripts/generate_aprilgrid.py:1114-1167.
+AG_API int ag_test_render_pose(ag_detector* det, void* d_frame, int width, int height, int cols, int rows,
+                               const float* hinv, int noise, uint64_t seed) {
+  if (!det || !d_frame || !hinv || width <= 0 || height <= 0 || cols < 1 || rows < 1) return AG_ERR_INVALID;
+  if (cols * rows > det->fam.n_codes) return fail(det, AG_ERR_INVALID, "board has more tags than the family has codes");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  float* d_h = nullptr;
+  AG_CUDA(det, cudaMalloc((void**)&d_h, sizeof(float) * 9));
+  AG_CUDA(det, cudaMemcpy(d_h, hinv, sizeof(float) * 9, cudaMemcpyHostToDevice));
+  det->launches += launch_render_boards((uint8_t*)d_frame, 1, width, height, cols, rows, det->d_codes, det->fam.edge,
+                                        det->fam.border, seed, d_h, noise, 0);
+  AG_CUDA(det, cudaDeviceSynchronize());
+  cudaFree(d_h);
+  return AG_OK;
+}
+
+// Test hook (not in the public header): the board search + decoding (K6) on a GIVEN saddle list
+// (n x {x, y, k, theta, phi}, host) over a host image -- so that tests can put saddles exactly on
+// the gates of init_quads / is_valid_quad / the theta histogram.  Returns the quads of the first
+// best board (the tap) and the tags.
+AG_API int ag_test_boards_from_saddles(ag_detector* det, const ag_saddle* saddles, int n, const void* pixels,
+                                       int width, int height, size_t row_stride, int format, int32_t* quads_out,
+                                       int quad_cap, int* n_quads, ag_tag* tags_out, int tag_cap, int* n_tags) {
+  if (!det || !saddles || !pixels || !quads_out || !n_quads || !tags_out || !n_tags || n < 0) return AG_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  det->tap_valid = false;
+  FrameGeom g;
+  int rc = make_geom(det, width, height, row_stride, 0, format, &g);
+  if (rc) return rc;
+  set_caps(det, g);
+  if (n > det->cur_saddles) return fail(det, AG_ERR_INVALID, "more saddles than max_saddles");
+  Slot& S = det->big;
+  if ((rc = ensure_slot(det, S, g, 1, det->fam.n_codes, true))) return rc;
+  const size_t bytes = g.row_stride * (size_t)(g.h - 1) + (size_t)g.w * bytes_per_px(g.format);
+  cudaStream_t s = S.stream;
+  AG_CUDA(det, cudaMemcpyAsync(S.d_in, pixels, bytes, cudaMemcpyHostToDevice, s));
+  if (n > 0) AG_CUDA(det, cudaMemcpyAsync(S.bb.d_refined, saddles, sizeof(ag_saddle) * n, cudaMemcpyHostToDevice, s));
+  AG_CUDA(det, cudaMemcpyAsync(S.bb.d_nref, &n, sizeof(int), cudaMemcpyHostToDevice, s));
+  AG_CUDA(det, cudaMemsetAsync(S.d_status, 0, sizeof(uint32_t), s));
+  if ((rc = run_boards(det, S.bb, S.d_in, g, 1, S.d_tags, S.cap_tags, S.d_ntags, S.d_status, true, s))) return rc;
+  int nq = 0, nt = 0;
+  AG_CUDA(det, cudaMemcpyAsync(&nq, S.bb.d_tap_nquads, sizeof(int), cudaMemcpyDeviceToHost, s));
+  AG_CUDA(det, cudaMemcpyAsync(&nt, S.d_ntags, sizeof(int), cudaMemcpyDeviceToHost, s));
+  AG_CUDA(det, cudaStreamSynchronize(s));
+  *n_quads = nq;
+  *n_tags = nt;
+  const int mq = std::min(std::min(nq, quad_cap), S.bb.layout[0].max_quads), mt = std::min(std::min(nt, tag_cap), S.cap_tags);
+  if (mq > 0) AG_CUDA(det, cudaMemcpy(quads_out, S.bb.d_tap_quads, sizeof(int32_t) * 4 * mq, cudaMemcpyDeviceToHost));
+  if (mt > 0) AG_CUDA(det, cudaMemcpy(tags_out, S.d_tags, sizeof(ag_tag) * mt, cudaMemcpyDeviceToHost));
   return AG_OK;
 }
 

@@ -433,8 +433,10 @@ AGB_NOINLINE int nearest3_within(const Frame& F, float qx, float qy, float r2, i
     const float r = sqrtf(r2) * 1.0001f + 0.01f;
     int x0 = (int)floorf((qx - r) * F.g_inv), x1 = (int)floorf((qx + r) * F.g_inv);
     int y0 = (int)floorf((qy - r) * F.g_inv), y1 = (int)floorf((qy + r) * F.g_inv);
-    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
-    x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+    // both ends clamped INTO the grid: saddles outside the image sit in the border buckets
+    // (grid_bucket clamps too), so a window hanging over the edge must still reach those
+    x0 = x0 < 0 ? 0 : (x0 >= F.g_nx ? F.g_nx - 1 : x0); y0 = y0 < 0 ? 0 : (y0 >= F.g_ny ? F.g_ny - 1 : y0);
+    x1 = x1 >= F.g_nx ? F.g_nx - 1 : (x1 < 0 ? 0 : x1); y1 = y1 >= F.g_ny ? F.g_ny - 1 : (y1 < 0 ? 0 : y1);
     const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
     if (bw > 0 && bh > 0) {
       // rows of buckets are contiguous in g_item: one (start, end) range per bucket row
@@ -490,8 +492,10 @@ AGB_FN int nearest3_within_single(const Frame& F, float qx, float qy, float r2, 
     const float r = sqrtf(r2) * 1.0001f + 0.01f;
     int x0 = (int)floorf((qx - r) * F.g_inv), x1 = (int)floorf((qx + r) * F.g_inv);
     int y0 = (int)floorf((qy - r) * F.g_inv), y1 = (int)floorf((qy + r) * F.g_inv);
-    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
-    x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+    // both ends clamped INTO the grid: saddles outside the image sit in the border buckets
+    // (grid_bucket clamps too), so a window hanging over the edge must still reach those
+    x0 = x0 < 0 ? 0 : (x0 >= F.g_nx ? F.g_nx - 1 : x0); y0 = y0 < 0 ? 0 : (y0 >= F.g_ny ? F.g_ny - 1 : y0);
+    x1 = x1 >= F.g_nx ? F.g_nx - 1 : (x1 < 0 ? 0 : x1); y1 = y1 >= F.g_ny ? F.g_ny - 1 : (y1 < 0 ? 0 : y1);
     const int bw = x1 - x0 + 1;
     if (bw > 0)
       for (int by = y0; by <= y1; ++by) {
@@ -658,8 +662,10 @@ __device__ __forceinline__ void expand_queries_warp(const Frame& F, const BoardS
     const float r = sqrtf(r2) * 1.0001f + 0.01f;
     int x0 = (int)floorf((qx - r) * F.g_inv), x1 = (int)floorf((qx + r) * F.g_inv);
     int y0 = (int)floorf((qy - r) * F.g_inv), y1 = (int)floorf((qy + r) * F.g_inv);
-    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
-    x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+    // both ends clamped INTO the grid: saddles outside the image sit in the border buckets
+    // (grid_bucket clamps too), so a window hanging over the edge must still reach those
+    x0 = x0 < 0 ? 0 : (x0 >= F.g_nx ? F.g_nx - 1 : x0); y0 = y0 < 0 ? 0 : (y0 >= F.g_ny ? F.g_ny - 1 : y0);
+    x1 = x1 >= F.g_nx ? F.g_nx - 1 : (x1 < 0 ? 0 : x1); y1 = y1 >= F.g_ny ? F.g_ny - 1 : (y1 < 0 ? 0 : y1);
     const int bw = x1 - x0 + 1;
     if (bw > 0)
       for (int yy = y0 + sub; yy <= y1; yy += 8) {

@@ -220,8 +220,9 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a,
       r = sqrtf(r2) * 1.0001f + 0.01f;
       x0 = (int)floorf((qx - r) * F.g_inv); x1 = (int)floorf((qx + r) * F.g_inv);
       y0 = (int)floorf((qy - r) * F.g_inv); y1 = (int)floorf((qy + r) * F.g_inv);
-      x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
-      x1 = x1 >= F.g_nx ? F.g_nx - 1 : x1; y1 = y1 >= F.g_ny ? F.g_ny - 1 : y1;
+      // both ends clamped INTO the grid (saddles outside the image sit in the border buckets)
+      x0 = x0 < 0 ? 0 : (x0 >= F.g_nx ? F.g_nx - 1 : x0); y0 = y0 < 0 ? 0 : (y0 >= F.g_ny ? F.g_ny - 1 : y0);
+      x1 = x1 >= F.g_nx ? F.g_nx - 1 : (x1 < 0 ? 0 : x1); y1 = y1 >= F.g_ny ? F.g_ny - 1 : (y1 < 0 ? 0 : y1);
       if (x0 <= x1 && y0 <= y1) {
         cy = (int)floorf(qy * F.g_inv);
         cy = cy < y0 ? y0 : (cy > y1 ? y1 : cy);
@@ -258,8 +259,8 @@ __device__ __forceinline__ unsigned group_knn(const QueryCtx& F, bool on, int a,
         const float R = fminf(r, sqrtf(d3) * 1.0001f + 0.01f);
         bx0 = (int)floorf((qx - R) * F.g_inv);
         bx1 = (int)floorf((qx + R) * F.g_inv);
-        bx0 = bx0 < x0 ? x0 : bx0;
-        bx1 = bx1 > x1 ? x1 : bx1;
+        bx0 = bx0 < x0 ? x0 : (bx0 > x1 ? x1 : bx0);
+        bx1 = bx1 > x1 ? x1 : (bx1 < x0 ? x0 : bx1);
       }
       const float lb = (float)(j > 0 ? j - 1 : 0) * bsz;  // every saddle of the row is farther than this
       if (lb * lb * 0.9999f > stop_d3) {                   // ... and so are the remaining rows

@@ -63,6 +63,6 @@ int launch_boards_decode(const uint8_t* frames, const FrameGeom& g, int n_frames
 // ag_render.cu
 int launch_render_boards(uint8_t* frames, int n_frames, int w, int h, int cols, int rows,
                          const uint64_t* d_codes, int edge, int border, uint64_t seed,
-                         cudaStream_t s);
+                         const float* d_fixed_hinv, int noise, cudaStream_t s);
 
 }  // namespace ag

@@ -112,12 +112,23 @@ __device__ __forceinline__ bool page_is_white(float X, float Y, const Pose& P, i
   return true;
 }
 
+// fixed_hinv: null = seeded random pose per frame; else ONE given pose (image -> page, row-major 3x3)
+// for every frame, and noise only if `noise` is set (renderer tests).
 __global__ void __launch_bounds__(256)
 k_render_boards(uint8_t* __restrict__ frames, int w, int h, int cols, int rows,
-                const uint64_t* __restrict__ codes, int edge, int border, uint64_t seed) {
+                const uint64_t* __restrict__ codes, int edge, int border, uint64_t seed,
+                const float* __restrict__ fixed_hinv, int noise) {
   __shared__ Pose s_pose;
   const int f = blockIdx.z;
-  if (threadIdx.x == 0 && threadIdx.y == 0) make_pose(seed, f, w, h, cols, rows, &s_pose);
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    if (fixed_hinv) {
+      for (int i = 0; i < 9; ++i) s_pose.hinv[i] = fixed_hinv[i];
+      s_pose.wb = cols * 1.3f + 0.3f;
+      s_pose.hb = rows * 1.3f + 0.3f;
+    } else {
+      make_pose(seed, f, w, h, cols, rows, &s_pose);
+    }
+  }
   __syncthreads();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= w || y >= h) return;
@@ -138,17 +149,17 @@ k_render_boards(uint8_t* __restrict__ frames, int w, int h, int cols, int rows,
   uint64_t s = seed ^ (((uint64_t)f << 40) + ((uint64_t)y << 20) + (uint64_t)x);
   const uint64_t r = splitmix64(s);
   const int nsum = (int)(r & 255) + (int)((r >> 8) & 255) + (int)((r >> 16) & 255) + (int)((r >> 24) & 255);
-  v += ((float)nsum - 510.0f) * (2.0f / 147.8f);  // ~N(0, 2^2)
+  if (noise) v += ((float)nsum - 510.0f) * (2.0f / 147.8f);  // ~N(0, 2^2)
   v = fminf(fmaxf(rintf(v), 0.0f), 255.0f);
   frames[((size_t)f * h + y) * w + x] = (uint8_t)v;
 }
 
 int launch_render_boards(uint8_t* frames, int n_frames, int w, int h, int cols, int rows,
                          const uint64_t* d_codes, int edge, int border, uint64_t seed,
-                         cudaStream_t s) {
+                         const float* d_fixed_hinv, int noise, cudaStream_t s) {
   dim3 block(32, 8);
   dim3 grid((w + 31) / 32, (h + 7) / 8, n_frames);
-  k_render_boards<<<grid, block, 0, s>>>(frames, w, h, cols, rows, d_codes, edge, border, seed);
+  k_render_boards<<<grid, block, 0, s>>>(frames, w, h, cols, rows, d_codes, edge, border, seed, d_fixed_hinv, noise);
   return 1;
 }
 

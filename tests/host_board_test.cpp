@@ -77,7 +77,8 @@ int hb_detect_from_saddles(const float* saddles, int n, const uint8_t* img, int 
   if (use_grid) {
     F.g_start = gstart.data(); F.g_item = gitem.data();
     F.g_nx = (w + bucket - 1) / bucket; F.g_ny = (h + bucket - 1) / bucket;
-    F.g_cap_cells = grid_cap; F.g_cap_items = 512;  // as on the device F.g_inv = 1.0f / (float)bucket;
+    F.g_cap_cells = grid_cap; F.g_cap_items = 512;  // as on the device
+    F.g_inv = 1.0f / (float)bucket;
   }
   F.stack = stack.data(); F.seeds = seeds.data(); F.nn_idx = nn.data(); F.same = same.data();
   F.diff = diff.data(); F.samp = samp.data(); F.hist = hist.data(); F.remove = remove.data();

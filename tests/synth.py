@@ -116,3 +116,69 @@ def render_board_numpy(w=640, h=480, cols=6, rows=6, seed=0, tag_px=None, family
 
 def fixture_like_frames(n, w, h, seed=0, **kw):
     return np.stack([render_board_numpy(w, h, seed=seed + i, **kw) for i in range(n)])
+
+
+def ulp_step(v, k):
+    v = np.float32(v)
+    for _ in range(abs(int(k))):
+        v = np.nextafter(v, np.float32(np.inf if k > 0 else -np.inf), dtype=np.float32)
+    return v
+
+
+def adversarial_saddle_sets(base, rng):
+    """Saddle lists sitting ON the discontinuous gates of the board search (detector.rs:556-560, :603;
+    saddle.rs:18-66): theta differences of 5 / 80 degrees give or take a few ulps, theta at x.5
+    (round() boundaries of the seed histogram), and projective distortions that put the
+    opposite-angle difference of the tag quads at 10 degrees +- 1e-4."""
+    n = len(base)
+    d2 = ((base[:, None, :2] - base[None, :, :2]) ** 2).sum(-1)
+    near = np.argsort(d2, axis=1)[:, 1:12]
+
+    def wrap(t):  # keep theta in (-90, 90]: theta_distance_degree works modulo 180
+        t = np.float32(t)
+        while t > 90:
+            t = np.float32(t - np.float32(180))
+        while t <= -90:
+            t = np.float32(t + np.float32(180))
+        return t
+
+    for trial in range(24):  # (a) theta gates, (b) histogram boundaries
+        s = base.copy()
+        for _ in range(40):
+            i = int(rng.integers(n))
+            j = int(near[i, rng.integers(near.shape[1])])
+            gate = np.float32(rng.choice([5.0, -5.0, 80.0, -80.0, 100.0, -100.0, 175.0, -175.0]))
+            s[j, 3] = wrap(ulp_step(np.float32(s[i, 3] + gate), int(rng.integers(-2, 3))))
+        for _ in range(25):
+            i = int(rng.integers(n))
+            s[i, 3] = wrap(ulp_step(np.float32(np.floor(s[i, 3]) + 0.5), int(rng.integers(-2, 3))))
+        yield "theta%d" % trial, s
+
+    def angle_gap(q):  # |a0 - a2| of a quad given as 4 x 2 (saddle.rs:47-54), float64
+        v = [q[(k + 1) % 4] - q[k] for k in range(4)]
+        ang = lambda a, b: np.degrees(np.arctan2(b[1] * a[0] - b[0] * a[1], a[0] * b[0] + a[1] * b[1]))
+        return abs(ang(v[0], v[1]) - ang(v[2], v[3]))
+
+    c = base[:, :2].mean(axis=0)
+    ref = base[np.argsort(((base[:, :2] - c) ** 2).sum(-1))[:1], :2][0]
+    quad_ix = np.argsort(((base[:, :2] - ref) ** 2).sum(-1))[:4]
+    order = quad_ix[np.argsort(np.arctan2(*(base[quad_ix, :2] - base[quad_ix, :2].mean(0)).T[::-1]))]
+    for trial in range(16):  # (c) projective keystone: bisect its strength onto the 10-degree gate
+        ax = rng.uniform(-1, 1, 2)
+        ax /= np.linalg.norm(ax)
+
+        def warp(strength, pts):
+            wgt = 1.0 + strength * ((pts - c) @ ax)
+            return c + (pts - c) / wgt[:, None]
+
+        lo, hi = 0.0, 4e-3
+        target = 10.0 + rng.choice([-1e-4, -1e-5, 0.0, 1e-5, 1e-4])
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            if angle_gap(warp(mid, base[order, :2].astype(np.float64))) < target:
+                lo = mid
+            else:
+                hi = mid
+        s = base.copy()
+        s[:, :2] = warp(0.5 * (lo + hi), base[:, :2].astype(np.float64)).astype(np.float32)
+        yield "keystone%d" % trial, s

@@ -122,3 +122,23 @@ def test_one_board_limit(hb, pkg, oracle, images):
     got, _, _, _ = host_detect(hb, pkg, oracle, img, max_boards=1)
     want = oracle.detect(img, max_boards=1)
     assert sorted(got) == sorted(want) and 0 < len(want) < 72
+
+
+def test_gate_adversarial_saddle_sets(hb, pkg, oracle):
+    """Saddle lists sitting on the discontinuous gates of the board search (theta differences of
+    5 / 80 degrees +- ulps, theta at x.5, opposite-angle differences of 10 degrees +- 1e-4; some
+    saddles outside the image): the product's board logic == the oracle, quads in the same order.
+    (The GPU suite runs the same sets through the kernel.)"""
+    img = synth.render_board_numpy(640, 480, seed=3, tag_px=44.0)
+    base = oracle.front_end(img, want_labels=False)["refined"]
+    rng = np.random.default_rng(2024)
+    n_boards = 0
+    for name, s in synth.adversarial_saddle_sets(base, rng):
+        want = oracle.try_find_best_board(s)
+        _, quads, _, _ = host_detect(hb, pkg, oracle, img, saddles=s)
+        if want is None:
+            assert len(quads) == 0, name
+        else:
+            assert np.array_equal(quads, want), name
+            n_boards += 1
+    assert n_boards >= 30

@@ -702,3 +702,54 @@ def test_cpp_mirror_end_to_end(pkg, oracle, tmp_path):
         f = ln.split()
         got[int(f[0])] = np.array([float(v) for v in f[1:]], np.float32).reshape(4, 2)
     assert_tags_match(got, want)
+
+
+def test_device_renderer_geometry_is_the_chart_generators(detector, pkg, oracle):
+    """The on-device renderer against the chart definition (scripts/generate_aprilgrid.py:1114-1167)
+    and against tests/synth.py: under a GIVEN pose, the noiseless device frame equals the numpy
+    rendering pixel for pixel (up to f32 edge cases), and tag id i + j * cols sits at lattice column
+    i, row j counted from the BOTTOM of the board, its four corners where the pose puts the corners
+    of that tag."""
+    import torch
+    w, h, cols, rows = 960, 720, 6, 5
+    scale, tx, ty = 80.0, 90.0, 60.0  # frontal view: page (X, Y) in tag sides -> image px
+    H = np.array([[scale, 0.0, tx], [0.0, scale, ty], [0.0, 0.0, 1.0]])
+    d = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+    detector._render_pose(d.data_ptr(), w, h, cols, rows, np.linalg.inv(H), noise=False)
+    got = d.cpu().numpy()
+    want = synth.render_board_numpy(w, h, cols, rows, H=H, noise=0.0)
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert (diff > 0).mean() < 1e-3 and diff.max() <= 11  # a 1/16 coverage step at the odd f32 edge sample
+    tags = detector.detect(got)
+    assert sorted(tags) == list(range(cols * rows))
+    assert_tags_match(tags, oracle.detect(got))
+    hb = rows * 1.3 + 0.3
+    for tid, xy in tags.items():
+        i, j = tid % cols, tid // cols              # ids run row-major from the bottom row
+        x0, x1 = 0.3 + 1.3 * i, 1.3 * (i + 1)        # page extent of the tag, Y measured from the top
+        y1, y0 = hb - (0.3 + 1.3 * j), hb - 1.3 * (j + 1)
+        # integer image coordinates are pixel centres in the renderer and in the detector alike
+        exp = {(scale * X + tx, scale * Y + ty) for X in (x0, x1) for Y in (y0, y1)}
+        for cx, cy in xy:
+            assert min(abs(cx - ex) + abs(cy - ey) for ex, ey in exp) < 0.6, (tid, xy, sorted(exp))
+        assert len({(int(round(cx)), int(round(cy))) for cx, cy in xy}) == 4
+
+
+def test_board_search_on_gate_adversarial_saddles(detector, oracle):
+    """GPU board search == oracle on saddle lists constructed to sit on every discontinuous gate (a
+    1-ulp disagreement in an angle would flip a candidate there).  Quads of the first best board,
+    same set, same order."""
+    img = synth.render_board_numpy(640, 480, seed=3, tag_px=44.0)
+    base = oracle.front_end(img, want_labels=False)["refined"]
+    assert len(base) > 150
+    rng = np.random.default_rng(2024)
+    n_boards = 0
+    for name, s in synth.adversarial_saddle_sets(base, rng):
+        want = oracle.try_find_best_board(s)
+        got, _ = detector._boards_from_saddles(s, img)
+        if want is None:
+            assert len(got) == 0, name
+        else:
+            assert np.array_equal(got, want), name
+            n_boards += 1
+    assert n_boards >= 30
