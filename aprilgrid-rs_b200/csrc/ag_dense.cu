@@ -203,7 +203,10 @@ struct BlurRow {  // one blurred row: v[1..4] = the lane's 4 columns, v[0] / v[5
 
 // UNROLL6: six row steps per loop trip instead of three (see the end of the kernel).
 template <int FMT, bool WRITE_BLUR, bool UNROLL6>
-__global__ void __launch_bounds__(S_WARPS * 32, FMT == AG_L8 ? 8 : 6)
+#ifndef AG_K1_MIN_BLOCKS
+#define AG_K1_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(S_WARPS * 32, FMT == AG_L8 ? AG_K1_MIN_BLOCKS : 6)
 k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __restrict__ blur,
                       float* __restrict__ resp, uint32_t* __restrict__ frame_min) {
   const int lane = threadIdx.x & 31;

@@ -11,7 +11,7 @@ across ranks with no data-path collective.
 Workloads (BASELINE.json configs):
   detect   configs[2]: rendered 6x6 T36H11 boards, 1280x1024 L8, 1024 frames per GPU per step (default)
   dense    configs[1]: blur + Hessian + threshold kernels alone, 256 frames per step
-  dense4k  configs[3]: 3840x2160 RGB8 frames of a dense 24x13 board, 32 frames per GPU per step
+  dense4k  configs[3]: 3840x2160 RGB8 frames of a dense 24x13 board, 256 frames per GPU per step
   rig      configs[4]: one 2048x1536 camera stream per GPU, frames submitted ONE AT A TIME;
            sustained frames/s and the submit -> result latency distribution
 
@@ -332,7 +332,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="detect", choices=["detect", "dense", "dense4k", "rig"])
-    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default 1024; dense 256; dense4k 32)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default 1024; dense 256; dense4k 256)")
     ap.add_argument("--chunk", type=int, default=0, help="override pipeline chunk_frames")
     ap.add_argument("--lattice", type=int, default=0, help="override board_lattice (16/32/64)")
     ap.add_argument("--board-warps", type=int, default=-1, help="override board_warps (0 auto, 1/2/4/8)")
@@ -443,7 +443,7 @@ def main():
 
     # ---- configs[3]: 4K RGB dense boards ------------------------------------------------------
     if args.workload == "dense4k":
-        B = args.batch or 32
+        B = args.batch or 256
         barrier()
         launches0 = det.launch_count
         sampler = ClockSampler(local) if rank == 0 else None
@@ -655,7 +655,7 @@ def main():
     if args.workload == "detect" and not args.no_extras and rank == 0:
         extras = {}
         try:
-            extras["dense4k"] = run_dense4k(pkg, det, torch, 16, 3, 1, stream, SEED)
+            extras["dense4k"] = run_dense4k(pkg, det, torch, 128, 2, 1, stream, SEED)
         except Exception as ex:  # never lose the headline line over an extra
             extras["dense4k"] = {"error": repr(ex)}
         try:
