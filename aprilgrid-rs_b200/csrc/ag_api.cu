@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -1613,8 +1614,51 @@ void ag_host_free(void* p) {
 // straight into the caller's arrays at its frames' positions -- the "gather" is the placement.
 struct ag_multi {
   std::vector<ag_detector*> dets;
+  std::vector<double> h2d_gbs;  // host-to-device rate of each device, all devices copying at once
   std::string err;
 };
+
+// Pinned host -> device rate of every device of the set, measured with all of them copying at the
+// same time (64 MB x 4 each).  The GPUs of a box do not all get the same share of the host's
+// bandwidth, and a host-fed batch is as slow as its slowest shard.
+static void measure_h2d_rates(ag_multi* m) {
+  const int G = (int)m->dets.size();
+  m->h2d_gbs.assign(G, 0.0);
+  if (G < 2) return;
+  const size_t bytes = 64u << 20;
+  std::atomic<int> ready(0);
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; ++g)
+    th.emplace_back([&, g] {
+      void *h = nullptr, *d = nullptr;
+      cudaStream_t s = nullptr;
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      bool ok = cudaSetDevice(m->dets[g]->device) == cudaSuccess && cudaMallocHost(&h, bytes) == cudaSuccess &&
+                cudaMalloc(&d, bytes) == cudaSuccess && cudaStreamCreate(&s) == cudaSuccess &&
+                cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+      if (ok) {
+        memset(h, 1, bytes);
+        ok = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess;
+      }
+      ++ready;
+      while (ready.load() < G) std::this_thread::yield();  // start together
+      if (ok) {
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < 4; ++i) cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s);
+        cudaEventRecord(e1, s);
+        float ms = 0.0f;
+        if (cudaStreamSynchronize(s) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms > 0.0f)
+          m->h2d_gbs[g] = 4.0 * (double)bytes / (ms * 1e-3) / 1e9;
+      }
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      if (s) cudaStreamDestroy(s);
+      if (d) cudaFree(d);
+      if (h) cudaFreeHost(h);
+    });
+  for (auto& t : th) t.join();
+  cudaGetLastError();
+}
 
 int ag_multi_create(int family, const ag_params* params, const int* devices, int n_devices, ag_multi** out) {
   if (!out) return AG_ERR_INVALID;
@@ -1638,6 +1682,12 @@ int ag_multi_create(int family, const ag_params* params, const int* devices, int
     }
     m->dets.push_back(det);
   }
+  // distinct devices only: two handles on one GPU (tests) share a link, equal shards are right there
+  bool distinct = true;
+  for (size_t i = 0; i < devs.size(); ++i)
+    for (size_t j = 0; j < i; ++j) distinct = distinct && devs[i] != devs[j];
+  if (distinct) measure_h2d_rates(m);
+  else m->h2d_gbs.assign(devs.size(), 0.0);
   *out = m;
   return AG_OK;
 }
@@ -1678,8 +1728,22 @@ int ag_multi_detect_batch(ag_multi* m, const void* frames, size_t frame_stride, 
   const size_t fs = frame_stride ? frame_stride : rs * (size_t)(height > 0 ? height : 0);
   const int G = (int)m->dets.size();
   std::vector<int> rcs(G, AG_OK);
+  // shard boundaries: equal ranges, or -- when the devices' measured host-to-device rates differ by
+  // more than 5 % -- ranges in proportion to those rates
+  std::vector<long long> bound(G + 1, 0);
+  {
+    double lo_r = 1e300, hi_r = 0.0, sum = 0.0;
+    for (double r : m->h2d_gbs) { lo_r = std::min(lo_r, r); hi_r = std::max(hi_r, r); sum += r; }
+    const bool weighted = (int)m->h2d_gbs.size() == G && lo_r > 0.0 && hi_r > 1.05 * lo_r;
+    double acc = 0.0;
+    for (int g = 0; g < G; ++g) {
+      acc += weighted ? m->h2d_gbs[g] / sum : 1.0 / G;
+      bound[g + 1] = g + 1 == G ? n_frames : std::min<long long>(n_frames, (long long)llround(acc * n_frames));
+      if (bound[g + 1] < bound[g]) bound[g + 1] = bound[g];
+    }
+  }
   auto work = [&](int g) {
-    const long long lo = (long long)n_frames * g / G, hi = (long long)n_frames * (g + 1) / G;
+    const long long lo = bound[g], hi = bound[g + 1];
     if (hi <= lo) return;
     rcs[g] = ag_detect_batch(m->dets[g], (const uint8_t*)frames + (size_t)lo * fs, fs, (int)(hi - lo), width, height,
                              rs, format, out + (size_t)lo * cap_per_frame, cap_per_frame, n_per_frame + lo,

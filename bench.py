@@ -566,15 +566,31 @@ def main():
     # ---- end to end through the host-buffer C-ABI call ("e2e") -------------------------------
     e2e = None
     if args.workload == "detect" and not args.no_e2e:
-        h_frames = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
-        h_frames.copy_(frames)
+        # Frames per rank.  The GPUs of a box do not all get the same share of the host's memory /
+        # PCIe bandwidth (measured above, all ranks copying at once), and a host-fed job is as slow as
+        # its slowest rank: the N x B frames of a step are therefore sharded in proportion to each
+        # rank's measured host-to-device rate (equal shards when the rates agree within 5 %, and
+        # always at N = 1).  The equal-shard figure is measured too and reported beside it.
+        h2d_all = gather_list(h2d_gbs, world, "cuda")
+        balanced = world > 1 and max(h2d_all) > 1.05 * min(h2d_all)
+        Be = B
+        if balanced:
+            Be = int(round(world * B * h2d_all[rank] / sum(h2d_all) / 8.0)) * 8
+            Be = max(8, min(Be, 2 * B))
+        shard_frames = [int(round(v)) for v in gather_list(Be, world, "cuda")]
+        h_frames = torch.empty((max(Be, B), H, W), dtype=torch.uint8).pin_memory()
+        for lo in range(0, max(Be, B), B):
+            n_cp = min(B, max(Be, B) - lo)
+            h_frames[lo:lo + n_cp].copy_(frames[:n_cp])
         torch.cuda.synchronize()
-        hf = h_frames.numpy()
+        hf_all = h_frames.numpy()
+        hf = hf_all[:B]
+        Bo = max(Be, B)
 
         def pinned_out():
-            return (torch.zeros((B, cap * 9), dtype=torch.int32).pin_memory().numpy().view(pkg.TAG_DTYPE).reshape(B, cap),
-                    torch.zeros(B, dtype=torch.int32).pin_memory().numpy(),
-                    torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32))
+            return (torch.zeros((Bo, cap * 9), dtype=torch.int32).pin_memory().numpy().view(pkg.TAG_DTYPE).reshape(Bo, cap),
+                    torch.zeros(Bo, dtype=torch.int32).pin_memory().numpy(),
+                    torch.zeros(Bo, dtype=torch.int32).pin_memory().numpy().view(np.uint32))
 
         # streaming: a second set of output arrays, two calls in flight (the uploads of step i+1
         # overlap the board searches of step i); every step still uploads its frames and
@@ -584,8 +600,10 @@ def main():
         det.set_option("host_async", 1 if e2e_streaming else 0)
 
         def host_steps(k, src):
+            n_src = src.shape[0]
             for i in range(k):
-                det.detect_batch_into(src, *outs[i & 1])
+                o = outs[i & 1]
+                det.detect_batch_into(src, o[0][:n_src], o[1][:n_src], o[2][:n_src])
                 if e2e_streaming:
                     det.detect_batch_wait(1)
             if e2e_streaming:
@@ -598,9 +616,20 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dt_all = gather_list(dt, world, "cuda")
-        assert np.array_equal(outs[0][1], cnt_host), "host-path and device-path results differ"
-        assert args.steps < 2 or np.array_equal(outs[1][1], cnt_host), "host-path and device-path results differ"
-        assert args.steps < 2 or np.array_equal(outs[1][0], outs[0][0]), "streaming host calls disagree"
+        assert np.array_equal(outs[0][1][:B], cnt_host), "host-path and device-path results differ"
+        assert args.steps < 2 or np.array_equal(outs[1][1][:B], cnt_host), "host-path and device-path results differ"
+        assert args.steps < 2 or np.array_equal(outs[1][0][:B], outs[0][0][:B]), "streaming host calls disagree"
+        dt_bal_all = None
+        if balanced:  # the same steps with the shards sized by each rank's link rate
+            src_b = hf_all[:Be]
+            host_steps(2, src_b)
+            barrier()
+            t0 = time.perf_counter()
+            host_steps(args.steps, src_b)
+            torch.cuda.synchronize()
+            dt_bal_all = gather_list(time.perf_counter() - t0, world, "cuda")
+            nb = min(B, Be)
+            assert np.array_equal(outs[0][1][:nb], cnt_host[:nb]), "balanced host path and device path differ"
         # the same calls on PAGEABLE frames (a plain numpy array: what detect_batch(&[DynamicImage])
         # hands over after packing)
         pg = np.empty((B, H, W), np.uint8)
@@ -613,22 +642,34 @@ def main():
         torch.cuda.synchronize()
         dt_pg = time.perf_counter() - t0
         dt_pg_all = gather_list(dt_pg, world, "cuda")
-        assert np.array_equal(outs[0][1], cnt_host), "pageable host path and device path differ"
+        assert np.array_equal(outs[0][1][:B], cnt_host), "pageable host path and device path differ"
         det.set_option("host_async", 0)
-        h2d_all = gather_list(h2d_gbs, world, "cuda")
         ceil_rank = [g * 1e9 / (W * H) for g in h2d_all]
-        e2e = {"value": world * B * args.steps / max(dt_all), "unit": UNIT,
-               "h2d_bytes_per_step": int(world * B * W * H),
-               "d2h_bytes_per_step": int(world * B * (cap * 36 + 8)),
+        equal = {"value": world * B * args.steps / max(dt_all), "frames_per_rank_per_step": B,
+                 "per_rank": [B * args.steps / d for d in dt_all]}
+        if balanced:
+            total_frames = sum(shard_frames)
+            e2e_value = total_frames * args.steps / max(dt_bal_all)
+            per_rank = [n * args.steps / d for n, d in zip(shard_frames, dt_bal_all)]
+            sharding = ("%d frames per step in all, sharded in proportion to each rank's measured host-to-device "
+                        "rate: %s frames per rank" % (total_frames, shard_frames))
+        else:
+            total_frames = world * B
+            e2e_value, per_rank = equal["value"], equal["per_rank"]
+            sharding = "equal shards, %d frames per rank per step" % B
+        e2e = {"value": e2e_value, "unit": UNIT,
+               "h2d_bytes_per_step": int(total_frames * W * H),
+               "d2h_bytes_per_step": int(total_frames * (cap * 36 + 8)),
                "timing": "host wall clock around ag_detect_batch, pinned host frames, max over ranks",
                "calls": "streaming (host_async): 2 calls in flight, ag_detect_batch_wait" if e2e_streaming
                         else "synchronous",
-               "per_rank": [B * args.steps / d for d in dt_all],
+               "sharding": sharding, "equal_shards": equal,
+               "per_rank": per_rank,
                "h2d_ceiling_gbs_per_rank": h2d_all,
                "h2d_ceiling_note": "pinned cudaMemcpyAsync of 256 MB x 12, all ranks copying at the same time, "
                                    "in this run; frames/s ceiling = GB/s / 1.31 MB",
                "ceiling_frames_per_s": float(sum(ceil_rank)),
-               "frac_of_ceiling": world * B * args.steps / max(dt_all) / max(sum(ceil_rank), 1e-9),
+               "frac_of_ceiling": e2e_value / max(sum(ceil_rank), 1e-9),
                "pageable": {"value": world * B * pg_steps / max(dt_pg_all), "unit": UNIT, "steps": pg_steps,
                             "per_rank": [B * pg_steps / d for d in dt_pg_all],
                             "note": "same calls, frames in ordinary (pageable) host memory"},

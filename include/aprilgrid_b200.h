@@ -228,7 +228,9 @@ AG_API void ag_host_free(void* p);
  * detect_batch for a multi-GPU host: frames are independent (src/detector.rs:505-540), so the
  * batch is cut into contiguous frame ranges [g*B/G, (g+1)*B/G), one per device, each handled by
  * that device's own pipeline on its own host thread; every device writes its results into the
- * caller's arrays at its frames' positions (no collective on the data path).  devices = NULL or
+ * caller's arrays at its frames' positions (no collective on the data path).  The ranges are equal
+ * unless the devices' host-to-device rates (measured at creation, all devices copying at once)
+ * differ by more than 5 %: then they are proportional to those rates.  devices = NULL or
  * n_devices = 0: every visible device.  Same arguments, results and error behaviour as
  * ag_detect_batch (always synchronous); byte-identical to one device processing the batch.   */
 typedef struct ag_multi ag_multi;
