@@ -180,3 +180,13 @@ def test_labels_are_4_connected_components_in_raster_order(oracle):
     assert np.array_equal(canon, labels)
     ys, xs = np.nonzero(labels == 0)
     assert centers[0, 0] == np.float32(xs.sum()) / np.float32(len(xs))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_point_index_equals_linear_scan(oracle, mode):
+    """The oracle's nearest-neighbour index (a uniform bucket grid standing in for kdtree 0.8's
+    `nearest`, detector.rs:550, :592-595; board.rs:88, :192-216) returns exactly the linear scan's
+    (d2, index) lists: uniform, clustered-with-duplicates and collinear point sets, k = 1 / 3 / 50,
+    queries inside and outside the cloud and on the points themselves (exact ties)."""
+    for n, k in ((0, 3), (5, 3), (20, 50), (126, 3), (270, 50), (270, 3), (2300, 3), (2300, 50), (12000, 1)):
+        assert oracle.selftest_point_index(n, 1500, k, mode, 7 + n) == 0, (mode, n, k)
