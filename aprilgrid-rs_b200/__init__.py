@@ -92,6 +92,7 @@ def lib():
         L.ag_destroy.argtypes = [vp]
         L.ag_set_option.argtypes = [vp, C.c_char_p, C.c_long]
         L.ag_detect.argtypes = [vp, vp, ci, ci, sz, ci, vp, ci, vp]
+        L.ag_detect_planes.argtypes = [vp, vp, sz, vp, sz, ci, ci, vp, ci, vp]
         L.ag_detect_batch.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp, ci, vp, vp]
         L.ag_detect_batch_device.argtypes = [vp, vp, sz, ci, ci, ci, sz, ci, vp, ci, vp, vp, vp]
         L.ag_detect_batch_device_wait.argtypes = [vp, vp]
@@ -220,6 +221,18 @@ class TagDetector:
         out = np.zeros(cap, TAG_DTYPE)
         n = C.c_int(0)
         self._check(lib().ag_detect(self._h, _p(img), w, h, st, fmt, _p(out), cap, C.byref(n)))
+        return _tags_to_dict(out[:n.value])
+
+    def detect_planes(self, luma32f, luma8, cap=1024):
+        """detect on a frame given as its two gray planes: to_luma32f(img) (H x W float32) and to_luma8(img)
+        (H x W uint8) -- for DynamicImage variants whose conversion the caller does with `image` itself."""
+        f = np.ascontiguousarray(luma32f, np.float32)
+        g = np.ascontiguousarray(luma8, np.uint8)
+        if f.ndim != 2 or f.shape != g.shape:
+            raise ValueError("luma32f and luma8 must be H x W arrays of one shape")
+        out = np.zeros(cap, TAG_DTYPE)
+        n = C.c_int(0)
+        self._check(lib().ag_detect_planes(self._h, _p(f), 0, _p(g), 0, f.shape[1], f.shape[0], _p(out), cap, C.byref(n)))
         return _tags_to_dict(out[:n.value])
 
     def detect_kornia(self, img):

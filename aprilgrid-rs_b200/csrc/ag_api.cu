@@ -1224,6 +1224,89 @@ int ag_detect(ag_detector* det, const void* pixels, int width, int height, size_
   return rc;
 }
 
+// detect on a frame given as the two gray planes the reference derives from its DynamicImage:
+// luma32f = img.to_luma32f() (the stencil chain, detector.rs:409) and luma8 = img.to_luma8() (bit
+// sampling, :507).  One frame, synchronous, on the one-frame slot; capacities grow as in ag_detect.
+int ag_detect_planes(ag_detector* det, const float* luma32f, size_t f32_row_stride, const uint8_t* luma8,
+                     size_t u8_row_stride, int width, int height, ag_tag* out, int cap, int* n) {
+  if (!det) return AG_ERR_INVALID;
+  if (!luma32f || !luma8 || !out || !n || cap < 1 || width <= 0 || height <= 0)
+    return fail(det, AG_ERR_INVALID, "null pointer or bad size");
+  if ((long long)width * height > (1ll << 30)) return fail(det, AG_ERR_INVALID, "image too large");
+  if (f32_row_stride == 0) f32_row_stride = sizeof(float) * (size_t)width;
+  if (u8_row_stride == 0) u8_row_stride = (size_t)width;
+  if (f32_row_stride < sizeof(float) * (size_t)width || (f32_row_stride & 3) || u8_row_stride < (size_t)width)
+    return fail(det, AG_ERR_INVALID, "bad row stride");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  det->tap_valid = false;
+  const size_t px = (size_t)width * height;
+  FrameGeom gf;  // the f32 plane, packed
+  gf.w = width; gf.h = height; gf.wpr = (width + 31) / 32; gf.n_words = gf.wpr * height; gf.n_px = width * height;
+  gf.row_stride = sizeof(float) * (size_t)width;
+  gf.frame_stride = 5 * px;  // the u8 plane follows the f32 plane in the slot's input buffer
+  gf.format = kFmtF32;
+  FrameGeom g8 = gf;  // the u8 plane
+  g8.row_stride = (size_t)width;
+  g8.format = AG_L8;
+  set_caps(det, gf);
+  Slot& S = det->big;
+  const int save_cl = det->cur_clusters, save_sd = det->cur_saddles;
+  int rc = AG_OK, cnt = 0;
+  uint32_t st = 0;
+  for (;;) {
+    if (!(rc = ensure_slot(det, S, gf, 1, det->fam.n_codes, true))) {
+      cudaStream_t s = S.stream;
+      uint8_t* d_u8 = S.d_in + 4 * px;
+      if (cudaMemcpy2DAsync(S.d_in, gf.row_stride, luma32f, f32_row_stride, gf.row_stride, height, cudaMemcpyHostToDevice, s) !=
+              cudaSuccess ||
+          cudaMemcpy2DAsync(d_u8, g8.row_stride, luma8, u8_row_stride, g8.row_stride, height, cudaMemcpyHostToDevice, s) !=
+              cudaSuccess)
+        rc = AG_ERR_CUDA;
+      if (!rc) rc = run_dense(det, S, S.d_in, gf, 1, true, s);
+      if (!rc) rc = run_sparse(det, S, S.bb, gf, 1, S.d_status, s);
+      if (!rc && (cudaMemcpyAsync(S.h_status, S.d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                  cudaStreamSynchronize(s) != cudaSuccess))
+        rc = AG_ERR_CUDA;
+      if (!rc && !(S.h_status[0] & kGrowable)) {
+        rc = run_boards(det, S.bb, d_u8, g8, 1, S.d_tags, S.cap_tags, S.d_ntags, S.d_status, false, s);
+        if (!rc && (cudaMemcpyAsync(S.h_ntags, S.d_ntags, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                    cudaMemcpyAsync(S.h_status, S.d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                    cudaMemcpyAsync(S.h_tags, S.d_tags, sizeof(ag_tag) * (size_t)S.cap_tags, cudaMemcpyDeviceToHost, s) !=
+                        cudaSuccess ||
+                    cudaStreamSynchronize(s) != cudaSuccess))
+          rc = AG_ERR_CUDA;
+      } else if (!rc) {
+        S.h_ntags[0] = 0;
+      }
+    }
+    if (rc) break;
+    st = S.h_status[0];
+    cnt = S.h_ntags[0];
+    bool grew = false;
+    if ((st & AG_FRAME_CLUSTER_OVERFLOW) && det->cur_clusters < (1 << 22)) {
+      det->cur_clusters = (int)std::min<long>((long)det->cur_clusters * 16, 1l << 22);
+      grew = true;
+    }
+    if ((st & AG_FRAME_SADDLE_OVERFLOW) && det->cur_saddles < 16384) {
+      det->cur_saddles = 16384;
+      grew = true;
+    }
+    if (!grew) break;
+  }
+  det->cur_clusters = save_cl;
+  det->cur_saddles = save_sd;
+  if (rc) {
+    if (det->err.empty()) det->err = "ag_detect_planes failed";
+    return rc;
+  }
+  *n = cnt;
+  memcpy(out, S.h_tags, sizeof(ag_tag) * (size_t)std::min(std::min(cnt, cap), S.cap_tags));
+  if (st & (kGrowable | AG_FRAME_BOARD_OVERFLOW))
+    return fail(det, AG_ERR_CAPACITY, "frame exceeds the detector's limits (clusters > 2^22, saddles > 16384 or a board wider than the lattice)");
+  return cnt > cap ? fail(det, AG_ERR_CAPACITY, "cap too small") : AG_OK;
+}
+
 // ---- stage taps -----------------------------------------------------------------------------
 int ag_stage_run(ag_detector* det, const void* pixels, int width, int height, size_t row_stride,
                  int format) {

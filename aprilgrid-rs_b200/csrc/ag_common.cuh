@@ -20,6 +20,10 @@
 
 namespace ag {
 
+// Internal pixel format of ag_detect_planes: the frame's Luma<f32> plane (the caller ran
+// to_luma32f itself); not a value of the public format enum.
+constexpr int kFmtF32 = 3;
+
 constexpr int kBlurRadius = 3;  // ceil(2 * 1.5), src/image_util.rs:111
 constexpr int kBlurTaps = 7;
 

@@ -44,6 +44,8 @@ AG_D float load_luma(const uint8_t* __restrict__ frame, size_t row_stride, int x
     return unorm8_to_f32((float)row[x]);
   } else if (FMT == AG_L16) {
     return unorm16_to_f32((float)reinterpret_cast<const uint16_t*>(row)[x]);
+  } else if (FMT == kFmtF32) {
+    return reinterpret_cast<const float*>(row)[x];
   } else {
     const uint8_t* p = row + 3 * x;
     return unorm8_to_f32((float)rgb_luma_u8(p[0], p[1], p[2]));
@@ -505,7 +507,7 @@ int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames,
   ++launches;
   const size_t al = g.format == AG_L16 ? 8 : 4;  // alignment of a lane's load
   const bool can_stream = (g.w % 4) == 0 && g.w >= 8 && (g.row_stride % al) == 0 && (g.frame_stride % al) == 0 &&
-                          ((uintptr_t)frames % al) == 0 && variant != 1;
+                          ((uintptr_t)frames % al) == 0 && variant != 1 && g.format != kFmtF32;
   if (can_stream) {
     const int strips = (g.w + S_COLS - 1) / S_COLS;
     dim3 grid((strips + S_WARPS - 1) / S_WARPS, (g.h + S_ROWS - 1) / S_ROWS, n_frames);
@@ -527,6 +529,7 @@ int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames,
   switch (g.format) {
     case AG_L8: launch_tile<AG_L8>(frames, g, n_frames, blur, resp, frame_min, write_blur, s); break;
     case AG_L16: launch_tile<AG_L16>(frames, g, n_frames, blur, resp, frame_min, write_blur, s); break;
+    case kFmtF32: launch_tile<kFmtF32>(frames, g, n_frames, blur, resp, frame_min, write_blur, s); break;
     default: launch_tile<AG_RGB8>(frames, g, n_frames, blur, resp, frame_min, write_blur, s); break;
   }
   return launches + 1;

@@ -108,6 +108,9 @@ mod ffi {
         pub fn ag_last_error(det: *const AgDetector) -> *const c_char;
         pub fn ag_detect(det: *mut AgDetector, pixels: *const c_void, width: c_int, height: c_int, row_stride: usize,
                          format: c_int, out: *mut AgTag, cap: c_int, n: *mut c_int) -> c_int;
+        pub fn ag_detect_planes(det: *mut AgDetector, luma32f: *const f32, f32_row_stride: usize, luma8: *const u8,
+                                u8_row_stride: usize, width: c_int, height: c_int, out: *mut AgTag, cap: c_int,
+                                n: *mut c_int) -> c_int;
         pub fn ag_detect_batch(det: *mut AgDetector, frames: *const c_void, frame_stride: usize, n_frames: c_int,
                                width: c_int, height: c_int, row_stride: usize, format: c_int, out: *mut AgTag,
                                cap_per_frame: c_int, n_per_frame: *mut c_int, frame_status: *mut u32) -> c_int;
@@ -183,11 +186,12 @@ fn last_error(h: *const ffi::AgDetector) -> String {
 
 /// Raw pixel view of the DynamicImage variants the detect path is used with (Luma8, Luma16,
 /// Rgb8: passed through untouched, converted on the GPU exactly as `image` 0.25 does).
-/// DEVIATION for every other variant: it is first converted with `image`'s own `to_luma16()`
-/// (16-bit and float sources) or `to_rgb8()` (8-bit sources with alpha); the reference calls
-/// `to_luma32f()` / `to_luma8()` on the ORIGINAL (src/detector.rs:409, :507), which for e.g.
-/// Rgb16 computes the float luma from 16-bit channels in f32 -- the last bits of the gray image
-/// can differ there.
+/// `detect` handles every OTHER variant exactly as the reference does:
+/// they compute `img.to_luma32f()` and `img.to_luma8()` with the `image` crate itself
+/// (src/detector.rs:409, :507) and hand both planes to `ag_detect_planes`.  Only `detect_batch`
+/// (frames packed into one buffer of one format) converts such variants first -- with `image`'s own
+/// `to_luma16()` (16-bit and float sources) or `to_rgb8()` (8-bit sources with alpha) -- where for
+/// e.g. Rgb16 the last bits of the float gray image can differ from the reference's.
 enum Pixels<'a> {
     Borrowed(&'a [u8], c_int, usize),
     Owned(Vec<u8>, c_int, usize),
@@ -272,9 +276,35 @@ impl TagDetector {
     }
 
     pub fn detect(&self, img: &DynamicImage) -> HashMap<u32, [(f32, f32); 4]> {
-        let (px, w, h) = pixels_of(img);
-        let (bytes, fmt, stride) = px.parts();
-        self.detect_raw(bytes.as_ptr(), w, h, stride, fmt)
+        match img {
+            DynamicImage::ImageLuma8(_) | DynamicImage::ImageLuma16(_) | DynamicImage::ImageRgb8(_) => {
+                let (px, w, h) = pixels_of(img);
+                let (bytes, fmt, stride) = px.parts();
+                self.detect_raw(bytes.as_ptr(), w, h, stride, fmt)
+            }
+            other => self.detect_planes(other),
+        }
+    }
+
+    /// Any other variant: the reference's own conversions (`to_luma32f`, `to_luma8`), both planes to the GPU.
+    fn detect_planes(&self, img: &DynamicImage) -> HashMap<u32, [(f32, f32); 4]> {
+        let luma32f = img.to_luma32f();
+        let luma8 = img.to_luma8();
+        let (w, h) = (img.width(), img.height());
+        let mut out = vec![AgTag { id: 0, xy: [0.0; 8] }; TAG_CAP];
+        let mut n: c_int = 0;
+        let det = self.checkout();
+        let rc = unsafe {
+            ffi::ag_detect_planes(det, luma32f.as_raw().as_ptr(), 0, luma8.as_raw().as_ptr(), 0, w as c_int, h as c_int,
+                                  out.as_mut_ptr(), TAG_CAP as c_int, &mut n)
+        };
+        if rc != 0 {
+            let msg = last_error(det);
+            self.checkin(det);
+            panic!("aprilgrid_b200: ag_detect_planes failed ({rc}): {msg}");
+        }
+        self.checkin(det);
+        out[..n as usize].iter().map(|t| (t.id, corners(t))).collect()
     }
 
     fn detect_raw(&self, ptr: *const u8, w: u32, h: u32, stride: usize, fmt: c_int) -> HashMap<u32, [(f32, f32); 4]> {

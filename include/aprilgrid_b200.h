@@ -127,6 +127,16 @@ AG_API int ag_set_option(ag_detector* det, const char* key, long value);
 AG_API int ag_detect(ag_detector* det, const void* pixels, int width, int height,
                      size_t row_stride, int format, ag_tag* out, int cap, int* n);
 
+/* TagDetector::detect on a frame given as the TWO gray planes the reference derives from its
+ * DynamicImage itself: luma32f = img.to_luma32f() (the stencil chain, src/detector.rs:409) and
+ * luma8 = img.to_luma8() (bit sampling, :507).  For DynamicImage variants other than Luma8 / Luma16 /
+ * Rgb8 (Rgb16, Rgba8, Rgb32F ...) a shim computes both planes with the `image` crate and calls
+ * this: the conversion is then the reference's own, whatever the variant.  Row strides in bytes
+ * (0 = packed).  Synchronous; same result and error conventions as ag_detect.              */
+AG_API int ag_detect_planes(ag_detector* det, const float* luma32f, size_t f32_row_stride,
+                            const uint8_t* luma8, size_t u8_row_stride, int width, int height,
+                            ag_tag* out, int cap, int* n);
+
 /* detect_batch: n_frames host images of one shape at frames + i*frame_stride.
  * out[i*cap_per_frame ..], n_per_frame[i]; frame_status may be NULL.                     */
 AG_API int ag_detect_batch(ag_detector* det, const void* frames, size_t frame_stride,

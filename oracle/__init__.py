@@ -283,6 +283,20 @@ def detect(img, family="t36h11", min_angle=30.0, max_angle=60.0, max_boards=2, c
     return {int(t["id"]): t["xy"].reshape(4, 2).copy() for t in out[:n]}
 
 
+def detect_planes(luma32f, luma8, family="t36h11", min_angle=30.0, max_angle=60.0, max_boards=2, cap=1024):
+    """detect on a frame given as its two gray planes (to_luma32f / to_luma8 of the DynamicImage)."""
+    f = np.ascontiguousarray(luma32f, np.float32)
+    g = np.ascontiguousarray(luma8, np.uint8)
+    assert f.shape == g.shape and f.ndim == 2
+    h, w = f.shape
+    out = np.zeros(cap, TAG_DTYPE)
+    L = lib()
+    L.orc_detect_planes.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                    C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = L.orc_detect_planes(FAMILY[family], min_angle, max_angle, max_boards, _p(f), 0, _p(g), 0, w, h, _p(out), cap)
+    return {int(t["id"]): t["xy"].reshape(4, 2).copy() for t in out[:min(n, cap)]}
+
+
 def detect_batch(frames, family="t36h11", threads=1, cap=128, max_boards=2):
     """frames: N x H x W (u8/u16) or N x H x W x 3 (u8), C-contiguous.  Returns list of dicts."""
     frames = np.ascontiguousarray(frames)

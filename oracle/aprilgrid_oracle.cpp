@@ -105,6 +105,8 @@ void to_luma_f32(const void* pixels, int w, int h, size_t stride, int fmt, float
     } else if (fmt == 1) {
       const uint16_t* r16 = (const uint16_t*)row;
       for (int x = 0; x < w; ++x) o[x] = (float)r16[x] / 65535.0f;
+    } else if (fmt == 3) {  // already a Luma<f32> plane (the caller ran to_luma32f itself): detect_planes
+      memcpy(o, row, sizeof(float) * (size_t)w);
     } else {
       for (int x = 0; x < w; ++x) o[x] = (float)rgb_luma_u8(row + 3 * x) / 255.0f;
     }
@@ -984,12 +986,15 @@ bool try_decode_quad(const Family& fam, const uint8_t* grey, uint32_t w, uint32_
 // a-14  detect -- src/detector.rs:505-540.  The result map is returned in ascending id order.
 //       Quads of one board are visited in Board::all_tag_indexes order (see Board); a repeated
 //       id overwrites, as HashMap::insert does.
+// grey_plane: null = to_luma8 of `pixels` (detector.rs:507); else the Luma<u8> plane itself, `pixels`
+// then being the Luma<f32> plane (fmt 3): the frame as its two derived gray images (detect_planes).
 int detect(const Family& fam, const Params& prm, const void* pixels, int w, int h, size_t stride,
-           int fmt, TagOut* out, int cap) {
+           int fmt, TagOut* out, int cap, const uint8_t* grey_plane = nullptr, size_t grey_stride = 0) {
   std::vector<uint8_t> grey((size_t)w * h);
   {
     StageTimer tm(0);
-    to_luma_u8(pixels, w, h, stride, fmt, grey.data());
+    if (grey_plane) to_luma_u8(grey_plane, w, h, grey_stride ? grey_stride : (size_t)w, 0, grey.data());
+    else to_luma_u8(pixels, w, h, stride, fmt, grey.data());
   }
   ++g_stage_frames;
   FrontEnd fe;
@@ -1286,6 +1291,19 @@ int orc_detect(int family, float min_angle, float max_angle, int max_boards, con
   prm.max_saddle_angle = max_angle;
   prm.max_num_of_boards = max_boards;
   return detect(f, prm, px, w, h, stride, fmt, (TagOut*)tags_out, cap);
+}
+
+// detect on a frame given as its two gray planes: luma32f = to_luma32f(img), luma8 = to_luma8(img).
+int orc_detect_planes(int family, float min_angle, float max_angle, int max_boards, const float* luma32f,
+                      size_t f32_stride, const uint8_t* luma8, size_t u8_stride, int w, int h, void* tags_out, int cap) {
+  Family f;
+  if (!family_by_id(family, &f)) return -1;
+  Params prm;
+  prm.min_saddle_angle = min_angle;
+  prm.max_saddle_angle = max_angle;
+  prm.max_num_of_boards = max_boards;
+  return detect(f, prm, luma32f, w, h, f32_stride ? f32_stride : sizeof(float) * (size_t)w, 3, (TagOut*)tags_out, cap, luma8,
+                u8_stride);
 }
 
 // Frame-parallel batch for the CPU baseline: each frame runs the single-threaded detect()

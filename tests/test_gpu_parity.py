@@ -753,3 +753,24 @@ def test_board_search_on_gate_adversarial_saddles(detector, oracle):
             assert np.array_equal(got, want), name
             n_boards += 1
     assert n_boards >= 30
+
+
+def test_detect_planes_matches_oracle(detector, oracle):
+    """ag_detect_planes: the frame as its two derived gray planes (to_luma32f / to_luma8), for
+    DynamicImage variants whose conversion the caller does with `image` itself.  Planes that no
+    single L8 / L16 / RGB8 image would produce (float luma from a 16-bit source with its own
+    rounding, an independently rounded 8-bit plane): tags identical to the oracle on the same planes,
+    and identical to plain detect when the planes ARE an L8 image's own."""
+    img16 = synth.render_board_numpy(800, 600, seed=21, tag_px=52.0, dtype=np.uint16)
+    rng = np.random.default_rng(4)
+    jitter = rng.integers(-90, 91, img16.shape)
+    v = np.clip(img16.astype(np.int64) + jitter, 0, 65535)
+    luma32f = (v.astype(np.float64) * (0.2126 + 0.7152 + 0.0722) / 65535.0).astype(np.float32)
+    luma8 = ((v + 77) // 257).clip(0, 255).astype(np.uint8)
+    want = oracle.detect_planes(luma32f, luma8)
+    assert len(want) == 36
+    assert_tags_match(detector.detect_planes(luma32f, luma8), want)
+    img8 = synth.render_board_numpy(640, 480, seed=3, tag_px=44.0)
+    got = detector.detect_planes(oracle.to_luma_f32(img8), oracle.to_luma_u8(img8))
+    ref = detector.detect(img8)
+    assert sorted(got) == sorted(ref) and all(np.array_equal(got[k], ref[k]) for k in ref)
