@@ -164,7 +164,7 @@ struct ag_detector {
   // loop in ag_dense_batch_device (no board kernel beside it); 1 = always the generic tile kernel;
   // 2 / 3 = the streaming K1 with the six-step / the compact loop everywhere
   long dense_variant = 0;
-  bool dense_only_call = false;  // set by ag_dense_batch_device around its run_dense calls
+  long k1_chunk_rows = 0;  // 0 = automatic; else the rows per warp of the streaming K1 (6k + 4)
   long board_lattice = 64;  // side of the tag lattice a board may span (16 / 32 / 64)
   // warps per frame in the board kernel: 0 = automatic (1 when a launch has enough frames to
   // fill the GPU with one-warp blocks, 4 otherwise), or 1 / 2 / 4 / 8
@@ -175,6 +175,7 @@ struct ag_detector {
   bool label_list = true;  // K3 over a compact pixel list (0 = word-oriented version only)
   bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
   bool board_fast = true;  // four-lane group scoring of candidate boards (0 = general path only)
+  long board_priority = 0;  // priority of the board-search streams: 0 = least (= default streams), 1 = greatest
   bool board_split = true;  // batches: small frames (<= 320 saddles) searched by their own launch with the small tier
   bool board_grid = true;  // bucket-grid radius queries in the board kernel (0 = exhaustive scan)
   bool profile = false;
@@ -272,7 +273,8 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
     // front end of the following chunks (caller's stream, default priority) off the SMs
     int prio_least = 0, prio_greatest = 0;
     AG_CUDA(det, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-    AG_CUDA(det, cudaStreamCreateWithPriority(&B.bstream, cudaStreamNonBlocking, prio_least));
+    AG_CUDA(det, cudaStreamCreateWithPriority(&B.bstream, cudaStreamNonBlocking,
+                                              det->board_priority ? prio_greatest : prio_least));
     AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_front, cudaEventDisableTiming));
     AG_CUDA(det, cudaEventCreateWithFlags(&B.ev_boards, cudaEventDisableTiming));
   }
@@ -509,9 +511,9 @@ void prof_mark(ag_detector* det, int stage, cudaStream_t s) {
 int run_dense(ag_detector* det, Slot& S, const uint8_t* d_frames, const FrameGeom& g, int n,
               bool write_blur, cudaStream_t s) {
   prof_mark(det, -1, s);
-  const int dv = (int)det->dense_variant;
-  const int variant = dv == 0 ? (det->dense_only_call ? 2 : 0) : (dv == 3 ? 0 : dv);
-  det->launches += launch_blur_hessian(d_frames, g, n, S.d_blur, S.d_resp, S.d_min, write_blur, variant, s);
+  const int variant = det->dense_variant == 1 ? 1 : 0;
+  det->launches += launch_blur_hessian(d_frames, g, n, S.d_blur, S.d_resp, S.d_min, write_blur, variant,
+                                       (int)det->k1_chunk_rows, s);
   prof_mark(det, 0, s);
   det->launches += launch_threshold(S.d_resp, g, n, S.d_min, S.d_mask, s);
   prof_mark(det, 1, s);
@@ -896,6 +898,10 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     det->max_saddles = value;
   } else if (!strcmp(key, "dense_variant")) {
     det->dense_variant = value;
+  } else if (!strcmp(key, "k1_chunk_rows")) {
+    if (value != 0 && (value < 4 || value > 65536 || (value + 8) % 6 != 0))
+      return fail(det, AG_ERR_INVALID, "k1_chunk_rows must be 0 or 6k + 4");
+    det->k1_chunk_rows = value;
   } else if (!strcmp(key, "board_lattice")) {
     if (value != 16 && value != 32 && value != 64) return fail(det, AG_ERR_INVALID, "board_lattice must be 16, 32 or 64");
     det->board_lattice = value;
@@ -930,6 +936,8 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     det->board_timing = value != 0;
   } else if (!strcmp(key, "board_fast")) {
     det->board_fast = value != 0;
+  } else if (!strcmp(key, "board_priority")) {  // takes effect for board streams created afterwards
+    det->board_priority = value != 0;
   } else if (!strcmp(key, "board_split")) {
     det->board_split = value != 0;
   } else if (!strcmp(key, "board_grid")) {
@@ -1075,10 +1083,7 @@ int ag_dense_batch_device(ag_detector* det, const void* d_frames, size_t frame_s
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
     const int n = std::min(chunk, n_frames - f0);
     const uint8_t* in = (const uint8_t*)d_frames + (size_t)f0 * g.frame_stride;
-    det->dense_only_call = true;
-    rc = run_dense(det, S, in, g, n, true, s);
-    det->dense_only_call = false;
-    if (rc) return rc;
+    if ((rc = run_dense(det, S, in, g, n, true, s))) return rc;
   }
   // later calls on this handle (any stream) order themselves after this one through slot 0's event
   AG_CUDA(det, cudaEventRecord(S.done, s));

@@ -160,7 +160,11 @@ k_blur_hessian_tile(const uint8_t* __restrict__ frames, FrameGeom g, float* __re
 // (4 bytes for L8 and RGB8 -- a lane's 4 RGB pixels are three words --, 8 bytes for L16).
 // -----------------------------------------------------------------------------------------
 constexpr int S_COLS = 120;  // output columns per warp
-constexpr int S_ROWS = 128;  // output rows per warp (chunk)
+// Output rows per warp (chunk): the launcher picks one of these.  chunk + 8 row steps (7 rows of
+// blur halo + 1 of Hessian halo) is a whole number of six-step loop trips for each of them.
+// Taller chunks recompute less halo but leave a longer tail of half-empty SMs: measured on 1024
+// frames of 1280x1024, 124 rows 0.663 of the HBM peak, 250 rows 0.653, 508 rows 0.637, 58 rows 0.647.
+constexpr int kChunkRows[] = {124, 58};
 constexpr int S_WARPS = 4;   // warps per CTA (adjacent strips of one row chunk)
 
 AG_D float u8_lane(uint32_t word, int k) {  // byte k of a packed pixel word -> luma f32
@@ -203,34 +207,46 @@ struct BlurRow {  // one blurred row: v[1..4] = the lane's 4 columns, v[0] / v[5
   float v[6];
 };
 
-// UNROLL6: six row steps per loop trip instead of three (see the end of the kernel).
-template <int FMT, bool WRITE_BLUR, bool UNROLL6>
+template <int FMT, bool WRITE_BLUR>
 #ifndef AG_K1_MIN_BLOCKS
-#define AG_K1_MIN_BLOCKS 8
+#define AG_K1_MIN_BLOCKS 7
 #endif
 __global__ void __launch_bounds__(S_WARPS * 32, FMT == AG_L8 ? AG_K1_MIN_BLOCKS : 6)
-k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __restrict__ blur,
+k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, int chunk_rows, float* __restrict__ blur,
                       float* __restrict__ resp, uint32_t* __restrict__ frame_min) {
   const int lane = threadIdx.x & 31;
   const int strip = blockIdx.x * S_WARPS + (threadIdx.x >> 5);
   const int X0 = strip * S_COLS;
   if (X0 >= g.w) return;
   const int f = blockIdx.z;
-  const int Y0 = blockIdx.y * S_ROWS, Y1 = min(Y0 + S_ROWS, g.h);
+  const int Y0 = blockIdx.y * chunk_rows, Y1 = min(Y0 + chunk_rows, g.h);
   const int c0 = X0 - 4 + 4 * lane;  // first of this lane's 4 columns (may lie outside the image)
   const int cw = min(max(c0, 0), g.w - 4);  // column of the word actually loaded
   constexpr int kBpp = FMT == AG_L8 ? 1 : (FMT == AG_L16 ? 2 : 3);
+  // frame bases are block-uniform; what varies per lane and row are 32-bit offsets (the launcher
+  // checks that a frame's bytes fit them)
+  // The lane's pointers into the frame are held in registers (opaque, or the compiler re-derives
+  // them from blockIdx in every row step); a row then costs one 32x32->64 multiply-add per access.
   const uint8_t* src = frames + (size_t)f * g.frame_stride + (size_t)cw * kBpp;
+  asm volatile("" : "+l"(src));
+  const uint32_t rs = (uint32_t)g.row_stride;
   const bool left_out = c0 < 0, right_out = c0 >= g.w;
-  const bool writer = lane >= 1 && lane <= 30 && !right_out;
+  // strips at the left / right image border: replicated pixels, zeroed border columns
+  const bool edge_strip = X0 == 0 || X0 + S_COLS + 4 >= g.w;  // warp-uniform
   const bool zero_first = c0 == 0, zero_last = c0 + 3 == g.w - 1;  // image border columns
   const float k0 = c_taps[0], k1 = c_taps[1], k2 = c_taps[2], k3 = c_taps[3];
   const int h1 = g.h - 1;
-  const size_t rs = g.row_stride;
+  // one register each for what every row step tests (kept opaque so that they are not recomputed
+  // from the thread index in every step)
+  int writer = (lane >= 1 && lane <= 30 && !right_out) ? 1 : 0;
+  asm volatile("" : "+r"(writer));
+  const int row_lo = max(Y0, 1);                         // first row with a non-zero response
+  const uint32_t emit_span = (uint32_t)(Y1 - Y0);        // rows this chunk writes
+  const uint32_t calc_span = (uint32_t)max(min(Y1, h1) - row_lo, 0);  // ... and computes
 
   auto load_row = [&](int r) -> RawPx<FMT> {
-    const int rr = min(max(r, 0), h1);
-    return load_raw<FMT>(src + (size_t)rr * rs);
+    const uint32_t rr = (uint32_t)min(max(r, 0), h1);
+    return load_raw<FMT>(src + (uint64_t)rr * rs);
   };
 
   // vertical partial sums: aj[c] = what output row (r + 3 - j) has accumulated so far
@@ -241,8 +257,11 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
 #pragma unroll
   for (int c = 0; c < 6; ++c) R0.v[c] = R1.v[c] = R2.v[c] = 0.0f;
   float mn = 3.40282347e+38f;
-  float* resp_f = resp + (size_t)f * g.n_px + c0;
-  float* blur_f = blur + (size_t)f * g.n_px + c0;
+  char* resp_l = reinterpret_cast<char*>(resp + ((size_t)f * g.n_px + c0));  // row 0, the lane's columns
+  char* blur_l = reinterpret_cast<char*>(blur + ((size_t)f * g.n_px + c0));
+  asm volatile("" : "+l"(resp_l));
+  if (WRITE_BLUR) asm volatile("" : "+l"(blur_l));
+  const uint32_t out_row_bytes = (uint32_t)g.w * 4u;
 
   const int r_begin = Y0 - 4, r_end = Y1 + 3;  // temp rows r_begin..r_end inclusive
   RawPx<FMT> w_cur = load_row(r_begin), w_n1 = load_row(r_begin + 1), w_n2 = load_row(r_begin + 2);
@@ -254,7 +273,7 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
     w_cur = w_n1;
     w_n1 = w_n2;
     w_n2 = load_row(r + 3);  // three rows ahead
-    if (FMT == AG_L8) {
+    if (FMT == AG_L8 && edge_strip) {
       if (left_out) wd.w[0] = (wd.w[0] & 0xffu) * 0x01010101u;  // replicate pixel 0
       if (right_out) wd.w[0] = (wd.w[0] >> 24) * 0x01010101u;   // replicate pixel w-1
     }
@@ -262,7 +281,7 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
     float p[10];
     p[3] = raw_luma<FMT>(wd, 0); p[4] = raw_luma<FMT>(wd, 1); p[5] = raw_luma<FMT>(wd, 2);
     p[6] = raw_luma<FMT>(wd, 3);
-    if (FMT != AG_L8) {  // strips hanging over the image edge replicate the edge pixel
+    if (FMT != AG_L8 && edge_strip) {  // strips hanging over the image edge replicate the edge pixel
       if (left_out) p[4] = p[5] = p[6] = p[3];
       if (right_out) p[3] = p[4] = p[5] = p[6];
     }
@@ -298,9 +317,9 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
     N.v[5] = __shfl_down_sync(0xffffffffu, N.v[1], 1);
     // ---- Hessian of row yh = r - 4 (image_util.rs:83-106)
     const int yh = r - 4;
-    if (yh >= Y0) {  // warp-uniform
+    if ((uint32_t)(yh - Y0) < emit_span) {  // warp-uniform: Y0 <= yh < Y1
       float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      if (yh >= 1 && yh < h1) {  // warp-uniform; border rows stay 0
+      if ((uint32_t)(yh - row_lo) < calc_span) {  // warp-uniform; border rows stay 0
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float t2 = __fmul_rn(C.v[c + 1], 2.0f);
@@ -310,40 +329,34 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, float* __
               __fmul_rn(__fsub_rn(__fadd_rn(__fsub_rn(M.v[c + 2], M.v[c]), N.v[c]), N.v[c + 2]), 0.25f);
           o[c] = __fsub_rn(__fmul_rn(lxx, lyy), __fmul_rn(lxy, lxy));
         }
-        if (zero_first) o[0] = 0.0f;
-        if (zero_last) o[3] = 0.0f;
+        if (edge_strip) {
+          if (zero_first) o[0] = 0.0f;
+          if (zero_last) o[3] = 0.0f;
+        }
       }
       if (writer) {
-        const size_t off = (size_t)yh * g.w;
-        __stcs(reinterpret_cast<float4*>(resp_f + off), make_float4(o[0], o[1], o[2], o[3]));
+        const uint64_t off = (uint64_t)(uint32_t)yh * out_row_bytes;
+        __stcs(reinterpret_cast<float4*>(resp_l + off), make_float4(o[0], o[1], o[2], o[3]));
         if (WRITE_BLUR)
-          __stcs(reinterpret_cast<float4*>(blur_f + off), make_float4(C.v[1], C.v[2], C.v[3], C.v[4]));
+          __stcs(reinterpret_cast<float4*>(blur_l + off), make_float4(C.v[1], C.v[2], C.v[3], C.v[4]));
         mn = fminf(fminf(mn, fminf(o[0], o[1])), fminf(o[2], o[3]));
       }
     }
   };
 
-  // The three blurred rows rotate roles (period 3), so three steps per trip need no copies for them;
-  // the six partial sums of a column move up one position per row (period 6), so only six
-  // unconditional steps per trip leave EVERY value in the register it started in.  UNROLL6 does
-  // that (K1 alone: 0.56 -> 0.66 of the measured HBM peak, 11 % fewer instructions), at 2.6 times
-  // the code; inside the detect pipeline the compact loop is used, because there the larger loop
-  // body costs the co-resident board kernel more than K1 gains (96.4 k -> 90.3 k frames/s).
-  int r = r_begin;
-  if (UNROLL6) {
-    for (; r + 5 <= r_end; r += 6) {
-      step(r, R0, R1, R2);
-      step(r + 1, R1, R2, R0);
-      step(r + 2, R2, R0, R1);
-      step(r + 3, R0, R1, R2);
-      step(r + 4, R1, R2, R0);
-      step(r + 5, R2, R0, R1);
-    }
-  }
-  for (; r <= r_end; r += 3) {
+  // The three blurred rows rotate roles with period 3 and the six partial sums of a column move up
+  // one position per row (period 6), so six unconditional steps per trip leave EVERY value in the
+  // register it started in: no register copies, no per-step loop tests.  Against a three-step loop
+  // with a conditional tail that is 11 % fewer instructions (K1 alone: 0.56 -> 0.66 of the measured
+  // HBM peak).  The chunk heights make chunk + 8 a multiple of six; in the last chunk of a frame the
+  // steps past r_end load clamped rows and emit nothing (yh >= Y1).
+  for (int r = r_begin; r <= r_end; r += 6) {
     step(r, R0, R1, R2);
-    if (r + 1 <= r_end) step(r + 1, R1, R2, R0);
-    if (r + 2 <= r_end) step(r + 2, R2, R0, R1);
+    step(r + 1, R1, R2, R0);
+    step(r + 2, R2, R0, R1);
+    step(r + 3, R0, R1, R2);
+    step(r + 4, R1, R2, R0);
+    step(r + 5, R2, R0, R1);
   }
   mn = warp_min(mn);
   if (lane == 0) atomicMin(&frame_min[f], float_to_ordered(mn));
@@ -501,23 +514,32 @@ static void launch_tile(const uint8_t* frames, const FrameGeom& g, int n_frames,
 
 int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames, float* blur,
                         float* resp, uint32_t* frame_min, bool write_blur, int variant,
-                        cudaStream_t s) {
+                        int chunk_rows_opt, cudaStream_t s) {
   int launches = 0;
   k_fill_u32<<<(n_frames + 255) / 256, 256, 0, s>>>(frame_min, n_frames, kOrderedFltMax);
   ++launches;
   const size_t al = g.format == AG_L16 ? 8 : 4;  // alignment of a lane's load
   const bool can_stream = (g.w % 4) == 0 && g.w >= 8 && (g.row_stride % al) == 0 && (g.frame_stride % al) == 0 &&
-                          ((uintptr_t)frames % al) == 0 && variant != 1 && g.format != kFmtF32;
+                          ((uintptr_t)frames % al) == 0 && variant != 1 && g.format != kFmtF32 &&
+                          (uint64_t)g.row_stride * (uint64_t)g.h < (1ull << 32);  // 32-bit offsets within a frame
   if (can_stream) {
     const int strips = (g.w + S_COLS - 1) / S_COLS;
-    dim3 grid((strips + S_WARPS - 1) / S_WARPS, (g.h + S_ROWS - 1) / S_ROWS, n_frames);
+    const int bx = (strips + S_WARPS - 1) / S_WARPS;
+    // the taller chunk when it still gives every SM a few waves of blocks
+    int chunk_rows = kChunkRows[1];
+    if (chunk_rows_opt > 0 && (chunk_rows_opt + 8) % 6 == 0) {
+      chunk_rows = chunk_rows_opt;  // option "k1_chunk_rows" (tests, experiments)
+    } else {
+      for (int c : kChunkRows) {
+        const long blocks = (long)bx * ((g.h + c - 1) / c) * n_frames;
+        if (blocks >= 148L * 7 * 4) { chunk_rows = c; break; }
+      }
+    }
+    dim3 grid(bx, (g.h + chunk_rows - 1) / chunk_rows, n_frames);
     const dim3 block(S_WARPS * 32);
-    const bool u6 = variant == 2;  // the long loop body: for K1 running without the board kernel beside it
 #define AG_STREAM(FMT)                                                                                          \
-    if (write_blur && u6) k_blur_hessian_stream<FMT, true, true><<<grid, block, 0, s>>>(frames, g, blur, resp, frame_min); \
-    else if (write_blur) k_blur_hessian_stream<FMT, true, false><<<grid, block, 0, s>>>(frames, g, blur, resp, frame_min); \
-    else if (u6) k_blur_hessian_stream<FMT, false, true><<<grid, block, 0, s>>>(frames, g, blur, resp, frame_min);         \
-    else k_blur_hessian_stream<FMT, false, false><<<grid, block, 0, s>>>(frames, g, blur, resp, frame_min)
+    if (write_blur) k_blur_hessian_stream<FMT, true><<<grid, block, 0, s>>>(frames, g, chunk_rows, blur, resp, frame_min); \
+    else k_blur_hessian_stream<FMT, false><<<grid, block, 0, s>>>(frames, g, chunk_rows, blur, resp, frame_min)
     switch (g.format) {
       case AG_L8: AG_STREAM(AG_L8); break;
       case AG_L16: AG_STREAM(AG_L16); break;

@@ -29,7 +29,7 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
 // ag_dense.cu
 int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames, float* blur,
                         float* resp, uint32_t* frame_min, bool write_blur, int variant,
-                        cudaStream_t s);
+                        int chunk_rows_opt, cudaStream_t s);
 int launch_threshold(const float* resp, const FrameGeom& g, int n_frames, const uint32_t* frame_min,
                      uint32_t* mask, cudaStream_t s);
 int launch_blur_f32(const float* in, float* tmp, float* out, int w, int h, const float* d_taps,

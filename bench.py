@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short dense4k / rig runs of the default line")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
-                    help="extra ag_set_option settings (experiments), e.g. --opt dense_variant=2")
+                    help="extra ag_set_option settings (experiments), e.g. --opt k1_chunk_rows=124")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -530,11 +530,9 @@ def main():
         torch.cuda.synchronize()
         det.stage_times(reset=True)
         det.set_option("profile", 1)
-        det.set_option("dense_variant", 3)  # the same K1 instantiation the detect pipeline launches
         for _ in range(3):
             det.dense_batch_device(frames.data_ptr(), B, W, H, pkg.FMT_L8, stream=sp)
         torch.cuda.synchronize()
-        det.set_option("dense_variant", 0)
         det.set_option("profile", 0)
         st_alone = det.stage_times(reset=True)
         k1_alone_ms = st_alone["blur_hessian_min"][0] / max(st_alone["blur_hessian_min"][1], 1)

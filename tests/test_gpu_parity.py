@@ -150,22 +150,28 @@ def test_streaming_dense_kernel_formats(detector, oracle, fmt, shape):
     assert g["min"] == g2["min"]
 
 
+@pytest.mark.parametrize("rows", [4, 58, 124, 250, 508])
 @pytest.mark.parametrize("shape", [(5, 8), (17, 120), (130, 244), (300, 364), (1024, 1280)])
-def test_streaming_dense_kernel_six_step_loop(detector, oracle, shape):
-    """The K1 instantiation with six row steps per trip (what ag_dense_batch_device launches) gives the
-    same bits as the compact loop of the detect pipeline, for row counts with every remainder."""
+def test_streaming_dense_kernel_chunk_heights(detector, oracle, shape, rows):
+    """The streaming K1 marches down chunks of 6k + 4 rows (the launcher picks the height from the
+    batch size); every height gives the bits of the generic tile kernel, for row counts with every
+    remainder and chunks shorter than one loop trip."""
     rng = np.random.default_rng(shape[0] + 3 * shape[1])
     img = rng.integers(0, 256, shape, dtype=np.uint8)
-    g = detector.stages(img)
-    detector.set_option("dense_variant", 2)
+    detector.set_option("dense_variant", 1)
+    try:
+        g = detector.stages(img)
+    finally:
+        detector.set_option("dense_variant", 0)
+    detector.set_option("k1_chunk_rows", rows)
     try:
         g2 = detector.stages(img)
     finally:
-        detector.set_option("dense_variant", 0)
+        detector.set_option("k1_chunk_rows", 0)
     assert np.array_equal(g["blur"].view(np.uint32), g2["blur"].view(np.uint32))
     assert np.array_equal(g["resp"].view(np.uint32), g2["resp"].view(np.uint32))
     assert g["min"] == g2["min"] and np.array_equal(g["mask"], g2["mask"])
-    if shape[0] <= 300:
+    if shape[0] <= 300 and rows == 58:
         o = oracle.front_end(img, want_labels=False)
         assert np.array_equal(g2["blur"].view(np.uint32), o["blur"].view(np.uint32))
 
