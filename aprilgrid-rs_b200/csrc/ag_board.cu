@@ -107,7 +107,14 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   return L;
 }
 
-__global__ void __launch_bounds__(kMaxBoardWarps * 32, 3)
+// Register cap: the 320-saddle tier runs seven 2-warp blocks per SM, so registers are not what
+// limits K6's residency -- what they decide is how many K1 blocks (72 registers x 128 threads) fit
+// beside them.  Measured in the detect pipeline: 80 registers 101.1 k frames/s, 88 103.6 k,
+// 96 104.0 k, 104 102.0 k, 112 102.3 k, 128 99.8 k (alone K6 keeps getting faster: fewer spills).
+#ifndef AG_K6_MAXNREG
+#define AG_K6_MAXNREG 96
+#endif
+__global__ void __maxnreg__(AG_K6_MAXNREG)
 k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
                 const ag_saddle* __restrict__ refined, const int* __restrict__ n_refined,
                 uint8_t* __restrict__ ws, BoardWsLayout L, const uint64_t* __restrict__ codes,
