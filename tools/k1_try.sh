@@ -1,4 +1,4 @@
-for v in k6r88 k6r96 k6r104 "" k6r96; do
+for v in "" ldcs "" ldcs; do
   if [ -n "$v" ]; then export AG_LIB=aprilgrid-rs_b200/lib/variants/libag_$v.so; else unset AG_LIB; fi
   echo "== variant '$v'"
   python bench.py --no-cpu --no-e2e --no-extras --steps 80 2>/dev/null | python -c "

@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """Join an ncu source-page CSV (SASS view) with nvdisasm line info: instructions executed and
 stall samples per device function and per source line.
-usage: tools/ncu_lines.py <report.ncu-rep> <kernel-regex> <cubin-object-name e.g. ag_board> [top_n]"""
+usage: tools/ncu_lines.py <report.ncu-rep> <kernel-regex> <cubin-object-name e.g. ag_board> [top_n]
+env NCU_LINES_STALL=long_sb (or any stall_* suffix): also list the instructions with the most samples
+of that stall reason (the instruction WAITING, with its source line)."""
 import csv
 import os
 import re
@@ -54,6 +56,7 @@ for ln in sass.splitlines():
 by_func, by_line = defaultdict(lambda: [0, 0, 0, 0]), defaultdict(lambda: [0, 0, 0, 0])
 tot = [0, 0, 0, 0]
 stall_tot = defaultdict(int)
+per_inst = []
 for r in data:
     off = int(r[iA], 16) - base
     f, l = mp.get(off, ("?", ("?", 0)))
@@ -65,6 +68,11 @@ for r in data:
             agg[k] += v[k]
     for i, h in stall_cols:
         stall_tot[h] += int(r[i] or 0)
+    if os.environ.get("NCU_LINES_STALL"):
+        want = "stall_" + os.environ["NCU_LINES_STALL"]
+        for i, h in stall_cols:
+            if h == want and int(r[i] or 0):
+                per_inst.append((int(r[i]), f, l, r[iSrc].strip(), int(r[iI] or 0)))
 def demangle(n):
     try:
         return subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip().split("(")[0]
@@ -84,3 +92,15 @@ for (f, l), v in sorted(by_line.items(), key=lambda x: -x[1][1])[:topn]:
     print("  %-24s %s:%-5d inst %5.2f%%  nonbar-samples %5.2f%%  thr/inst %.1f" %
           (demangle(f)[-24:], l[0], l[1], 100.0 * v[1] / tot[1], 100.0 * (v[0] - v[3]) / max(tot[0] - tot[3], 1),
            v[2] / max(v[1], 1)))
+if per_inst:
+    want = os.environ["NCU_LINES_STALL"]
+    n_all = sum(p[0] for p in per_inst)
+    print("\ninstructions waiting with stall_%s (%d samples = %.1f%% of all):" % (want, n_all, 100.0 * n_all / tot[0]))
+    by_l = defaultdict(int)
+    for c, f, l, src, ex in per_inst:
+        by_l[(f, l)] += c
+    for (f, l), c in sorted(by_l.items(), key=lambda x: -x[1])[:topn]:
+        print("  %-24s %s:%-5d %5.1f%% of that stall" % (demangle(f)[-24:], l[0], l[1], 100.0 * c / n_all))
+    print("  -- by instruction:")
+    for c, f, l, src, ex in sorted(per_inst, key=lambda x: -x[0])[:topn]:
+        print("  %5.1f%%  %s:%-5d exec %-8d %s" % (100.0 * c / n_all, l[0], l[1], ex, src[:80]))
