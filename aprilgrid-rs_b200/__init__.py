@@ -101,6 +101,7 @@ def lib():
         L.ag_refined_saddle_points.argtypes = [vp, vp, ci, ci, sz, ci, vp, ci, vp]
         L.ag_gaussian_blur_f32.argtypes = [vp, vp, ci, ci, C.c_float, vp]
         L.ag_hessian_response.argtypes = [vp, vp, ci, ci, vp]
+        L.ag_gaussian_blur_f32_device.argtypes = [vp, vp, ci, ci, ci, C.c_float, vp, vp]
         L.ag_stage_run.argtypes = [vp, vp, ci, ci, sz, ci]
         for n in ("ag_stage_blur", "ag_stage_response", "ag_stage_threshold", "ag_stage_mask",
                   "ag_stage_labels"):
@@ -306,6 +307,12 @@ class TagDetector:
         out = np.empty_like(a)
         self._check(lib().ag_gaussian_blur_f32(self._h, _p(a), a.shape[1], a.shape[0], sigma, _p(out)))
         return out
+
+    def gaussian_blur_f32_device(self, d_in_ptr, n_frames, width, height, sigma, d_out_ptr, stream=None):
+        """gaussian_blur_f32 on n_frames contiguous device-resident f32 images (enqueued on `stream`)."""
+        return self._check(lib().ag_gaussian_blur_f32_device(
+            self._h, C.c_void_p(d_in_ptr), n_frames, width, height, sigma, C.c_void_p(d_out_ptr),
+            C.c_void_p(stream) if stream else None))
 
     def hessian_response(self, img):
         """image_util::hessian_response (image_util.rs:72-109)."""

@@ -1508,26 +1508,31 @@ static int ensure_f32(ag_detector* det, size_t n) {
   return AG_OK;
 }
 
+// taps exactly as src/image_util.rs:111-124 computes them at run time (platform expf)
+static bool blur_taps_host(float sigma, std::vector<float>& taps, int& radius) {
+  radius = (int)ceilf(sigma * 2.0f);
+  if (!(sigma > 0.0f) || radius < 0 || radius > 100) return false;
+  taps.assign(2 * radius + 1, 0.0f);
+  volatile float two_sigma_sq = 2.0f * sigma * sigma;
+  volatile float sum = 0.0f;
+  for (int i = 0; i <= 2 * radius; ++i) {
+    float x = (float)(i - radius);
+    volatile float xx = x * x;
+    float v = expf(-xx / two_sigma_sq);
+    taps[i] = v;
+    sum = sum + v;
+  }
+  for (auto& v : taps) v = v / sum;
+  return true;
+}
+
 int ag_gaussian_blur_f32(ag_detector* det, const float* img, int width, int height, float sigma,
                          float* out) {
   if (!det) return AG_ERR_INVALID;
   if (!img || !out || width <= 0 || height <= 0) return fail(det, AG_ERR_INVALID, "bad argument");
-  // taps exactly as src/image_util.rs:111-124 computes them at run time (platform expf)
-  int radius = (int)ceilf(sigma * 2.0f);
-  if (radius < 0 || radius > 100) return fail(det, AG_ERR_INVALID, "sigma out of range");
-  std::vector<float> taps(2 * radius + 1);
-  {
-    volatile float two_sigma_sq = 2.0f * sigma * sigma;
-    volatile float sum = 0.0f;
-    for (int i = 0; i <= 2 * radius; ++i) {
-      float x = (float)(i - radius);
-      volatile float xx = x * x;
-      float v = expf(-xx / two_sigma_sq);
-      taps[i] = v;
-      sum = sum + v;
-    }
-    for (auto& v : taps) v = v / sum;
-  }
+  int radius = 0;
+  std::vector<float> taps;
+  if (!blur_taps_host(sigma, taps, radius)) return fail(det, AG_ERR_INVALID, "sigma out of range");
   std::lock_guard<std::mutex> lk(det->mu);
   AG_CUDA(det, cudaSetDevice(det->device));
   { int qrc = quiesce_device_path(det); if (qrc) return qrc; }
@@ -1542,11 +1547,34 @@ int ag_gaussian_blur_f32(ag_detector* det, const float* img, int width, int heig
   AG_CUDA(det, cudaMemcpyAsync(det->d_taps, taps.data(), sizeof(float) * taps.size(),
                                cudaMemcpyHostToDevice, S.stream));
   AG_CUDA(det, cudaMemcpyAsync(det->d_f32_a, img, sizeof(float) * n, cudaMemcpyHostToDevice, S.stream));
-  det->launches += launch_blur_f32(det->d_f32_a, det->d_f32_b, det->d_f32_c, width, height, det->d_taps,
-                                   radius, S.stream);
+  det->launches += launch_blur_f32(det->d_f32_a, det->d_f32_b, det->d_f32_c, width, height, 1, taps.data(),
+                                   det->d_taps, radius, S.stream);
   AG_CUDA(det, cudaGetLastError());
   AG_CUDA(det, cudaMemcpyAsync(out, det->d_f32_c, sizeof(float) * n, cudaMemcpyDeviceToHost, S.stream));
   AG_CUDA(det, cudaStreamSynchronize(S.stream));
+  return AG_OK;
+}
+
+int ag_gaussian_blur_f32_device(ag_detector* det, const float* d_in, int n_frames, int width, int height,
+                                float sigma, float* d_out, void* stream) {
+  if (!det) return AG_ERR_INVALID;
+  if (n_frames < 0 || width <= 0 || height <= 0 || (n_frames > 0 && (!d_in || !d_out || d_in == d_out)))
+    return fail(det, AG_ERR_INVALID, "bad argument");
+  int radius = 0;
+  std::vector<float> taps;
+  if (!blur_taps_host(sigma, taps, radius)) return fail(det, AG_ERR_INVALID, "sigma out of range");
+  std::lock_guard<std::mutex> lk(det->mu);
+  AG_CUDA(det, cudaSetDevice(det->device));
+  if (n_frames == 0) return AG_OK;
+  const size_t n = (size_t)width * height;
+  int rc = ensure_f32(det, n);  // scratch image + tap buffer of the general path
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  // the tap upload is synchronous with respect to the host (pageable source), ordered on s
+  AG_CUDA(det, cudaMemcpyAsync(det->d_taps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice, s));
+  det->launches += launch_blur_f32(d_in, det->d_f32_b, d_out, width, height, n_frames, taps.data(), det->d_taps,
+                                   radius, s);
+  AG_CUDA(det, cudaGetLastError());
   return AG_OK;
 }
 

@@ -467,6 +467,97 @@ k_blur_f32_v(const float* __restrict__ tmp, float* __restrict__ out, int w, int 
   }
   out[(size_t)y * w + x] = val;
 }
+// gaussian_blur_f32 for radius 3 (1 < sigma <= 1.5: the detector's own sigma and bench_blur.rs's),
+// width % 4 == 0: the streaming structure of K1 without the gray conversion and the Hessian -- one
+// warp per 120-column strip, 4 columns per lane (one 16-byte load per lane-row, prefetched three
+// rows ahead), halo pixels by shuffle, six running partial sums per column, a loop of six
+// unconditional row steps.  8 B/px of traffic (4 in + 4 out), no intermediate image.
+// The accumulations start from 0.0 explicitly: 0.0 + (-0.0) is +0.0 (image_util.rs:138-203
+// accumulates into a zero-initialised value), which matters for inputs that are not >= 0.
+__global__ void __launch_bounds__(S_WARPS * 32, 6)
+k_blur_f32_stream(const float* __restrict__ in, float* __restrict__ out, int w, int h, int chunk_rows,
+                  float k0, float k1, float k2, float k3) {
+  const int lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * S_WARPS + (threadIdx.x >> 5);
+  const int X0 = strip * S_COLS;
+  if (X0 >= w) return;
+  const int f = blockIdx.z;
+  const int Y0 = blockIdx.y * chunk_rows, Y1 = min(Y0 + chunk_rows, h);
+  const int c0 = X0 - 4 + 4 * lane;
+  const int cw = min(max(c0, 0), w - 4);
+  const size_t n_px = (size_t)w * h;
+  const char* src = reinterpret_cast<const char*>(in + (f * n_px + cw));
+  char* dst = reinterpret_cast<char*>(out + f * n_px) + (ptrdiff_t)c0 * 4;
+  asm volatile("" : "+l"(src));
+  asm volatile("" : "+l"(dst));
+  const uint32_t row_bytes = (uint32_t)w * 4u;
+  const bool left_out = c0 < 0, right_out = c0 >= w;
+  const bool edge_strip = X0 == 0 || X0 + S_COLS + 4 >= w;  // warp-uniform
+  int writer = (lane >= 1 && lane <= 30 && !right_out) ? 1 : 0;
+  asm volatile("" : "+r"(writer));
+  const int h1 = h - 1;
+  const uint32_t emit_span = (uint32_t)(Y1 - Y0);
+  auto load_row = [&](int r) -> float4 {
+    const uint32_t rr = (uint32_t)min(max(r, 0), h1);
+    return __ldg(reinterpret_cast<const float4*>(src + (uint64_t)rr * row_bytes));
+  };
+  float a1[4], a2[4], a3[4], a4[4], a5[4], a6[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) a1[c] = a2[c] = a3[c] = a4[c] = a5[c] = a6[c] = 0.0f;
+  const int r_begin = Y0 - 3, r_end = Y1 + 2;  // input rows of this chunk's output rows
+  float4 w_cur = load_row(r_begin), w_n1 = load_row(r_begin + 1), w_n2 = load_row(r_begin + 2);
+  // consumes input row r, completes output row r - 3
+  auto step = [&](int r) {
+    const float4 wd = w_cur;
+    w_cur = w_n1;
+    w_n1 = w_n2;
+    w_n2 = load_row(r + 3);
+    float p[10];
+    p[3] = wd.x; p[4] = wd.y; p[5] = wd.z; p[6] = wd.w;
+    if (edge_strip) {  // lanes hanging over the image edge replicate the edge pixel
+      if (left_out) p[4] = p[5] = p[6] = p[3];
+      if (right_out) p[3] = p[4] = p[5] = p[6];
+    }
+    p[0] = __shfl_up_sync(0xffffffffu, p[4], 1);
+    p[1] = __shfl_up_sync(0xffffffffu, p[5], 1);
+    p[2] = __shfl_up_sync(0xffffffffu, p[6], 1);
+    p[7] = __shfl_down_sync(0xffffffffu, p[3], 1);
+    p[8] = __shfl_down_sync(0xffffffffu, p[4], 1);
+    p[9] = __shfl_down_sync(0xffffffffu, p[5], 1);
+    float o[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float t = __fadd_rn(0.0f, __fmul_rn(p[c], k0));
+      t = __fadd_rn(t, __fmul_rn(p[c + 1], k1));
+      t = __fadd_rn(t, __fmul_rn(p[c + 2], k2));
+      t = __fadd_rn(t, __fmul_rn(p[c + 3], k3));
+      t = __fadd_rn(t, __fmul_rn(p[c + 4], k2));
+      t = __fadd_rn(t, __fmul_rn(p[c + 5], k1));
+      t = __fadd_rn(t, __fmul_rn(p[c + 6], k0));
+      const float q0 = __fmul_rn(t, k0), q1 = __fmul_rn(t, k1), q2 = __fmul_rn(t, k2),
+                  q3 = __fmul_rn(t, k3);
+      o[c] = __fadd_rn(a6[c], q0);
+      a6[c] = __fadd_rn(a5[c], q1);
+      a5[c] = __fadd_rn(a4[c], q2);
+      a4[c] = __fadd_rn(a3[c], q3);
+      a3[c] = __fadd_rn(a2[c], q2);
+      a2[c] = __fadd_rn(a1[c], q1);
+      a1[c] = __fadd_rn(0.0f, q0);
+    }
+    const int yo = r - 3;
+    if ((uint32_t)(yo - Y0) < emit_span && writer)
+      __stcs(reinterpret_cast<float4*>(dst + (uint64_t)(uint32_t)yo * row_bytes), make_float4(o[0], o[1], o[2], o[3]));
+  };
+  for (int r = r_begin; r <= r_end; r += 6) {  // chunk heights are multiples of six; steps past r_end emit nothing
+    step(r);
+    step(r + 1);
+    step(r + 2);
+    step(r + 3);
+    step(r + 4);
+    step(r + 5);
+  }
+}
+
 // image_util::hessian_response(img)
 __global__ void __launch_bounds__(256)
 k_hessian_f32(const float* __restrict__ img, float* __restrict__ out, int w, int h) {
@@ -576,12 +667,28 @@ int launch_threshold(const float* resp, const FrameGeom& g, int n_frames, const 
   return 1;
 }
 
-int launch_blur_f32(const float* in, float* tmp, float* out, int w, int h, const float* d_taps,
-                    int radius, cudaStream_t s) {
+// n_frames contiguous f32 images; `taps` are the 2 * radius + 1 host-side taps, `d_taps` their device
+// copy, `tmp` one image of scratch (only the general path uses the last two).
+int launch_blur_f32(const float* in, float* tmp, float* out, int w, int h, int n_frames, const float* taps,
+                    const float* d_taps, int radius, cudaStream_t s) {
+  const bool can_stream = radius == 3 && (w % 4) == 0 && w >= 8 && ((uintptr_t)in % 16) == 0 &&
+                          ((uintptr_t)out % 16) == 0 && (uint64_t)w * 4u * (uint64_t)h < (1ull << 32);
+  if (can_stream) {
+    const int strips = (w + S_COLS - 1) / S_COLS;
+    const int bx = (strips + S_WARPS - 1) / S_WARPS;
+    int chunk_rows = 60;
+    if ((long)bx * ((h + 125) / 126) * n_frames >= 148L * 6 * 4) chunk_rows = 126;
+    dim3 grid(bx, (h + chunk_rows - 1) / chunk_rows, n_frames);
+    k_blur_f32_stream<<<grid, S_WARPS * 32, 0, s>>>(in, out, w, h, chunk_rows, taps[0], taps[1], taps[2], taps[3]);
+    return 1;
+  }
   dim3 grid((w + 255) / 256, h);
-  k_blur_f32_h<<<grid, 256, 0, s>>>(in, tmp, w, h, d_taps, radius);
-  k_blur_f32_v<<<grid, 256, 0, s>>>(tmp, out, w, h, d_taps, radius);
-  return 2;
+  for (int f = 0; f < n_frames; ++f) {
+    const size_t o = (size_t)f * w * h;
+    k_blur_f32_h<<<grid, 256, 0, s>>>(in + o, tmp, w, h, d_taps, radius);
+    k_blur_f32_v<<<grid, 256, 0, s>>>(tmp, out + o, w, h, d_taps, radius);
+  }
+  return 2 * n_frames;
 }
 int launch_hessian_f32(const float* in, float* out, int w, int h, cudaStream_t s) {
   dim3 grid((w + 255) / 256, h);

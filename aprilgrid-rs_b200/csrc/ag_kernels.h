@@ -32,8 +32,8 @@ int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames,
                         int chunk_rows_opt, cudaStream_t s);
 int launch_threshold(const float* resp, const FrameGeom& g, int n_frames, const uint32_t* frame_min,
                      uint32_t* mask, cudaStream_t s);
-int launch_blur_f32(const float* in, float* tmp, float* out, int w, int h, const float* d_taps,
-                    int radius, cudaStream_t s);
+int launch_blur_f32(const float* in, float* tmp, float* out, int w, int h, int n_frames, const float* taps,
+                    const float* d_taps, int radius, cudaStream_t s);
 int launch_hessian_f32(const float* in, float* out, int w, int h, cudaStream_t s);
 int launch_unorm_table(float* out8, float* out16, float* ref8, float* ref16, cudaStream_t s);
 

@@ -17,7 +17,7 @@ Workloads (BASELINE.json configs):
 
 One JSON line on stdout (rank 0).  `value` = device-resident throughput, `e2e` = through
 ag_detect_batch with HOST buffers (H2D + D2H inside the timed region).  The default line also
-carries short runs of dense4k and rig under "extras".
+carries short runs of dense4k, the f32 blur operator alone (benches/bench_blur.rs) and rig under "extras".
 `--impl reference` times the reference's CPU algorithm (the oracle port, all host threads) on
 the first frames of the same device-rendered batch.
 """
@@ -326,6 +326,32 @@ def run_dense4k(pkg, det, torch, n, steps, warmup, stream, seed):
     return {"image": [w, h], "format": "RGB8", "board": "24x13 T36H11", "frames_per_step": n, "steps": steps,
             "frames_per_s": float(n * steps / (ms * 1e-3)), "ms_per_step": ms / steps,
             "tags_per_frame": float(cnt.float().mean()), "status_bits": sorted(set(int(x) for x in st.cpu().tolist()))}
+
+
+# -------------------------------------------------------------------------------------------
+# benches/bench_blur.rs: gaussian_blur_f32(luma_f32, 1.5) alone, f32 -> f32, batched on the device
+# -------------------------------------------------------------------------------------------
+def run_blur_f32(pkg, det, torch, n, steps, stream):
+    w, h = 1280, 1024
+    src = torch.rand((n, h, w), dtype=torch.float32, device="cuda")
+    dst = torch.empty_like(src)
+    for _ in range(3):
+        det.gaussian_blur_f32_device(src.data_ptr(), n, w, h, 1.5, dst.data_ptr(), stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        det.gaussian_blur_f32_device(src.data_ptr(), n, w, h, 1.5, dst.data_ptr(), stream=stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak, peak_src = measured_peaks()
+    gbs = 8.0 * n * w * h / (ms * 1e-3) / 1e9
+    return {"operator": "image_util::gaussian_blur_f32(sigma 1.5), f32 -> f32 (benches/bench_blur.rs)",
+            "image": [w, h], "frames_per_step": n, "steps": steps, "ms_per_step": ms,
+            "frames_per_s": float(n / (ms * 1e-3)), "algorithmic_bytes_per_px": 8,
+            "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak, "peak_source": peak_src,
+            "l2": "input + output (2.7 GB per step) larger than L2"}
 
 
 def main():
@@ -717,6 +743,10 @@ def main():
             extras["dense4k"] = run_dense4k(pkg, det, torch, 256, 3, 1, stream, SEED)
         except Exception as ex:  # never lose the headline line over an extra
             extras["dense4k"] = {"error": repr(ex)}
+        try:
+            extras["blur_f32"] = run_blur_f32(pkg, det, torch, 256, 10, stream)
+        except Exception as ex:
+            extras["blur_f32"] = {"error": repr(ex)}
         try:
             extras["rig"] = run_rig(pkg, det, torch, 200, 10, sp, SEED)
         except Exception as ex:

@@ -183,6 +183,13 @@ AG_API int ag_gaussian_blur_f32(ag_detector* det, const float* img, int width, i
                                 float sigma, float* out);
 AG_API int ag_hessian_response(ag_detector* det, const float* img, int width, int height,
                                float* out);
+/* gaussian_blur_f32 on n_frames contiguous device-resident f32 images (d_out != d_in), enqueued on
+ * `stream` (0 = the default stream); returns when enqueued.  This is the operator
+ * benches/bench_blur.rs:34-46 times (src/image_util.rs:110-206), batched: 8 B/px of traffic.
+ * The scratch image of the general path (radius != 3 or width % 4 != 0) belongs to the handle:
+ * one such call at a time per handle.                                                          */
+AG_API int ag_gaussian_blur_f32_device(ag_detector* det, const float* d_in, int n_frames, int width,
+                                       int height, float sigma, float* d_out, void* stream);
 
 /* Dense front end only (gray -> blur -> Hessian -> min -> threshold mask), device-resident
  * frames, results stay in the detector's workspace.  This is the unit bench.py times for

@@ -19,7 +19,7 @@ def declared_symbols():
 def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for must in ["ag_create", "ag_destroy", "ag_detect", "ag_detect_batch", "ag_detect_batch_device",
-                 "ag_refined_saddle_points", "ag_gaussian_blur_f32", "ag_hessian_response",
+                 "ag_refined_saddle_points", "ag_gaussian_blur_f32", "ag_gaussian_blur_f32_device", "ag_hessian_response",
                  "ag_family_from_str", "ag_stage_blur", "ag_stage_labels", "ag_stage_saddles"]:
         assert must in syms
 
