@@ -174,7 +174,7 @@ AG_D float u8_lane(uint32_t word, int k) {  // byte k of a packed pixel word -> 
 // A lane's 4 raw pixels of one row: 1 (L8), 2 (L16) or 3 (RGB8) 32-bit words.
 template <int FMT>
 struct RawPx {
-  static constexpr int NW = FMT == AG_L8 ? 1 : (FMT == AG_L16 ? 2 : 3);
+  static constexpr int NW = FMT == AG_L8 ? 1 : (FMT == AG_L16 ? 2 : (FMT == kFmtF32 ? 4 : 3));
   uint32_t w[NW];
 };
 template <int FMT>
@@ -184,6 +184,12 @@ AG_D RawPx<FMT> load_raw(const uint8_t* p) {
     const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
     r.w[0] = v.x;
     r.w[RawPx<FMT>::NW - 1] = v.y;
+  } else if (FMT == kFmtF32) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    r.w[0] = v.x;
+    r.w[1 % RawPx<FMT>::NW] = v.y;
+    r.w[2 % RawPx<FMT>::NW] = v.z;
+    r.w[3 % RawPx<FMT>::NW] = v.w;
   } else {
 #pragma unroll
     for (int i = 0; i < RawPx<FMT>::NW; ++i) r.w[i] = __ldg(reinterpret_cast<const uint32_t*>(p) + i);
@@ -195,6 +201,8 @@ template <int FMT>
 AG_D float raw_luma(const RawPx<FMT>& r, int k) {
   if (FMT == AG_L8) {
     return u8_lane(r.w[0], k);
+  } else if (FMT == kFmtF32) {  // a to_luma32f plane handed in as is (ag_detect_planes)
+    return __uint_as_float(r.w[k % RawPx<FMT>::NW]);
   } else if (FMT == AG_L16) {
     return unorm16_to_f32((float)((r.w[(k >> 1) % RawPx<FMT>::NW] >> (16 * (k & 1))) & 0xffffu));
   } else {
@@ -222,7 +230,7 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, int chunk
   const int Y0 = blockIdx.y * chunk_rows, Y1 = min(Y0 + chunk_rows, g.h);
   const int c0 = X0 - 4 + 4 * lane;  // first of this lane's 4 columns (may lie outside the image)
   const int cw = min(max(c0, 0), g.w - 4);  // column of the word actually loaded
-  constexpr int kBpp = FMT == AG_L8 ? 1 : (FMT == AG_L16 ? 2 : 3);
+  constexpr int kBpp = FMT == AG_L8 ? 1 : (FMT == AG_L16 ? 2 : (FMT == kFmtF32 ? 4 : 3));
   // frame bases are block-uniform; what varies per lane and row are 32-bit offsets (the launcher
   // checks that a frame's bytes fit them)
   // The lane's pointers into the frame are held in registers (opaque, or the compiler re-derives
@@ -294,8 +302,10 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, int chunk
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       // ---- horizontal pass (image_util.rs:138-185): val = 0; val += px * k[i], i = 0..6
-      //      (0.0 + x*k0 == x*k0 for x >= 0)
+      //      (0.0 + x*k0 == x*k0 for x >= 0; an f32 plane may hold negative values or -0.0, where
+      //      0.0 + (-0.0) = +0.0, so that instantiation keeps the addition)
       float t = __fmul_rn(p[c], k0);
+      if (FMT == kFmtF32) t = __fadd_rn(0.0f, t);
       t = __fadd_rn(t, __fmul_rn(p[c + 1], k1));
       t = __fadd_rn(t, __fmul_rn(p[c + 2], k2));
       t = __fadd_rn(t, __fmul_rn(p[c + 3], k3));
@@ -311,7 +321,7 @@ k_blur_hessian_stream(const uint8_t* __restrict__ frames, FrameGeom g, int chunk
       a4[c] = __fadd_rn(a3[c], q3);       // tap 3 of row r
       a3[c] = __fadd_rn(a2[c], q2);       // tap 2 of row r + 1
       a2[c] = __fadd_rn(a1[c], q1);       // tap 1 of row r + 2
-      a1[c] = q0;                         // tap 0 of row r + 3 (0.0 + q0)
+      a1[c] = FMT == kFmtF32 ? __fadd_rn(0.0f, q0) : q0;  // tap 0 of row r + 3 (0.0 + q0)
     }
     N.v[0] = __shfl_up_sync(0xffffffffu, N.v[4], 1);
     N.v[5] = __shfl_down_sync(0xffffffffu, N.v[1], 1);
@@ -609,9 +619,9 @@ int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames,
   int launches = 0;
   k_fill_u32<<<(n_frames + 255) / 256, 256, 0, s>>>(frame_min, n_frames, kOrderedFltMax);
   ++launches;
-  const size_t al = g.format == AG_L16 ? 8 : 4;  // alignment of a lane's load
+  const size_t al = g.format == AG_L16 ? 8 : (g.format == kFmtF32 ? 16 : 4);  // alignment of a lane's load
   const bool can_stream = (g.w % 4) == 0 && g.w >= 8 && (g.row_stride % al) == 0 && (g.frame_stride % al) == 0 &&
-                          ((uintptr_t)frames % al) == 0 && variant != 1 && g.format != kFmtF32 &&
+                          ((uintptr_t)frames % al) == 0 && variant != 1 &&
                           (uint64_t)g.row_stride * (uint64_t)g.h < (1ull << 32);  // 32-bit offsets within a frame
   if (can_stream) {
     const int strips = (g.w + S_COLS - 1) / S_COLS;
@@ -634,6 +644,7 @@ int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames,
     switch (g.format) {
       case AG_L8: AG_STREAM(AG_L8); break;
       case AG_L16: AG_STREAM(AG_L16); break;
+      case kFmtF32: AG_STREAM(kFmtF32); break;
       default: AG_STREAM(AG_RGB8); break;
     }
 #undef AG_STREAM

@@ -807,3 +807,9 @@ def test_detect_planes_matches_oracle(detector, oracle):
     got = detector.detect_planes(oracle.to_luma_f32(img8), oracle.to_luma_u8(img8))
     ref = detector.detect(img8)
     assert sorted(got) == sorted(ref) and all(np.array_equal(got[k], ref[k]) for k in ref)
+    # a width that is not a multiple of four takes the tile kernel's f32 instantiation
+    img_odd = synth.render_board_numpy(642, 481, seed=5, tag_px=44.0)
+    f_odd, u_odd = oracle.to_luma_f32(img_odd), oracle.to_luma_u8(img_odd)
+    want_odd = oracle.detect_planes(f_odd, u_odd)
+    assert len(want_odd) == 36
+    assert_tags_match(detector.detect_planes(f_odd, u_odd), want_odd)
