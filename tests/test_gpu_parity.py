@@ -303,12 +303,15 @@ def test_blur_f32_streaming_and_batched(detector, oracle):
     n, h, w = 5, 130, 244
     batch = (rng.random((n, h, w), dtype=np.float32) * 3.0 - 1.0).astype(np.float32)
     d_in = torch.from_numpy(batch).cuda()
+    guard = 4096  # floats of canary on either side of the output: nothing may be written there
     for sigma in (1.5, 2.6):  # streaming kernel / general two-pass path
-        d_out = torch.zeros_like(d_in)
+        buf = torch.full((guard + n * h * w + guard,), 12345.0, dtype=torch.float32, device="cuda")
+        d_out = buf[guard:guard + n * h * w]
         detector.gaussian_blur_f32_device(d_in.data_ptr(), n, w, h, sigma, d_out.data_ptr(),
                                           stream=torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
-        out = d_out.cpu().numpy()
+        assert bool((buf[:guard] == 12345.0).all()) and bool((buf[guard + n * h * w:] == 12345.0).all())
+        out = d_out.cpu().numpy().reshape(n, h, w)
         for i in range(n):
             assert np.array_equal(out[i].view(np.uint32), oracle.gaussian_blur(batch[i], sigma).view(np.uint32)), (i, sigma)
     detector.gaussian_blur_f32_device(0, 0, w, h, 1.5, 0)  # empty batch
