@@ -45,6 +45,7 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   L.off_tag_valid = take(agb::kMaxCodes);
   L.off_tag_by_id = take(sizeof(agb::TagRec) * agb::kMaxCodes);
   L.off_qcache = take(sizeof(unsigned long long) * agb::kQCacheEntries);
+  L.off_gitem = take(sizeof(uint16_t) * N);  // bucket-grid items of frames with more saddles than the on-chip tier
   // ... and per warp of the frame's block
   L.off_warp0 = o;
   size_t w = 0;
@@ -191,6 +192,13 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
     F.g_ny = (g.h + bucket - 1) / bucket;
     F.g_cap_cells = L.grid_cap_cells;
     F.g_cap_items = L.smem_saddles;
+    if (F.n > L.smem_saddles) {
+      // a frame too large for the on-chip tier (the general path): the bucket starts stay in shared
+      // memory, the sorted item list goes to the frame's global workspace -- a radius query still
+      // visits a few buckets instead of every saddle of the frame
+      F.g_item = (uint16_t*)(W + L.off_gitem);
+      F.g_cap_items = L.max_saddles;
+    }
     F.g_inv = 1.0f / (float)bucket;
     F.g_on = 0;
   }

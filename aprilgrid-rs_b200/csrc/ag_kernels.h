@@ -13,7 +13,7 @@ struct BoardWsLayout {
   // global workspace per frame: frame-wide part, then `warps` per-warp parts
   size_t off_pos[3];
   size_t off_best_quads, off_best_touched, off_best_vals;
-  size_t off_seeds, off_remove, off_tag_valid, off_tag_by_id, off_qcache;
+  size_t off_seeds, off_remove, off_tag_valid, off_tag_by_id, off_qcache, off_gitem;
   size_t off_warp0, bytes_per_warp;
   size_t woff_quads, woff_touched, woff_sb_quads, woff_sb_touched, woff_sb_vals, woff_stack;
   size_t bytes_per_frame;
