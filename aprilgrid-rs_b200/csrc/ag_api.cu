@@ -67,8 +67,8 @@ struct BoardSlot {
   int32_t* d_tap_quads = nullptr;
   int* d_tap_nquads = nullptr;
   // [tier]: 0 = 320, 1 = 512, 2 = 1024 saddles on chip in the board kernel
-  BoardWsLayout layout[3]{};        // sized for the largest warps-per-frame (allocation)
-  BoardWsLayout layout_batch[3]{};  // layout used when many frames are in flight
+  BoardWsLayout layout[4]{};        // sized for the largest warps-per-frame (allocation)
+  BoardWsLayout layout_batch[4]{};  // layout used when many frames are in flight
   // host-frame path (ag_detect_batch): staged input of the chunk (K6 samples the tag bits from it,
   // so it lives as long as the slot's board search), device results and pinned result staging
   uint8_t* d_in = nullptr;
@@ -171,7 +171,7 @@ struct ag_detector {
   long board_warps = 0;
   long board_batch_frames = 148;  // automatic mode: launches with at least this many frames use 2 warps per frame
   long label_variant = 0;  // K3: 0 = run-based in shared memory, 1 = pixel list with per-pixel parents
-  long board_saddle_tier = -1;  // -1 automatic, 0 = 512, 1 = 1024 saddles on chip in the board kernel
+  long board_saddle_tier = -1;  // -1 automatic, 0 = 512, 1 = 1024, 2 = 4096 saddles on chip in the board kernel
   bool label_list = true;  // K3 over a compact pixel list (0 = word-oriented version only)
   bool board_timing = false;  // per-frame timing taps of the board kernel (ag_test_board_times)
   bool board_fast = true;  // four-lane group scoring of candidate boards (0 = general path only)
@@ -291,11 +291,13 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
   if ((rc = regrow(det, &B.d_status, (size_t)F))) return rc;
   if ((rc = regrow(det, &B.d_refined, (size_t)F * nsd))) return rc;
   // layouts for both tiers of on-chip saddle capacity (chosen per launch from the image size)
-  for (int tier = 0; tier < 3; ++tier) {
-    const int cap = tier == 0 ? 320 : (tier == 1 ? 512 : 1024);
+  for (int tier = 0; tier < 4; ++tier) {
+    const int cap = tier == 0 ? 320 : (tier == 1 ? 512 : (tier == 2 ? 1024 : 4096));
     B.layout[tier] = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 8, cap);
+    // the batch launch of the 4096 tier only sees frames of more than 1024 saddles (general path):
+    // no grid-ordered positions, two frames per SM instead of one
     B.layout_batch[tier] =
-        make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 2, cap);
+        make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 2, cap, tier != 3);
   }
   if ((rc = regrow(det, &B.d_board_ws, (size_t)F * B.layout[0].bytes_per_frame))) return rc;
   if ((rc = regrow(det, &B.d_tap_quads, (size_t)F * B.layout[0].max_quads * 4))) return rc;
@@ -551,20 +553,29 @@ int run_boards(ag_detector* det, BoardSlot& S, const uint8_t* d_frames, const Fr
   prof_mark(det, -1, s);
   // automatic warps per frame: throughput (2 warps: most frames resident per SM) once a launch can
   // fill the GPU, latency (8 warps share one frame's seeds) for a handful of frames.
-  // On-chip saddle capacity (tier): 512 up to 1.5 Mpx, 1024 above (larger images carry more
-  // saddles); frames beyond the tier take the general path inside the kernel.  A batch is searched
-  // by TWO launches: frames of at most 320 saddles (one board) with the small tier -- 32 KB of
-  // shared memory per frame, seven frames per SM -- and the others with the image's tier; a block
-  // whose frame belongs to the other launch exits at once.
+  // On-chip saddle capacity (tier): 512 up to 1.5 Mpx, 1024 up to 6 Mpx, 4096 above (larger images
+  // carry more saddles); frames beyond the tier keep their saddles in global memory and take the
+  // general path inside the kernel.  A batch is searched by up to THREE launches: frames of at most
+  // 320 saddles (one board) with the small tier -- 32 KB of shared memory per frame, seven frames
+  // per SM --, frames of up to 512 / 1024 saddles with that tier, and (large images only) the rest
+  // with the 4096 tier; a block whose frame belongs to another launch exits at once.
   const int big = det->board_saddle_tier >= 0 ? (int)det->board_saddle_tier + 1
-                                              : ((long long)g.w * g.h > 1572864ll ? 2 : 1);
+                                              : ((long long)g.w * g.h > 6291456ll ? 3 : ((long long)g.w * g.h > 1572864ll ? 2 : 1));
   const bool many = n >= det->board_batch_frames;
   const bool batch = det->board_warps == 0 && many;
-  const int n_launch = (many && det->board_split) ? 2 : 1;
+  const bool split = many && det->board_split;
+  int tiers[3], n_launch = 0;
+  if (split) {
+    tiers[n_launch++] = 0;
+    tiers[n_launch++] = big == 3 ? 2 : big;
+    if (big == 3) tiers[n_launch++] = 3;
+  } else {
+    tiers[n_launch++] = (batch && big == 3) ? 2 : big;  // layout_batch[3] is for frames beyond the throughput path only
+  }
   for (int pass = 0; pass < n_launch; ++pass) {
-    const int tier = (n_launch == 2 && pass == 0) ? 0 : big;
-    const int n_above = (n_launch == 2 && pass == 1) ? S.layout[0].smem_saddles : -1;
-    const int n_upto = (n_launch == 2 && pass == 0) ? S.layout[0].smem_saddles : 0x7fffffff;
+    const int tier = tiers[pass];
+    const int n_above = pass == 0 ? -1 : S.layout[tiers[pass - 1]].smem_saddles;
+    const int n_upto = pass == n_launch - 1 ? 0x7fffffff : S.layout[tier].smem_saddles;
     const BoardWsLayout& BL = batch ? S.layout_batch[tier] : S.layout[tier];
     det->launches += launch_boards_decode(
         d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->d_codes, det->fam.n_codes, det->fam.edge,
@@ -928,7 +939,7 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     if (value < 0 || value > 1) return fail(det, AG_ERR_INVALID, "label_variant must be 0 or 1");
     det->label_variant = value;
   } else if (!strcmp(key, "board_saddle_tier")) {
-    if (value < -1 || value > 1) return fail(det, AG_ERR_INVALID, "board_saddle_tier must be -1, 0 (512) or 1 (1024)");
+    if (value < -1 || value > 2) return fail(det, AG_ERR_INVALID, "board_saddle_tier must be -1, 0 (512), 1 (1024) or 2 (4096)");
     det->board_saddle_tier = value;
   } else if (!strcmp(key, "label_list")) {
     det->label_list = value != 0;

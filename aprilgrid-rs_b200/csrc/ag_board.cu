@@ -19,7 +19,7 @@ constexpr int kMaxBoardWarps = 8;  // warps per frame (one block per frame): 1, 
 
 int g_board_smem_pad = 0;  // experiment: extra dynamic shared memory per block (limits blocks per SM)
 
-BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles) {
+BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles, bool with_gpos) {
   const int kBoardWarps = warps < 1 ? 1 : (warps > kMaxBoardWarps ? kMaxBoardWarps : warps);
   BoardWsLayout L;
   const int N = max_saddles;
@@ -63,9 +63,10 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   L.bytes_per_warp = align_up(w, 64);
   L.bytes_per_frame = align_up(L.off_warp0 + L.bytes_per_warp * kBoardWarps, 256);
   // shared memory of the block: frame-wide part, then one part per warp
-  // tier of the throughput path: 320 (the usual frame: one board, ~270 saddles; seven frames per SM),
-  // 512 or 1024 saddles on chip
-  L.smem_saddles = smem_saddles <= 320 ? 320 : (smem_saddles <= 512 ? 512 : 1024);
+  // tier: 320 (the usual frame: one board, ~270 saddles; seven frames per SM), 512 or 1024 saddles
+  // on chip (the throughput path handles up to 1024), 4096 for large images (general path, saddle
+  // list and bucket grid still on chip)
+  L.smem_saddles = smem_saddles <= 320 ? 320 : (smem_saddles <= 512 ? 512 : (smem_saddles <= 1024 ? 1024 : 4096));
   L.grid_cap_cells = agb::kGridCapCells;  // 1280x1024 at 32 px buckets = 1280 buckets
   size_t sm = 0;
   auto stake = [&](size_t bytes) {
@@ -78,7 +79,10 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   // path derives the addresses of the last two from the first (agb::kGridStartBytes, 8 bytes per
   // saddle of the tier), so the order and the sizes here are part of its contract
   L.sm_gstart = stake(sizeof(uint16_t) * (L.grid_cap_cells + 2));
-  L.sm_gpos = stake(sizeof(float2) * L.smem_saddles);
+  // (a layout without them -- the launch that only ever sees frames beyond the throughput path's
+  // 1024 saddles -- saves 8 bytes per saddle; the kernel then finds the contract broken and
+  // takes the general path, which does not use the grid-ordered positions)
+  L.sm_gpos = stake(with_gpos ? sizeof(float2) * L.smem_saddles : 0);
   L.sm_gitem = stake(sizeof(uint16_t) * L.smem_saddles);
   L.sm_ctl = stake(sizeof(int) * 16);
   // throughput path (ag_board_fast.cuh): per wave slot best score + quad

@@ -24,7 +24,7 @@ struct BoardWsLayout {
   size_t smw_cell, smw_active, smw_small, smw_qlist, smw_qscore, smw_fvec, smw_squeue;
   size_t smem_per_warp, smem_per_block;
 };
-BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles);
+BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles, bool with_gpos = true);
 
 // ag_dense.cu
 int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames, float* blur,
