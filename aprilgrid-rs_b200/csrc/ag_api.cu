@@ -50,6 +50,10 @@ constexpr int kSlots = 2;
 // is multi-buffered, so the board searches of up to kBoardSlots chunks overlap each other and
 // the front end of later chunks, which hides the long tail of the slowest frames of a chunk.
 constexpr int kBoardSlots = 8;
+#ifndef AG_BIG_TIER_WARPS
+#define AG_BIG_TIER_WARPS 2
+#endif
+constexpr int kBigTierBatchWarps = AG_BIG_TIER_WARPS;  // warps per frame of the 4096-tier batch launch
 
 // Board-search side of a chunk: what K4 hands to K6, K6's workspace, its stream and events.
 // A few hundred KB per frame, so many of these can be in flight (see kBoardSlots).
@@ -297,7 +301,7 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
     // the batch launch of the 4096 tier only sees frames of more than 1024 saddles (general path):
     // no grid-ordered positions, two frames per SM instead of one
     B.layout_batch[tier] =
-        make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 2, cap, tier != 3);
+        make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : (tier == 3 ? kBigTierBatchWarps : 2), cap, tier != 3);
   }
   if ((rc = regrow(det, &B.d_board_ws, (size_t)F * B.layout[0].bytes_per_frame))) return rc;
   if ((rc = regrow(det, &B.d_tap_quads, (size_t)F * B.layout[0].max_quads * 4))) return rc;

@@ -84,6 +84,11 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   // takes the general path, which does not use the grid-ordered positions)
   L.sm_gpos = stake(with_gpos ? sizeof(float2) * L.smem_saddles : 0);
   L.sm_gitem = stake(sizeof(uint16_t) * L.smem_saddles);
+  // Large images, general path: the 1408 buckets above would be 128 px wide on a 4K frame (a radius
+  // query then scans two or three rows of a dozen saddles each with two or three of its eight
+  // lanes); 8192 buckets keep them at 32 px -- one or two saddles per row and lane.
+  L.grid_cap_cells_big = L.smem_saddles == 4096 ? 8192 : 0;
+  L.sm_gstart_big = L.grid_cap_cells_big ? stake(sizeof(uint16_t) * (L.grid_cap_cells_big + 2)) : 0;
   L.sm_ctl = stake(sizeof(int) * 16);
   // throughput path (ag_board_fast.cuh): per wave slot best score + quad
   L.sm_wave = stake(32 * (sizeof(uint16_t) + 4 * sizeof(int16_t)));
@@ -184,17 +189,24 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.dec_qlist = (int16_t*)(W + L.off_warp0 + L.woff_sb_quads);  // warp 0's seed-best arrays: free while decoding
   F.dec_qbits = (unsigned long long*)(W + L.off_warp0 + L.woff_sb_vals);
   F.seeds = (int16_t*)(W + L.off_seeds);
-  // bucket grid: 32 px buckets, doubled until the grid fits its shared-memory budget
+  // block-uniform: the whole frame takes the throughput path or the general one
+  F.fast_on = (fast && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles &&
+               L.sm_gpos - L.sm_gstart == (size_t)agb::kGridStartBytes &&
+               L.sm_gitem - L.sm_gpos == sizeof(float2) * (size_t)L.smem_saddles) ? 1 : 0;
+  // bucket grid: 32 px buckets, doubled until the grid fits its shared-memory budget (the general
+  // path of the 4096 tier has a larger budget of its own)
   {
+    const bool big_grid = !F.fast_on && L.grid_cap_cells_big > 0;
+    const int cap_cells = big_grid ? L.grid_cap_cells_big : L.grid_cap_cells;
     int bucket = 32;
-    while (((g.w + bucket - 1) / bucket) * ((g.h + bucket - 1) / bucket) > L.grid_cap_cells) bucket *= 2;
-    F.g_base = use_grid ? (uint16_t*)(smem + L.sm_gstart) : nullptr;
+    while (((g.w + bucket - 1) / bucket) * ((g.h + bucket - 1) / bucket) > cap_cells) bucket *= 2;
+    F.g_base = use_grid ? (uint16_t*)(smem + (big_grid ? L.sm_gstart_big : L.sm_gstart)) : nullptr;
     F.g_start = F.g_base;
     F.g_item = (uint16_t*)(smem + L.sm_gitem);
     F.g_pos = (float2*)(smem + L.sm_gpos);
     F.g_nx = (g.w + bucket - 1) / bucket;
     F.g_ny = (g.h + bucket - 1) / bucket;
-    F.g_cap_cells = L.grid_cap_cells;
+    F.g_cap_cells = cap_cells;
     F.g_cap_items = L.smem_saddles;
     if (F.n > L.smem_saddles) {
       // a frame too large for the on-chip tier (the general path): the bucket starts stay in shared
@@ -252,11 +264,6 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.fx_qcache = (unsigned long long*)(W + L.off_qcache);
   F.fx_wscore = (uint16_t*)(smem + L.sm_wave);
   F.fx_wquad = (int16_t*)(F.fx_wscore + 32);
-  // block-uniform: the whole frame takes the throughput path or the general one
-  F.fast_on = (fast && use_grid && F.n <= agb::kFastMaxSaddles && F.n <= L.smem_saddles &&
-               L.sm_gpos - L.sm_gstart == (size_t)agb::kGridStartBytes &&
-               L.sm_gitem - L.sm_gpos == sizeof(float2) * (size_t)L.smem_saddles) ? 1 : 0;
-
   // init: every warp clears its lattice and activates every saddle; warp 0 clears the tag map
   {
     const int cells = L.lattice * L.lattice;

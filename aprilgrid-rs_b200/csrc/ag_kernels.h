@@ -19,6 +19,9 @@ struct BoardWsLayout {
   size_t bytes_per_frame;
   // shared memory per block (= per frame in flight): frame-wide part, then per-warp parts
   int smem_saddles, grid_cap_cells;
+  // 4096 tier only: a second, finer bucket-start array for the general path (0 = none)
+  size_t sm_gstart_big;
+  int grid_cap_cells_big;
   size_t sm_pos, sm_gstart, sm_gitem, sm_hist, sm_ctl, sm_warp0;
   size_t sm_wave, sm_gpos;
   size_t smw_cell, smw_active, smw_small, smw_qlist, smw_qscore, smw_fvec, smw_squeue;
