@@ -23,10 +23,11 @@ sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], captur
 src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
                          capture_output=True, text=True).stdout
 rows = list(csv.reader(src_csv.splitlines()))
-# several launches of the same kernel may be in the report: keep the first
+# several launches of the same kernel may be in the report: keep the first (or NCU_LINES_LAUNCH = k)
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
-end = starts[1] if len(starts) > 1 else len(rows)
-hdr, data = rows[starts[0] + 1], rows[starts[0] + 2:end]
+k_launch = int(os.environ.get("NCU_LINES_LAUNCH", "0"))
+end = starts[k_launch + 1] if len(starts) > k_launch + 1 else len(rows)
+hdr, data = rows[starts[k_launch] + 1], [r for r in rows[starts[k_launch] + 2:end] if len(r) == len(rows[starts[k_launch] + 1])]
 iS, iA, iI, iT = (hdr.index(k) for k in ("# Samples", "Address", "Instructions Executed", "Thread Instructions Executed"))
 iSrc = hdr.index("Source")
 stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
