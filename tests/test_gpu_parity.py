@@ -403,6 +403,41 @@ def test_saddle_tiers_of_the_board_kernel(pkg, oracle):
                 det.close()
 
 
+def test_4k_batch_takes_every_tier_of_the_board_kernel(pkg, oracle):
+    """A batch of 4K frames in batch mode (three launches of the board kernel): a sparse 6 x 6 board
+    (<= 320 saddles: small tier, throughput path), the 24 x 13 board of configs[3] and a 29 x 20 board
+    of 580 tags (4096 tier: saddle list and 32 px bucket grid on chip, general path).  With the
+    on-chip tier forced down to 1024 the two large frames keep their saddles and grid items in
+    global memory.  Each equals the oracle every time."""
+    frames = [synth.render_board_numpy(3840, 2160, cols=6, rows=6, seed=5, tag_px=110.0, ss=2),
+              synth.render_board_numpy(3840, 2160, cols=24, rows=13, seed=3, tag_px=100.0, ss=2),
+              synth.render_board_numpy(3840, 2160, cols=29, rows=20, seed=9, tag_px=84.0, ss=2)]
+    n_ref = [len(oracle.front_end(f, want_labels=False)["refined"]) for f in frames]
+    assert n_ref[0] <= 320 and 1024 < n_ref[1] <= 4096 and 3500 < n_ref[2] <= 4096, n_ref
+    want = [oracle.detect(f, cap=1024) for f in frames]
+    assert len(want[0]) == 36 and len(want[1]) > 290 and len(want[2]) > 500, [len(w) for w in want]
+    det = pkg.TagDetector(pkg.TagFamily.T36H11)
+    try:
+        det.set_option("board_batch_frames", 1)  # batch mode (2 warps per frame, launches split by tier)
+        tags, status = det.detect_batch(np.stack(frames), cap_per_frame=640, return_status=True)
+        assert not status.any(), status
+        for got, w in zip(tags, want):
+            assert_tags_match(got, w)
+        det.set_option("board_saddle_tier", 1)  # 1024 on chip: the large frames live in global memory
+        tags, status = det.detect_batch(np.stack(frames), cap_per_frame=640, return_status=True)
+        assert not status.any(), status
+        for got, w in zip(tags, want):
+            assert_tags_match(got, w)
+        det.set_option("board_saddle_tier", -1)
+        det.set_option("board_split", 0)  # one launch, one tier for all three
+        tags, status = det.detect_batch(np.stack(frames), cap_per_frame=640, return_status=True)
+        assert not status.any(), status
+        for got, w in zip(tags, want):
+            assert_tags_match(got, w)
+    finally:
+        det.close()
+
+
 def test_4k_rgb_dense_board_through_detect_kornia(pkg, oracle):
     """BASELINE.json configs[3]: 3840 x 2160 RGB8, 24 x 13 tags, through detect / detect_kornia with
     DEFAULT options.  The frame has more refined saddles than a 1280 x 1024 frame's capacity (the
