@@ -374,7 +374,72 @@ AGB_FN int grid_bucket(const Frame& F, float x, float y) {
   by = by < 0 ? 0 : (by >= F.g_ny ? F.g_ny - 1 : by);
   return by * F.g_nx + bx;
 }
+#if AGB_DEVICE
+// The grid built by the whole warp.  Layout: G[0] = 0, G[b + 1] = first entry of bucket b,
+// G[nc + 1] = n, with G = F.g_base; F.g_start = G + 1 afterwards (every warp of the block sets it
+// when it learns that the grid is on).  Order inside a bucket is arbitrary: every query selects by
+// the total order (d2, index).  with_pos: also the grid-ordered positions of the throughput path.
+__device__ __forceinline__ void grid_build_parallel(Frame& F, bool with_pos) {
+  F.g_on = 0;
+  if (!F.g_base) return;
+  const int nc = F.g_nx * F.g_ny;
+  if (F.n > F.g_cap_items || nc > F.g_cap_cells || F.n > 65535) return;
+  F.g_on = 1;
+  uint16_t* G = F.g_base;
+  for (int c = F.lane; c <= nc + 1; c += 32) G[c] = 0;
+  __syncwarp();
+  // counts into G[b + 1]
+  for (int base = 0; base < F.n; base += 32) {
+    const int i = base + F.lane;
+    const int b = i < F.n ? grid_bucket(F, F.sx[i], F.sy[i]) : (0x10000 + F.lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) G[b + 1] = (uint16_t)(G[b + 1] + __popc(peers));
+    __syncwarp();
+  }
+  // inclusive scan of G[1 .. nc]: afterwards G[b + 1] = end of bucket b
+  {
+    const int per = (nc + 31) / 32;
+    const int c0 = 1 + F.lane * per, c1 = min(c0 + per, nc + 1);
+    unsigned sum = 0;
+    for (int c = c0; c < c1; ++c) sum += G[c];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (F.lane >= o) incl += v;
+    }
+    unsigned run = incl - sum;
+    for (int c = c0; c < c1; ++c) {
+      run += G[c];
+      G[c] = (uint16_t)run;
+    }
+  }
+  __syncwarp();
+  // fill from the back of every bucket: G[b + 1] walks down from end(b) to start(b)
+  for (int base = 0; base < F.n; base += 32) {
+    const int i = base + F.lane;
+    const int b = i < F.n ? grid_bucket(F, F.sx[i], F.sy[i]) : (0x10000 + F.lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (i < F.n) {
+      const int rank = __popc(peers & ((1u << F.lane) - 1u));
+      const int e = G[b + 1];
+      F.g_item[e - 1 - rank] = (uint16_t)i;
+      if (with_pos) F.g_pos[e - 1 - rank] = make_float2(F.sx[i], F.sy[i]);
+    }
+    __syncwarp();
+    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) G[b + 1] = (uint16_t)(G[b + 1] - __popc(peers));
+    __syncwarp();
+  }
+  if (F.lane == 0) G[nc + 1] = (uint16_t)F.n;
+  F.g_start = G + 1;
+  __syncwarp();
+}
+#endif
 AGB_NOINLINE void grid_build(Frame& F) {
+#if AGB_DEVICE
+  grid_build_parallel(F, false);  // the general path does not use the grid-ordered positions
+  return;
+#endif
   F.g_on = 0;
   if (!F.g_start) return;
   const int nc = F.g_nx * F.g_ny;
@@ -1032,6 +1097,9 @@ AGB_NOINLINE int find_best_board(Frame& F) {
   AGB_BLOCK_SYNC();
   int seeds_left = F.ctl[0];
   F.g_on = F.ctl[5];  // the grid was (or was not) built by warp 0 for everybody
+#if AGB_DEVICE
+  if (F.g_on) F.g_start = F.g_base + 1;  // layout of grid_build_parallel
+#endif
   int best_score = 0, count = 0;
   bool stop = false;
   while (seeds_left > 0 && count < 30 && !stop) {

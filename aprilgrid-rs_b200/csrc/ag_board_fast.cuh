@@ -53,64 +53,8 @@ constexpr int kDiffCap = 52;        // `diff` / `same` entries of a seed: at mos
 #if AGB_DEVICE
 namespace agb {
 
-// ---- bucket grid, built by the whole warp ------------------------------------------------------
-// Layout: G[0] = 0, G[b + 1] = first entry of bucket b, G[nc + 1] = n; F.g_start = G + 1.
-// Order inside a bucket is arbitrary: every query selects by the total order (d2, index).
-__device__ __noinline__ void grid_build_warp(Frame& F) {
-  F.g_on = 0;
-  if (!F.g_base) return;
-  const int nc = F.g_nx * F.g_ny;
-  if (F.n > F.g_cap_items || nc > F.g_cap_cells || F.n > 65535) return;
-  F.g_on = 1;
-  uint16_t* G = F.g_base;
-  for (int c = F.lane; c <= nc + 1; c += 32) G[c] = 0;
-  __syncwarp();
-  // counts into G[b + 1]
-  for (int base = 0; base < F.n; base += 32) {
-    const int i = base + F.lane;
-    const int b = i < F.n ? grid_bucket(F, F.sx[i], F.sy[i]) : (0x10000 + F.lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, b);
-    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) G[b + 1] = (uint16_t)(G[b + 1] + __popc(peers));
-    __syncwarp();
-  }
-  // inclusive scan of G[1 .. nc]: afterwards G[b + 1] = end of bucket b
-  {
-    const int per = (nc + 31) / 32;
-    const int c0 = 1 + F.lane * per, c1 = min(c0 + per, nc + 1);
-    unsigned sum = 0;
-    for (int c = c0; c < c1; ++c) sum += G[c];
-    unsigned incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (F.lane >= o) incl += v;
-    }
-    unsigned run = incl - sum;
-    for (int c = c0; c < c1; ++c) {
-      run += G[c];
-      G[c] = (uint16_t)run;
-    }
-  }
-  __syncwarp();
-  // fill from the back of every bucket: G[b + 1] walks down from end(b) to start(b)
-  for (int base = 0; base < F.n; base += 32) {
-    const int i = base + F.lane;
-    const int b = i < F.n ? grid_bucket(F, F.sx[i], F.sy[i]) : (0x10000 + F.lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, b);
-    if (i < F.n) {
-      const int rank = __popc(peers & ((1u << F.lane) - 1u));
-      const int e = G[b + 1];
-      F.g_item[e - 1 - rank] = (uint16_t)i;
-      F.g_pos[e - 1 - rank] = make_float2(F.sx[i], F.sy[i]);
-    }
-    __syncwarp();
-    if (i < F.n && (__ffs((int)peers) - 1) == F.lane) G[b + 1] = (uint16_t)(G[b + 1] - __popc(peers));
-    __syncwarp();
-  }
-  if (F.lane == 0) G[nc + 1] = (uint16_t)F.n;
-  F.g_start = G + 1;
-  __syncwarp();
-}
+// ---- bucket grid, built by the whole warp (grid_build_parallel, ag_board_core.h) -------------------
+__device__ __noinline__ void grid_build_warp(Frame& F) { grid_build_parallel(F, true); }
 
 // ---- one neighbour search of try_expand_one per lane, the whole warp in step -----------------------
 // find_closest_potential_saddle_idxs (board.rs:177-234) for the edge a -> b seen from `self`:
