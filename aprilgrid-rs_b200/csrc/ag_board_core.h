@@ -592,11 +592,75 @@ AGB_NOINLINE int nearest1(const Frame& F, float qx, float qy) {
 // The k (<= 64) nearest saddles of a point, ascending, written to F.nn_idx; returns the count.
 // Selection by repeated extraction: each round takes the smallest (d2, idx) strictly greater
 // than the previous pick.
+#if AGB_DEVICE
+// ... restricted to a window of grid buckets around the query, when the grid is on: the selection
+// below over the window's saddles only, accepted when the k-th distance found is strictly smaller
+// than the distance from the query to every side of the window that has buckets beyond it (a
+// saddle in a bucket beyond a side is at least that far away, also after rounding: dx, dx*dx and
+// the sum are monotone), otherwise repeated with a larger window.  Same picks as the full scan.
+__device__ __forceinline__ int nearest_k_window(Frame& F, float qx, float qy, int kk) {
+  const int nx = F.g_nx, ny = F.g_ny;
+  const float bsz = 1.0f / F.g_inv;  // a power of two: bucket edges are exact
+  int cx = (int)floorf(qx * F.g_inv), cy = (int)floorf(qy * F.g_inv);
+  cx = cx < 0 ? 0 : (cx >= nx ? nx - 1 : cx);
+  cy = cy < 0 ? 0 : (cy >= ny ? ny - 1 : cy);
+  // first half-width: the window holds ~2.5 k saddles at the frame's average density
+  int w = 1;
+  while ((long long)(2 * w + 1) * (2 * w + 1) * F.n * 2 < 5ll * kk * nx * ny && w < 64) ++w;
+  for (;;) {
+    const int x0 = cx - w < 0 ? 0 : cx - w, x1 = cx + w >= nx ? nx - 1 : cx + w;
+    const int y0 = cy - w < 0 ? 0 : cy - w, y1 = cy + w >= ny ? ny - 1 : cy + w;
+    const int bw = x1 - x0 + 1;
+    int cnt = 0;
+    float last_d = -1.0f;
+    int last_i = -1;
+    for (int r = 0; r < kk; ++r) {
+      float bd = 3.0e38f;
+      int bi = kNone;
+      // eight bucket rows per pass, four lanes per row
+      for (int rb = y0; rb <= y1; rb += 8) {
+        const int row = rb + (F.lane >> 2);
+        if (row <= y1) {
+          const int b0 = row * nx + x0;
+          const int e1 = F.g_start[b0 + bw];
+          for (int e = F.g_start[b0] + (F.lane & 3); e < e1; e += 4) {
+            const int i = F.g_item[e];
+            const float d = dist2(F, qx, qy, i);
+            if (nn_less(last_d, last_i, d, i) && nn_less(d, i, bd, bi)) { bd = d; bi = i; }
+          }
+        }
+      }
+      warp_argmin(bd, bi);
+      if (bi == kNone) break;
+      if (F.lane == 0) F.nn_idx[cnt] = (int16_t)bi;
+      ++cnt;
+      last_d = bd;
+      last_i = bi;
+    }
+    const bool whole = x0 == 0 && y0 == 0 && x1 == nx - 1 && y1 == ny - 1;
+    if (whole) return cnt;
+    float r_in = 3.0e38f;
+    if (x0 > 0) r_in = fminf(r_in, fsub(qx, (float)x0 * bsz));
+    if (x1 < nx - 1) r_in = fminf(r_in, fsub((float)(x1 + 1) * bsz, qx));
+    if (y0 > 0) r_in = fminf(r_in, fsub(qy, (float)y0 * bsz));
+    if (y1 < ny - 1) r_in = fminf(r_in, fsub((float)(y1 + 1) * bsz, qy));
+    if (cnt == kk && r_in > 0.0f && last_d < fmul(r_in, r_in)) return cnt;
+    w *= 2;
+  }
+}
+#endif
 AGB_NOINLINE int nearest_k(Frame& F, float qx, float qy, int k) {
   int cnt = 0;
   float last_d = -1.0f;
   int last_i = -1;
   const int kk = k < F.n ? k : F.n;
+#if AGB_DEVICE
+  if (F.g_on && kk > 0 && fabsf(qx) < 1.0e9f && fabsf(qy) < 1.0e9f) {  // (false for NaN)
+    cnt = nearest_k_window(F, qx, qy, kk);
+    __syncwarp();
+    return cnt;
+  }
+#endif
   for (int r = 0; r < kk; ++r) {
     float bd = 3.0e38f;
     int bi = kNone;
