@@ -53,7 +53,12 @@ constexpr int kBoardSlots = 8;
 #ifndef AG_BIG_TIER_WARPS
 #define AG_BIG_TIER_WARPS 2
 #endif
-constexpr int kBigTierBatchWarps = AG_BIG_TIER_WARPS;  // warps per frame of the 4096-tier batch launch
+constexpr int kBigTierBatchWarps = AG_BIG_TIER_WARPS;
+#ifndef AG_SINGLE_WARPS
+#define AG_SINGLE_WARPS 16
+#endif
+constexpr int kSingleFrameWarps = AG_SINGLE_WARPS;  // warps per frame when a launch holds only a few frames
+constexpr size_t kMaxBlockSmem = 227 * 1024;       // dynamic shared memory a block may ask for on sm_100  // warps per frame of the 4096-tier batch launch
 
 // Board-search side of a chunk: what K4 hands to K6, K6's workspace, its stream and events.
 // A few hundred KB per frame, so many of these can be in flight (see kBoardSlots).
@@ -297,11 +302,20 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
   // layouts for both tiers of on-chip saddle capacity (chosen per launch from the image size)
   for (int tier = 0; tier < 4; ++tier) {
     const int cap = tier == 0 ? 320 : (tier == 1 ? 512 : (tier == 2 ? 1024 : 4096));
-    B.layout[tier] = make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : 8, cap);
+    // warps per frame: halved until the tier's shared memory fits a block
+    auto fitted = [&](int warps, bool with_gpos) {
+      for (;;) {
+        BoardWsLayout L = make_board_layout(nsd, (int)det->board_lattice, warps, cap, with_gpos);
+        if (L.smem_per_block <= kMaxBlockSmem || warps == 1) return L;
+        warps /= 2;
+      }
+    };
+    // few frames per launch: as many warps per frame as there is room for
+    B.layout[tier] = fitted(det->board_warps ? (int)det->board_warps : kSingleFrameWarps, true);
     // the batch launch of the 4096 tier only sees frames of more than 1024 saddles (general path):
     // no grid-ordered positions, two frames per SM instead of one
     B.layout_batch[tier] =
-        make_board_layout(nsd, (int)det->board_lattice, det->board_warps ? (int)det->board_warps : (tier == 3 ? kBigTierBatchWarps : 2), cap, tier != 3);
+        fitted(det->board_warps ? (int)det->board_warps : (tier == 3 ? kBigTierBatchWarps : 2), tier != 3);
   }
   if ((rc = regrow(det, &B.d_board_ws, (size_t)F * B.layout[0].bytes_per_frame))) return rc;
   if ((rc = regrow(det, &B.d_tap_quads, (size_t)F * B.layout[0].max_quads * 4))) return rc;
@@ -922,8 +936,8 @@ int ag_set_option(ag_detector* det, const char* key, long value) {
     det->board_lattice = value;
 
   } else if (!strcmp(key, "board_warps")) {
-    if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
-      return fail(det, AG_ERR_INVALID, "board_warps must be 0 (auto), 1, 2, 4 or 8");
+    if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+      return fail(det, AG_ERR_INVALID, "board_warps must be 0 (auto), 1, 2, 4, 8 or 16");
     det->board_warps = value;
   } else if (!strcmp(key, "device_async")) {
     det->device_async = value != 0;

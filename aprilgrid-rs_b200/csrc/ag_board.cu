@@ -15,7 +15,10 @@ namespace ag {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-constexpr int kMaxBoardWarps = 8;  // warps per frame (one block per frame): 1, 2, 4 or 8
+#ifndef AG_MAX_BOARD_WARPS
+#define AG_MAX_BOARD_WARPS 16
+#endif
+constexpr int kMaxBoardWarps = AG_MAX_BOARD_WARPS;  // warps per frame (one block per frame): 1, 2, 4, 8 or 16
 
 int g_board_smem_pad = 0;  // experiment: extra dynamic shared memory per block (limits blocks per SM)
 
@@ -89,7 +92,7 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   // lanes); 8192 buckets keep them at 32 px -- one or two saddles per row and lane.
   L.grid_cap_cells_big = L.smem_saddles == 4096 ? 8192 : 0;
   L.sm_gstart_big = L.grid_cap_cells_big ? stake(sizeof(uint16_t) * (L.grid_cap_cells_big + 2)) : 0;
-  L.sm_ctl = stake(sizeof(int) * 16);
+  L.sm_ctl = stake(sizeof(int) * (16 + kMaxBoardWarps));  // 16 control words, then one score per warp
   // throughput path (ag_board_fast.cuh): per wave slot best score + quad
   L.sm_wave = stake(32 * (sizeof(uint16_t) + 4 * sizeof(int16_t)));
   L.sm_warp0 = sm;
@@ -220,7 +223,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   }
   F.hist = (int*)(smem + L.sm_hist);
   F.ctl = (int*)(smem + L.sm_ctl);
-  F.w_score = F.ctl + 8;
+  F.w_score = F.ctl + 16;
   F.nn_idx = (int16_t*)(SW + L.smw_small);
   F.same = F.nn_idx + 64;
   F.diff = F.same + 64;

@@ -381,7 +381,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default 1024; dense 256; dense4k 256)")
     ap.add_argument("--chunk", type=int, default=0, help="override pipeline chunk_frames")
     ap.add_argument("--lattice", type=int, default=0, help="override board_lattice (16/32/64)")
-    ap.add_argument("--board-warps", type=int, default=-1, help="override board_warps (0 auto, 1/2/4/8)")
+    ap.add_argument("--board-warps", type=int, default=-1, help="override board_warps (0 auto, 1/2/4/8/16)")
     ap.add_argument("--sync-calls", action="store_true",
                     help="order every step's results on the stream before the next step starts "
                          "(default: steps stream through the pipeline, one wait at the end)")

@@ -340,8 +340,9 @@ def test_other_families(pkg, oracle):
 
 # ---- board search variants: the four-lane group scoring path vs the general warp-wide path ----
 BOARD_VARIANTS = [dict(board_fast=1, board_warps=1), dict(board_fast=1, board_warps=4),
-                  dict(board_fast=1, board_warps=8), dict(board_fast=0, board_warps=1),
-                  dict(board_fast=0, board_warps=4)]
+                  dict(board_fast=1, board_warps=8), dict(board_fast=1, board_warps=16),
+                  dict(board_fast=0, board_warps=1), dict(board_fast=0, board_warps=4),
+                  dict(board_fast=0, board_warps=16)]
 
 
 @pytest.mark.parametrize("variant", BOARD_VARIANTS, ids=lambda v: "fast%d_w%d" % (v["board_fast"], v["board_warps"]))
@@ -393,7 +394,7 @@ def test_saddle_tiers_of_the_board_kernel(pkg, oracle):
     want = oracle.detect(img)
     assert len(want) >= 100
     for tier in (0, 1):
-        for warps in (2, 8):
+        for warps in (2, 8, 16):
             det = pkg.TagDetector(pkg.TagFamily.T36H11)
             try:
                 det.set_option("board_saddle_tier", tier)
