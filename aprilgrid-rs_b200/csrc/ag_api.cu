@@ -168,10 +168,7 @@ struct ag_detector {
   // stage-tap state
   FrameGeom tap_geom{};
   bool tap_valid = false;
-  // optional per-stage timing (ag_set_option "profile"): CUDA events between the kernels
-  // 0 = auto: the streaming K1 where applicable -- its compact loop inside detect, its six-step
-  // loop in ag_dense_batch_device (no board kernel beside it); 1 = always the generic tile kernel;
-  // 2 / 3 = the streaming K1 with the six-step / the compact loop everywhere
+  // 0 = auto: the streaming K1 where applicable; 1 = always the generic tile kernel
   long dense_variant = 0;
   long k1_chunk_rows = 0;  // 0 = automatic; else the rows per warp of the streaming K1 (6k + 4)
   long board_lattice = 64;  // side of the tag lattice a board may span (16 / 32 / 64)
