@@ -117,7 +117,10 @@ AG_API const char* ag_last_error(const ag_detector* det);
  * area -- they bound memory, not results: see the frame status bits), "profile" (0/1, see ag_stage_times), "device_async"
  * (see ag_detect_batch_device_wait), "host_async" (see ag_detect_batch_wait), "dense_variant" (K1: 0 auto, 1 generic tile kernel),
  * "k1_chunk_rows" (rows per warp of the streaming K1: 0 automatic, else 6k + 4), "board_warps" (warps per frame in the board search:
- * 0 = automatic, 1/2/4/8/16; fewer where a tier's shared memory would not fit), "board_fast" (0 = general board path only), "board_lattice".
+ * 0 = automatic, 1/2/4/8/16; fewer where a tier's shared memory would not fit), "board_fast" (0 = general board path only), "board_lattice", "board_saddle_tier" (saddles kept on chip by the
+ * board kernel: -1 automatic from the image size, 0 / 1 / 2 = 512 / 1024 / 4096), "board_batch_frames" (launches with at
+ * least this many frames use the batch configuration), "board_split", "board_priority" (1 = board streams at the
+ * greatest stream priority; set before the first detect call).
  * Capacities must be set before the first detect call that needs them larger. */
 AG_API int ag_set_option(ag_detector* det, const char* key, long value);
 
