@@ -727,8 +727,8 @@ def main():
                "sharding": sharding, "equal_shards": equal,
                "per_rank": per_rank,
                "h2d_ceiling_gbs_per_rank": h2d_all,
-               "h2d_ceiling_note": "pinned cudaMemcpyAsync of 256 MB x 12, all ranks copying at the same time, "
-                                   "in this run; frames/s ceiling = GB/s / 1.31 MB",
+               "h2d_ceiling_note": "best of 4 passes of 12 pinned 256 MB cudaMemcpyAsync (one and two streams), all "
+                                   "ranks copying at the same time, in this run; frames/s ceiling = GB/s / 1.31 MB",
                "ceiling_frames_per_s": float(sum(ceil_rank)),
                "frac_of_ceiling": e2e_value / max(sum(ceil_rank), 1e-9),
                "pageable": {"value": world * B * pg_steps / max(dt_pg_all), "unit": UNIT, "steps": pg_steps,
