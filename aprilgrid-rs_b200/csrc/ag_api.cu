@@ -156,7 +156,7 @@ struct ag_detector {
   bool device_async = false;  // ag_detect_batch_device returns without ordering the results on the
                               // caller's stream; ag_detect_batch_device_wait does that
   uint64_t launches = 0;
-  long chunk_frames = 512;
+  long chunk_frames = 1024;  // measured on 1280x1024 frames, 1024 per call: 512 -> 102.8 k, 1024 -> 107.6 k frames/s (2048 with larger calls: 112 k)
   long host_chunk_frames = 128;  // chunk of the host-buffer path (ag_detect_batch)
   // per-frame capacities; 0 = automatic (from the image area, see set_caps).  A frame that still
   // overflows them is re-run on its own with grown capacities (host entry points), so they bound
