@@ -78,6 +78,7 @@ struct BoardSlot {
   // [tier]: 0 = 320, 1 = 512, 2 = 1024 saddles on chip in the board kernel
   BoardWsLayout layout[4]{};        // sized for the largest warps-per-frame (allocation)
   BoardWsLayout layout_batch[4]{};  // layout used when many frames are in flight
+  BoardWsLayout layout_split0{};    // ... by the first launch of a split batch: frames of at most 320 saddles only
   // host-frame path (ag_detect_batch): staged input of the chunk (K6 samples the tag bits from it,
   // so it lives as long as the slot's board search), device results and pinned result staging
   uint8_t* d_in = nullptr;
@@ -314,6 +315,7 @@ int ensure_board_slot(ag_detector* det, BoardSlot& B, int frames, bool drain) {
     B.layout_batch[tier] =
         fitted(det->board_warps ? (int)det->board_warps : (tier == 3 ? kBigTierBatchWarps : 2), tier != 3);
   }
+  B.layout_split0 = make_board_layout(nsd, (int)det->board_lattice, B.layout_batch[0].warps, 320, true, 320);
   if ((rc = regrow(det, &B.d_board_ws, (size_t)F * B.layout[0].bytes_per_frame))) return rc;
   if ((rc = regrow(det, &B.d_tap_quads, (size_t)F * B.layout[0].max_quads * 4))) return rc;
   if ((rc = regrow(det, &B.d_tap_nquads, (size_t)F))) return rc;
@@ -591,7 +593,7 @@ int run_boards(ag_detector* det, BoardSlot& S, const uint8_t* d_frames, const Fr
     const int tier = tiers[pass];
     const int n_above = pass == 0 ? -1 : S.layout[tiers[pass - 1]].smem_saddles;
     const int n_upto = pass == n_launch - 1 ? 0x7fffffff : S.layout[tier].smem_saddles;
-    const BoardWsLayout& BL = batch ? S.layout_batch[tier] : S.layout[tier];
+    const BoardWsLayout& BL = batch ? ((split && pass == 0) ? S.layout_split0 : S.layout_batch[tier]) : S.layout[tier];
     det->launches += launch_boards_decode(
         d_frames, g, n, S.d_refined, S.d_nref, S.d_board_ws, BL, det->d_codes, det->fam.n_codes, det->fam.edge,
         det->fam.border, det->fam.hamming, det->params.max_num_of_boards, d_tags, cap, d_ntags,
@@ -1643,6 +1645,21 @@ int ag_render_boards_device(ag_detector* det, void* d_frames, int n_frames, int 
                                           (cudaStream_t)stream);
   }
   AG_CUDA(det, cudaGetLastError());
+  return AG_OK;
+}
+
+// Test hook (not in the public header; needs no GPU): the board kernel's shared-memory / workspace
+// budget for a configuration, so that CPU tests can pin the residency the design counts on
+// (seven 2-warp frames per SM in the 320-saddle tier, every tier within a block's 227 KB).
+// out = {smem_per_block, bytes_per_frame, warps, smem_saddles}.
+AG_API int ag_test_board_layout(int max_saddles, int lattice, int warps, int smem_saddles, int with_gpos,
+                                int active_cap, long long out[4]) {
+  if (!out || max_saddles < 1) return AG_ERR_INVALID;
+  const BoardWsLayout L = make_board_layout(max_saddles, lattice, warps, smem_saddles, with_gpos != 0, active_cap);
+  out[0] = (long long)L.smem_per_block;
+  out[1] = (long long)L.bytes_per_frame;
+  out[2] = L.warps;
+  out[3] = L.smem_saddles;
   return AG_OK;
 }
 

@@ -22,7 +22,8 @@ constexpr int kMaxBoardWarps = AG_MAX_BOARD_WARPS;  // warps per frame (one bloc
 
 int g_board_smem_pad = 0;  // experiment: extra dynamic shared memory per block (limits blocks per SM)
 
-BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles, bool with_gpos) {
+BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles, bool with_gpos,
+                                int active_cap) {
   const int kBoardWarps = warps < 1 ? 1 : (warps > kMaxBoardWarps ? kMaxBoardWarps : warps);
   BoardWsLayout L;
   const int N = max_saddles;
@@ -104,7 +105,9 @@ BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int sme
   };
   // the lattice region doubles as the eight 1 KB group states of the throughput path
   L.smw_cell = swtake(std::max(sizeof(int16_t) * cells, (size_t)agb::kGroupsPerWarp * agb::kGroupBytes));
-  L.smw_active = swtake(sizeof(uint32_t) * ((N + 31) / 32));
+  // a launch that only ever sees frames of at most active_cap saddles needs no larger masks
+  L.active_saddles = active_cap > 0 && active_cap < N ? active_cap : N;
+  L.smw_active = swtake(sizeof(uint32_t) * ((L.active_saddles + 31) / 32));
   L.smw_small = swtake(sizeof(int16_t) * 64 * 4);  // nn_idx, same, diff, samp
   // throughput path: the warp's quad list and enumeration scratch
   L.smw_qlist = swtake(sizeof(int16_t) * 4 * agb::kQListCap);
@@ -246,7 +249,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
   F.tap_n_quads = tap_n_quads ? tap_n_quads + f : nullptr;
   F.tap_cap = tap_cap;
   F.status = 0;
-  F.active_words = (L.max_saddles + 31) / 32;
+  F.active_words = (L.active_saddles + 31) / 32;
   F.tm = timing ? timing + (size_t)f * 32 : nullptr;
   unsigned long long t_start = 0;
   if (F.tm) {
@@ -272,7 +275,7 @@ k_boards_decode(const uint8_t* __restrict__ frames, FrameGeom g, int n_frames,
     const int cells = L.lattice * L.lattice;
     uint32_t* c = (uint32_t*)F.bs.cell;
     for (int i = lane; i < cells / 2; i += 32) c[i] = 0u;
-    for (int i = lane; i < (L.max_saddles + 31) / 32; i += 32) F.bs.active[i] = 0xffffffffu;
+    for (int i = lane; i < (L.active_saddles + 31) / 32; i += 32) F.bs.active[i] = 0xffffffffu;
     if (warp == 0) {
       uint32_t* tv = (uint32_t*)F.tag_valid;
       for (int i = lane; i < agb::kMaxCodes / 4; i += 32) tv[i] = 0;

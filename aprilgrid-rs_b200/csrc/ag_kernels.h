@@ -19,6 +19,7 @@ struct BoardWsLayout {
   size_t bytes_per_frame;
   // shared memory per block (= per frame in flight): frame-wide part, then per-warp parts
   int smem_saddles, grid_cap_cells;
+  int active_saddles;  // saddles the per-warp `active` bit masks cover (max_saddles unless the launch bounds its frames)
   // 4096 tier only: a second, finer bucket-start array for the general path (0 = none)
   size_t sm_gstart_big;
   int grid_cap_cells_big;
@@ -27,7 +28,8 @@ struct BoardWsLayout {
   size_t smw_cell, smw_active, smw_small, smw_qlist, smw_qscore, smw_fvec, smw_squeue;
   size_t smem_per_warp, smem_per_block;
 };
-BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles, bool with_gpos = true);
+BoardWsLayout make_board_layout(int max_saddles, int lattice, int warps, int smem_saddles, bool with_gpos = true,
+                                int active_cap = 0);
 
 // ag_dense.cu
 int launch_blur_hessian(const uint8_t* frames, const FrameGeom& g, int n_frames, float* blur,

@@ -92,3 +92,31 @@ def test_product_does_not_reference_the_oracle():
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in txt and "import oracle" not in txt and "oracle/" not in txt, \
                     os.path.join(dp, f)
+
+
+def test_board_kernel_shared_memory_budget(pkg):
+    """The residency the design counts on: the first launch of a split batch (frames
+    of at most 320 saddles, two warps per frame) fits SEVEN blocks per SM (228 KB per SM, 1 KB
+    reserved per block) for every image size, every single-frame configuration the API may choose
+    fits a block's 227 KB, and the batch launch of the 4096 tier (no grid-ordered positions) fits
+    two blocks per SM."""
+    import ctypes as C
+    lib = pkg.lib()
+
+    def layout(max_saddles, warps, tier, gpos=1, active_cap=0, lattice=64):
+        out = (C.c_longlong * 4)()
+        assert lib.ag_test_board_layout(max_saddles, lattice, warps, tier, gpos, active_cap, out) == 0
+        return [int(v) for v in out]
+
+    sm_bytes, reserve, block_max = 228 * 1024, 1024, 227 * 1024
+    for max_saddles in (2048, 5120, 13056):  # automatic capacities of 1280x1024, 2048x1536, 3840x2160 frames
+        smem, _, warps, tier = layout(max_saddles, 2, 320, active_cap=320)
+        assert warps == 2 and tier == 320
+        assert 7 * (smem + reserve) <= sm_bytes, (max_saddles, smem)
+    for max_saddles in (2048, 5120):
+        for t in (320, 512, 1024):
+            assert layout(max_saddles, 16, t)[0] <= block_max, (max_saddles, t)
+    big = 13056
+    assert 2 * (layout(big, 2, 4096, gpos=0)[0] + reserve) <= sm_bytes
+    assert layout(big, 8, 4096)[0] <= block_max
+    assert layout(big, 16, 4096)[0] > block_max  # the API halves the warps here (ensure_board_slot)
